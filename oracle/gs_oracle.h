@@ -1,0 +1,80 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the reference hot path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker.  The product library
+ * (libgsb200.so) never links, loads or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  Every function below is checked (tests/test_oracle_*.py)
+ * against oracle/_ref/libgsref.so, which is the unmodified reference header compiled
+ * in place from /root/reference (see oracle/Makefile), and against the reference's own
+ * fixtures (labs/lab3/src/OpenCVHW1/main6.cc:192-253) committed under tests/golden/.
+ * Exception: the Poisson stencil (orc_poisson_*) restates Eigen 3.3.3's A^T*A / A^T*b
+ * (un-vendored NuGet dependency, labs/lab8/src/OpenCVHW1/packages.config); it is pinned
+ * against a generic sparse product of the reference's own triplet list
+ * (tests/test_oracle_poisson.py), not against Eigen itself.
+ *
+ * Element type: values are held as double.  The reference instantiates T=int (lab3)
+ * and T=double (lab8/project); every int32 is exact in a double, so one code path
+ * restates both.  Index type is int (reference default, v2 :107,119).
+ */
+#ifndef GS_ORACLE_H
+#define GS_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_matrix {
+    double *values;  /* values_          */
+    int *cols;       /* col_offset_      */
+    int64_t store;   /* values_.size()   */
+    int64_t cap;
+    int *row_begin;  /* row_begin_       */
+    int *row_nnz;    /* row_num_nze_     */
+    int *row_left;   /* row_space_left_  */
+    int n_rows, n_cols;
+} orc_matrix;
+
+orc_matrix *orc_new(void);
+void orc_free(orc_matrix *m);
+
+/* A1: v1 :209-255 / v2 :265-319 */
+int orc_init_from_vector(orc_matrix *m, const int *rows, const int *cols, const double *vals, int64_t n);
+/* A2: v1 :257-272 / v2 :332-347 */
+int orc_init_dense(orc_matrix *m, int n_rows, int n_cols, const double *dense);
+/* A3: v2 :537-620 */
+int orc_import_csr(orc_matrix *m, const double *values, int n_values, const int *row_off, int n_row_off,
+                   const int *col_idx, int n_col_off, const int *nnz_per_row);
+/* A4: v2 :162-178, :627-645 */
+double orc_at(const orc_matrix *m, int row, int col);
+/* A5: v2 :183-247 (defects P1/P2 of SURVEY.md section 0 are NOT reproduced) */
+void orc_insert(orc_matrix *m, double val, int row, int col);
+/* A6: v2 :350-380.  Returns 0; *sweeps = cnt, *last_eps = eps at exit. x has n entries. */
+int orc_gauss_seidel(const orc_matrix *m, const double *b, int64_t n, double epsilon, int max_iteration,
+                     double *x, int *sweeps, double *last_eps);
+/* A7: v2 :382-393 */
+void orc_spmv(const orc_matrix *m, const double *in, double *out);
+/* A8: v2 :45-105 (serial left-to-right order: the reference's PSTL backend is serial without TBB) */
+double orc_l1_dist(const double *a, const double *b, int64_t n);
+double orc_dot(const double *a, const double *b, int64_t n);
+/* N1: v2 :396-434 (conjugateGradient with optional initial guess; x0 may be NULL) */
+int orc_cg(const orc_matrix *m, const double *b, int64_t n, double epsilon, int max_iteration, const double *x0,
+           double *x, int *iters);
+/* N1: v2 :472-535 (Jacobi-PCG, conjugateGradientEigen) */
+int orc_pcg(const orc_matrix *m, const double *b, int64_t n, double epsilon, int max_iteration, double *x,
+            int *iters);
+
+/* A9: project/src/PhotoMontage/PhotoMontage.cpp:541-597 == labs/lab8/src/OpenCVHW1/hw8_pa.cc:911-967.
+ * Closed form of A^T*A for the forward-difference system, compressed CSR, ascending columns. */
+int64_t orc_poisson_nnz(int W, int H);
+void orc_poisson_csr(int W, int H, int *row_off /* W*H+1 */, int *col_idx, double *values);
+/* A^T*b.  gx, gy: H*W float32, row-major, entries with x==W-1 or y==H-1 are never read. */
+void orc_poisson_rhs(int W, int H, const float *gx, const float *gy, double constraint, double *b);
+/* A10: PhotoMontage.cpp:617-626: uchar(clamp(x,0,255)), truncating */
+void orc_writeback_u8(const double *x, int64_t n, unsigned char *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
