@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: Gauss-Seidel throughput (Gnnz/s) and fraction of the HBM roofline
+on the 4096^2 x 3-channel Poisson system (configs[2]), 1/2/4/8 B200.
+
+A "step" is one pass of the hot path over one batch of synthetic input: `--sweeps` Gauss-Seidel sweeps
+(reference cadence: the stop rule is evaluated every sweep) over the reference-faithful full-grid
+matrix with the three colour channels as three right-hand sides sharing one pass over the CSR.
+
+  value     whole-job Gnnz/s = nnz * sweeps * channels * steps / time, inputs resident in HBM
+  e2e       same metric through the reference-facing API with HOST buffers:
+            initializeFromEigenRowMajor(host CSR) + gaussSeidel(host b) -> host x, copies timed
+  roofline  algorithmic bytes (12*nnz + 4*n + 24*k*n per sweep) / device time of the sweep
+            loop (CUDA events on the library stream, gsb_gs_stats.solve_ms) vs MEASURED_PEAKS.json
+  cpu_baseline  oracle/_ref (the unmodified reference header) on the host cores, bounded sample
+
+`--impl reference` times the reference's own CPU gaussSeidel on the same system (bounded sample).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--size", type=int, default=4096, help="image width = height")
+    p.add_argument("--channels", type=int, default=3)
+    p.add_argument("--sweeps", type=int, default=100, help="GS sweeps per step")
+    p.add_argument("--check-every", type=int, default=1)
+    p.add_argument("--kernel", type=int, default=0)
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_per_sweep(nnz, n, k):
+    return 12.0 * nnz + 4.0 * n + 24.0 * k * n
+
+
+def synth_rhs(pkg, wl, W, H, ch):
+    """Gradients of a synthetic two-exposure image -> A^T b on the device path, host result (ch, n)."""
+    img = wl.synth_image(W, H, ch, seed=7)
+    gx, gy = wl.seamless_gradients(img)
+    b = pkg.poisson_rhs(W, H, gx, gy, img[:, 0, 0].astype(np.float64))
+    return np.ascontiguousarray(b.reshape(ch, W * H))
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm (also the cpu_baseline leg of the GPU arm)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(W, H, ch, sweeps, steps, warmup, b_host=None):
+    """The reference's own gaussSeidel (oracle/_ref, else the oracle port) on the W x H Poisson system:
+    `ch` channels run concurrently on `ch` host threads (each sweep is serial by construction,
+    v2 :359-374).  Returns (Gnnz/s, ms_per_step, cores, kind, nnz)."""
+    from oracle import pyoracle
+    pyoracle.build()
+    from coursecomputationalphotography_b200 import workloads as wl
+    ro, ci, va = pyoracle.poisson_csr(W, H)
+    n, nnz = W * H, int(ro[-1])
+    kind = "reference" if pyoracle.ref_available() else "port"
+    if b_host is None:
+        img = wl.synth_image(W, H, ch, seed=7)
+        gx, gy = wl.seamless_gradients(img)
+        b_host = np.stack([pyoracle.poisson_rhs(W, H, gx[c], gy[c], float(img[c, 0, 0])) for c in range(ch)])
+    if kind == "reference":
+        mats = [pyoracle.Ref(2, "f64").import_csr(va, ro[:-1], ci, n) for _ in range(1)]
+        solve = lambda c: mats[0].gauss_seidel(b_host[c], 0.0, sweeps)
+    else:
+        mats = [pyoracle.Oracle().import_csr(va, ro[:-1], ci, n)]
+        solve = lambda c: mats[0].gauss_seidel(b_host[c], 0.0, sweeps)
+    cores = min(ch, os.cpu_count() or 1)
+
+    def step():
+        if cores <= 1:
+            for c in range(ch):
+                solve(c)
+            return
+        ths = [threading.Thread(target=solve, args=(c,)) for c in range(ch)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return nnz * sweeps * ch * steps / dt / 1e9, dt / steps * 1e3, cores, kind, nnz
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W = H = args.size
+    sweeps = 2  # bounded sample: 2 sweeps x channels per step (~0.3 s per sweep per channel at 4096^2)
+    val, ms, cores, kind, nnz = cpu_reference_run(W, H, args.channels, sweeps, args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "gauss_seidel_throughput", "value": val, "unit": "Gnnz/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, args.channels),
+                   "sweeps_per_step": sweeps, "nnz": nnz},
+        "cpu_baseline": {"value": val, "unit": "Gnnz/s", "cores": cores, "kind": kind,
+                         "sample": "%d sweeps x %d channels per step, %d steps, %dx%d" %
+                                   (sweeps, args.channels, args.steps, W, H)},
+        "e2e": {"value": val, "unit": "Gnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import coursecomputationalphotography_b200 as pkg
+    from coursecomputationalphotography_b200 import workloads as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    L = pkg.load()
+    pkg._lib.check(L.gsb_set_device(local), "gsb_set_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from coursecomputationalphotography_b200 import dist_bench
+        return dist_bench.run(args, pkg, wl, dist, rank, world, local)
+
+    W = H = args.size
+    ch = args.channels
+    n = W * H
+    stream = torch.cuda.ExternalStream(L.gsb_stream())
+    sp = pkg.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    nnz = sp._nnz
+    b_host = synth_rhs(pkg, wl, W, H, ch)
+    b_dev = torch.from_numpy(b_host).cuda()
+    x_dev = torch.empty_like(b_dev)
+    opts = pkg.SparseMatrix.options(check_every=args.check_every, kernel=args.kernel)
+    info = sp.analyze()
+    torch.cuda.synchronize()
+
+    def step():
+        return sp.gaussSeidel_dev(b_dev.data_ptr(), x_dev.data_ptr(), ch, 0.0, args.sweeps, opts)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, solve_ms, sweeps_done = 0, 0.0, 0
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = step()
+        launches += st.kernel_launches
+        solve_ms += st.solve_ms
+        sweeps_done += st.sweeps
+    e1.record(stream)
+    torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    assert sweeps_done == args.sweeps * args.steps, "stop rule fired early: %d sweeps" % sweeps_done
+    value = nnz * ch * sweeps_done / (total_ms * 1e-3) / 1e9
+    # residual after the last step (sanity: the sweeps did real work)
+    x_host = x_dev.cpu().numpy()
+    resid = [sp.residual(b_host[c], x_host[c]) for c in range(ch)]
+
+    peak, peak_src = peaks()
+    abytes = algorithmic_bytes_per_sweep(nnz, n, ch)
+    n_phase_launches = sweeps_done * info["n_colors"]
+    per_launch_ms = solve_ms / n_phase_launches
+    achieved = (abytes / info["n_colors"]) / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "gs_phase (one colour phase, %d RHS)" % ch, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": abytes / info["n_colors"], "avg_launch_ms": per_launch_ms,
+                "frac_of_8TBps_nominal": achieved / 8000.0}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("gs_phase_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: reference-facing API, host buffers, copies inside the timed region -------------------
+    e2e = None
+    if not args.no_e2e:
+        # host CSR as Eigen would hand it over (valuePtr / outerIndexPtr / innerIndexPtr): taken from the
+        # device-built matrix, untimed (it stands for the reference's Eigen A^T*A step)
+        va, ci, _, rn, _ = sp.layout()
+        va, ci = va.copy(), ci.copy()
+        ro_in = np.zeros(n, np.int32)
+        ro_in[1:] = np.cumsum(rn[:-1])
+        x_out = None
+        spe = pkg.SparseMatrix(np.float64)
+        t_e2e, steps_e2e = 0.0, max(1, args.e2e_steps)
+        for it in range(steps_e2e + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            spe.initializeFromEigenRowMajor(va, len(va), ro_in, n, ci, n)
+            x_out = spe.gaussSeidel(b_host, 0.0, args.sweeps, opts)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                t_e2e += dt
+        h2d = va.nbytes + ci.nbytes + ro_in.nbytes + b_host.nbytes
+        d2h = x_out.nbytes
+        e2e = {"value": nnz * ch * args.sweeps * steps_e2e / t_e2e / 1e9, "unit": "Gnnz/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / steps_e2e * 1e3,
+               "steps": steps_e2e, "includes": "CSR import (H2D) + ordering analysis + b H2D + sweeps + x D2H",
+               "host_memory": "pageable numpy buffers"}
+        assert np.array_equal(x_out, x_host), "e2e result differs from the resident-input result"
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sw_cpu = 3
+        v, ms, cores, kind, _ = cpu_reference_run(W, H, ch, sw_cpu, 1, 0, b_host)
+        cpu = {"value": v, "unit": "Gnnz/s", "cores": cores, "kind": kind,
+               "sample": "%d sweeps x %d channels (one channel per thread), %dx%d, %.1f s" % (sw_cpu, ch, W, H, ms / 1e3)}
+
+    line = {
+        "metric": "gauss_seidel_throughput", "value": value, "unit": "Gnnz/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, ch),
+                   "n": n, "nnz": int(nnz), "sweeps_per_step": args.sweeps, "ordering": "red-black",
+                   "n_colors": info["n_colors"], "check_every": args.check_every,
+                   "l2": "working set %.2f GB per sweep >> 126 MB L2 (no flush needed)" % (abytes / 1e9),
+                   "sweeps_per_s": sweeps_done / (total_ms * 1e-3), "residual_l2": resid},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

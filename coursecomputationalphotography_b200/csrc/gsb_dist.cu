@@ -1,0 +1,757 @@
+// gsb_dist.cu -- multi-GPU row strips.  One rank per GPU; each rank owns a contiguous
+// block of matrix rows (image rows [y0,y1) of the grid), coloured by GLOBAL pixel parity so strips
+// agree, stored colour-major with the ghost unknowns (the neighbour strips' boundary rows) appended.
+// After every colour phase the values of that colour which a neighbour reads are packed and moved
+// with grouped ncclSend/ncclRecv over NVLink; every checked sweep one ncclAllReduce of the per-RHS
+// L1 update norms keeps the stop decision identical on all ranks.
+//
+// Entries inside a row are ordered by (colour, global column) -- the order the single-GPU solver
+// uses -- so an N-strip solve is bit-identical to the 1-GPU solve of the same system.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2": the copy torch already loaded, else the system
+// one), so libgsb200.so itself has no link dependency on it.
+#include "gsb_internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <new>
+
+// ---------------------------------------------------------------------------------------------
+// NCCL binding
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.handle) return GSB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        gsb_set_error("NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+        return GSB_ERR_NCCL;
+    }
+#define LOAD(field, sym)                                              \
+    *(void **)(&g_nccl.field) = dlsym(h, sym);                        \
+    if (!g_nccl.field) {                                              \
+        gsb_set_error("NCCL symbol %s missing", sym);                 \
+        return GSB_ERR_NCCL;                                          \
+    }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(AllReduce, "ncclAllReduce")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    g_nccl.handle = h;
+    return GSB_OK;
+}
+
+#define GSB_NCCL(call)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess) {                                                                    \
+            gsb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+            return GSB_ERR_NCCL;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// the per-rank handle
+// ---------------------------------------------------------------------------------------------
+struct gsb_dist {
+    int rank = 0, world = 1, device = 0;
+    ncclComm_t comm = nullptr;
+    // local system
+    bool built = false;
+    int64_t row0 = 0, n_global = 0;
+    int n_local = 0, n_ghost = 0, W = 1;
+    int64_t ld = 0; // n_local + n_ghost: leading dimension of xw / bw
+    int64_t nnz_local = 0;
+    int color_start[3] = {0, 0, 0};
+    DevBuf<int> perm, iperm, rp, ci;
+    DevBuf<double> va;
+    // halo: peer 0 = rank-1 (rows above), peer 1 = rank+1 (rows below); second index = colour
+    int need_cnt[2][2] = {{0, 0}, {0, 0}};
+    int ghost_start[2][2] = {{0, 0}, {0, 0}};
+    int send_cnt[2][2] = {{0, 0}, {0, 0}};
+    DevBuf<int> send_idx[2][2];
+    DevBuf<double> sendbuf[2][2];
+    // natural-order copy for the residual
+    DevBuf<int> nat_rp, nat_cg;
+    DevBuf<double> nat_va;
+    // workspaces
+    DevBuf<double> xw, bw, partials;
+    DevBuf<unsigned char> ctl;
+    void *ctl_host = nullptr;
+    int ws_nrhs = 0;
+    int peer_rank(int p) const { return p == 0 ? rank - 1 : rank + 1; }
+    bool has_peer(int p) const { return p == 0 ? rank > 0 : rank < world - 1; }
+};
+
+extern "C" int gsb_dist_unique_id(unsigned char id[GSB_UNIQUE_ID_BYTES]) {
+    if (!id) return GSB_ERR_ARG;
+    GSB_TRY(nccl_load());
+    ncclUniqueId u;
+    GSB_NCCL(g_nccl.GetUniqueId(&u));
+    static_assert(sizeof(u) == GSB_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &u, sizeof(u));
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_init(gsb_dist **out, const unsigned char id[GSB_UNIQUE_ID_BYTES], int rank, int world,
+                             int device) {
+    if (!out || !id || world < 1 || rank < 0 || rank >= world) {
+        gsb_set_error("dist_init: bad argument");
+        return GSB_ERR_ARG;
+    }
+    GSB_TRY(nccl_load());
+    GSB_TRY(gsb_set_device(device));
+    gsb_dist *d = new (std::nothrow) gsb_dist();
+    if (!d) return GSB_ERR_ALLOC;
+    d->rank = rank;
+    d->world = world;
+    d->device = device;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclResult_t r = g_nccl.CommInitRank(&d->comm, world, u, rank);
+    if (r != ncclSuccess) {
+        gsb_set_error("ncclCommInitRank(rank %d of %d) -> %s", rank, world, g_nccl.GetErrorString(r));
+        delete d;
+        return GSB_ERR_NCCL;
+    }
+    *out = d;
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_finalize(gsb_dist *d) {
+    if (!d) return GSB_OK;
+    cudaSetDevice(d->device);
+    cudaStreamSynchronize(gsb_cur_stream());
+    if (d->comm) g_nccl.CommDestroy(d->comm);
+    if (d->ctl_host) cudaFreeHost(d->ctl_host);
+    delete d;
+    return GSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// local build kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int parity_of(int64_t g, int W) { return (int)(((g % W) + (g / W)) & 1); }
+
+__global__ void __launch_bounds__(256) d_minmax_col(const int *__restrict__ cg, int64_t nnz, int *__restrict__ mm) {
+    int lo = INT32_MAX, hi = -1;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * 256) {
+        int c = cg[k];
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_down_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_down_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
+    }
+}
+
+// flags of the ghost columns in the two windows [row0-halo_lo,row0) and [row1,row1+halo_hi), split by colour:
+// flag[(w*2+colour)][j]
+__global__ void __launch_bounds__(256) d_mark_ghosts(const int *__restrict__ cg, int64_t nnz, int64_t row0,
+                                                     int64_t row1, int halo_lo, int halo_hi, int W,
+                                                     int *__restrict__ f_lo0, int *__restrict__ f_lo1,
+                                                     int *__restrict__ f_hi0, int *__restrict__ f_hi1) {
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * 256) {
+        int64_t c = cg[k];
+        if (c < row0) {
+            int j = (int)(c - (row0 - halo_lo));
+            (parity_of(c, W) ? f_lo1 : f_lo0)[j] = 1;
+        } else if (c >= row1) {
+            int j = (int)(c - row1);
+            (parity_of(c, W) ? f_hi1 : f_hi0)[j] = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) d_owned_flag(int64_t row0, int n_local, int W, int *__restrict__ f) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n_local) f[i] = parity_of(row0 + i, W) == 0 ? 1 : 0;
+    if (i == n_local) f[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) d_owned_place(int64_t row0, int n_local, int W, const int *__restrict__ scan0,
+                                                     int n0, int *__restrict__ perm, int *__restrict__ iperm) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_local) return;
+    int s = scan0[i];
+    int p = parity_of(row0 + i, W) == 0 ? s : n0 + (i - s);
+    perm[p] = i;
+    iperm[i] = p;
+}
+
+// window flag scan -> ghost map (local id of window slot j, -1 if not a ghost) and the ordered id list
+__global__ void __launch_bounds__(256) d_ghost_place(const int *__restrict__ scan, int len, int64_t gid0, int base,
+                                                     int *__restrict__ map, int *__restrict__ ids) {
+    int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= len) return;
+    int s = scan[j];
+    if (scan[j + 1] != s) {
+        map[j] = base + s;
+        ids[s] = (int)(gid0 + j);
+    }
+}
+
+__global__ void __launch_bounds__(256) d_perm_len(const int *__restrict__ perm, const int *__restrict__ rp_nat,
+                                                  int n_local, int *__restrict__ len) {
+    int p = blockIdx.x * 256 + threadIdx.x;
+    if (p < n_local) {
+        int o = perm[p];
+        len[p] = rp_nat[o + 1] - rp_nat[o];
+    }
+    if (p == n_local) len[p] = 0;
+}
+
+// copy rows in permuted order, sorting each row by (colour, global column); then map to local ids
+__global__ void __launch_bounds__(128) d_fill_rows(const int *__restrict__ perm, const int *__restrict__ iperm,
+                                                   const int *__restrict__ rp_nat, const int *__restrict__ cg_nat,
+                                                   const double *__restrict__ va_nat, int n_local, int64_t row0,
+                                                   int64_t row1, int halo_lo, int W, const int *__restrict__ map_lo,
+                                                   const int *__restrict__ map_hi, const int *__restrict__ rp,
+                                                   int *__restrict__ ci, double *__restrict__ va,
+                                                   int *__restrict__ bad) {
+    int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= n_local) return;
+    const int o = perm[p];
+    const int src = rp_nat[o], len = rp_nat[o + 1] - src, dst = rp[p];
+    const int my_par = parity_of(row0 + o, W);
+    for (int k = 0; k < len; ++k) { // insertion sort on key (colour, global id); ci temporarily holds global ids
+        int g = cg_nat[src + k];
+        double v = va_nat[src + k];
+        int gp = parity_of(g, W);
+        if (g != row0 + o && gp == my_par) atomicOr(bad, 1); // parity colouring improper for this matrix
+        int q = dst + k;
+        while (q > dst) {
+            int h = ci[q - 1];
+            int hp = parity_of(h, W);
+            if (hp < gp || (hp == gp && h <= g)) break;
+            ci[q] = h;
+            va[q] = va[q - 1];
+            --q;
+        }
+        ci[q] = g;
+        va[q] = v;
+    }
+    for (int k = 0; k < len; ++k) {
+        int64_t g = ci[dst + k];
+        int l;
+        if (g < row0)
+            l = map_lo[(int)(g - (row0 - halo_lo))];
+        else if (g >= row1)
+            l = map_hi[(int)(g - row1)];
+        else
+            l = iperm[(int)(g - row0)];
+        ci[dst + k] = l;
+    }
+}
+
+__global__ void __launch_bounds__(256) d_ids_to_local(const int *__restrict__ ids, int cnt, int64_t row0, int n_local,
+                                                      const int *__restrict__ iperm, int *__restrict__ out,
+                                                      int *__restrict__ bad) {
+    int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= cnt) return;
+    int64_t l = (int64_t)ids[j] - row0;
+    if (l < 0 || l >= n_local) {
+        atomicOr(bad, 2);
+        out[j] = 0;
+    } else {
+        out[j] = iperm[l];
+    }
+}
+
+__global__ void __launch_bounds__(256) d_pack(const double *__restrict__ x, int64_t ld, const int *__restrict__ idx,
+                                              int cnt, int nrhs, double *__restrict__ buf) {
+    int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= cnt) return;
+    int s = idx[j];
+    for (int r = 0; r < nrhs; ++r) buf[(size_t)r * cnt + j] = x[r * ld + s];
+}
+
+__global__ void __launch_bounds__(256) d_gather(const double *__restrict__ src, int64_t src_ld,
+                                                const int *__restrict__ perm, int n_local, int nrhs, int64_t dst_ld,
+                                                double *__restrict__ dst) {
+    int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n_local) return;
+    int o = perm[p];
+    for (int r = 0; r < nrhs; ++r) dst[r * dst_ld + p] = src[r * src_ld + o];
+}
+
+__global__ void __launch_bounds__(256) d_scatter(const double *__restrict__ src, int64_t src_ld,
+                                                 const int *__restrict__ perm, int n_local, int nrhs, int64_t dst_ld,
+                                                 double *__restrict__ dst) {
+    int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n_local) return;
+    int o = perm[p];
+    for (int r = 0; r < nrhs; ++r) dst[r * dst_ld + o] = src[r * src_ld + p];
+}
+
+__global__ void __launch_bounds__(256) d_fill(double *__restrict__ p, int64_t n, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// build from device-resident natural-order local rows (global columns)
+// ---------------------------------------------------------------------------------------------
+static int scan_count(DevBuf<int> &f, int len, cudaStream_t st, int *count) {
+    // f has len+1 entries with f[len] = 0; after the scan f[len] is the count
+    GSB_TRY(gsb_exclusive_scan_i32(f.p, f.p, (int64_t)len + 1, nullptr, st));
+    GSB_CUDA(cudaMemcpyAsync(count, f.p + len, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, int W) {
+    cudaStream_t st = gsb_cur_stream();
+    const int64_t row1 = row0 + n_local;
+    d->row0 = row0;
+    d->n_local = n_local;
+    d->n_global = n_global;
+    d->W = W < 1 ? 1 : W;
+    W = d->W;
+    int nnz = 0;
+    GSB_CUDA(cudaMemcpyAsync(&nnz, d->nat_rp.p + n_local, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    d->nnz_local = nnz;
+
+    // 1. column range -> halo widths
+    DevBuf<int> mm;
+    GSB_TRY(mm.alloc(4));
+    int init[4] = {INT32_MAX, -1, 0, 0};
+    GSB_CUDA(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        d_minmax_col<<<gsb_blocks_for(nnz, 256 * 8, gsb_sm_count() * 8), 256, 0, st>>>(d->nat_cg.p, nnz, mm.p);
+        GSB_KERNEL_CHECK();
+    }
+    int h_mm[2];
+    GSB_CUDA(cudaMemcpyAsync(h_mm, mm.p, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    int halo_lo = 0, halo_hi = 0;
+    if (nnz > 0) {
+        if (h_mm[0] < 0 || h_mm[1] >= n_global) {
+            gsb_set_error("dist: column index out of range [0,%lld)", (long long)n_global);
+            return GSB_ERR_SHAPE;
+        }
+        if (h_mm[0] < row0) halo_lo = (int)(row0 - h_mm[0]);
+        if (h_mm[1] >= row1) halo_hi = (int)(h_mm[1] - (row1 - 1));
+    }
+    if ((halo_lo && d->rank == 0) || (halo_hi && d->rank == d->world - 1)) {
+        gsb_set_error("dist: rank %d of %d references rows outside the partition", d->rank, d->world);
+        return GSB_ERR_SHAPE;
+    }
+
+    // 2./3. ghost flags per window and colour; owned ordering
+    DevBuf<int> f[4], owned;
+    const int flen[4] = {halo_lo, halo_lo, halo_hi, halo_hi};
+    for (int q = 0; q < 4; ++q) {
+        GSB_TRY(f[q].alloc((int64_t)flen[q] + 1));
+        GSB_CUDA(cudaMemsetAsync(f[q].p, 0, sizeof(int) * (size_t)(flen[q] + 1), st));
+    }
+    if (nnz > 0 && (halo_lo || halo_hi)) {
+        d_mark_ghosts<<<gsb_blocks_for(nnz, 256 * 8, gsb_sm_count() * 8), 256, 0, st>>>(
+            d->nat_cg.p, nnz, row0, row1, halo_lo, halo_hi, W, f[0].p, f[1].p, f[2].p, f[3].p);
+        GSB_KERNEL_CHECK();
+    }
+    GSB_TRY(owned.alloc((int64_t)n_local + 1));
+    d_owned_flag<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(row0, n_local, W, owned.p);
+    GSB_KERNEL_CHECK();
+    int n0 = 0;
+    GSB_TRY(scan_count(owned, n_local, st, &n0));
+    GSB_TRY(d->perm.alloc(n_local));
+    GSB_TRY(d->iperm.alloc(n_local));
+    d_owned_place<<<(n_local + 255) / 256, 256, 0, st>>>(row0, n_local, W, owned.p, n0, d->perm.p, d->iperm.p);
+    GSB_KERNEL_CHECK();
+    d->color_start[0] = 0;
+    d->color_start[1] = n0;
+    d->color_start[2] = n_local;
+
+    // 4. ghost numbering: [lo colour0 | lo colour1 | hi colour0 | hi colour1] after the owned rows
+    DevBuf<int> map_lo, map_hi, need_ids[2][2];
+    GSB_TRY(map_lo.alloc(halo_lo));
+    GSB_TRY(map_hi.alloc(halo_hi));
+    GSB_CUDA(cudaMemsetAsync(map_lo.p, 0xff, sizeof(int) * (size_t)(halo_lo > 0 ? halo_lo : 1), st));
+    GSB_CUDA(cudaMemsetAsync(map_hi.p, 0xff, sizeof(int) * (size_t)(halo_hi > 0 ? halo_hi : 1), st));
+    int base = n_local;
+    for (int w = 0; w < 2; ++w)
+        for (int c = 0; c < 2; ++c) {
+            int q = w * 2 + c, len = flen[q], cnt = 0;
+            if (len > 0) GSB_TRY(scan_count(f[q], len, st, &cnt));
+            d->need_cnt[w][c] = cnt;
+            d->ghost_start[w][c] = base;
+            GSB_TRY(need_ids[w][c].alloc(cnt));
+            if (cnt > 0) {
+                d_ghost_place<<<(len + 255) / 256, 256, 0, st>>>(f[q].p, len, w == 0 ? row0 - halo_lo : row1, base,
+                                                                 w == 0 ? map_lo.p : map_hi.p, need_ids[w][c].p);
+                GSB_KERNEL_CHECK();
+            }
+            base += cnt;
+        }
+    d->n_ghost = base - n_local;
+    d->ld = base;
+
+    // 5. colour-major local CSR
+    GSB_TRY(d->rp.alloc((int64_t)n_local + 1));
+    d_perm_len<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(d->perm.p, d->nat_rp.p, n_local, d->rp.p);
+    GSB_KERNEL_CHECK();
+    GSB_TRY(gsb_exclusive_scan_i32(d->rp.p, d->rp.p, (int64_t)n_local + 1, nullptr, st));
+    GSB_TRY(d->ci.alloc(nnz));
+    GSB_TRY(d->va.alloc(nnz));
+    GSB_CUDA(cudaMemsetAsync(mm.p + 2, 0, sizeof(int), st));
+    d_fill_rows<<<(n_local + 127) / 128, 128, 0, st>>>(d->perm.p, d->iperm.p, d->nat_rp.p, d->nat_cg.p, d->nat_va.p,
+                                                      n_local, row0, row1, halo_lo, W, map_lo.p, map_hi.p, d->rp.p,
+                                                      d->ci.p, d->va.p, mm.p + 2);
+    GSB_KERNEL_CHECK();
+    int h_bad = 0;
+    GSB_CUDA(cudaMemcpyAsync(&h_bad, mm.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (h_bad) {
+        gsb_set_error("dist: parity colouring with grid width %d is not proper for this matrix", W);
+        return GSB_ERR_COLORING;
+    }
+
+    // 6. tell the neighbours which of their unknowns this rank reads (counts, then id lists)
+    DevBuf<int> cnt_out, cnt_in;
+    GSB_TRY(cnt_out.alloc(4));
+    GSB_TRY(cnt_in.alloc(4));
+    int h_out[4] = {d->need_cnt[0][0], d->need_cnt[0][1], d->need_cnt[1][0], d->need_cnt[1][1]};
+    GSB_CUDA(cudaMemcpyAsync(cnt_out.p, h_out, sizeof(h_out), cudaMemcpyHostToDevice, st));
+    GSB_CUDA(cudaMemsetAsync(cnt_in.p, 0, 4 * sizeof(int), st));
+    GSB_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < 2; ++p)
+        if (d->has_peer(p)) {
+            GSB_NCCL(g_nccl.Send(cnt_out.p + 2 * p, 2, ncclInt32, d->peer_rank(p), d->comm, st));
+            GSB_NCCL(g_nccl.Recv(cnt_in.p + 2 * p, 2, ncclInt32, d->peer_rank(p), d->comm, st));
+        }
+    GSB_NCCL(g_nccl.GroupEnd());
+    int h_in[4];
+    GSB_CUDA(cudaMemcpyAsync(h_in, cnt_in.p, sizeof(h_in), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    DevBuf<int> req_ids[2][2];
+    for (int p = 0; p < 2; ++p)
+        for (int c = 0; c < 2; ++c) {
+            d->send_cnt[p][c] = d->has_peer(p) ? h_in[2 * p + c] : 0;
+            GSB_TRY(req_ids[p][c].alloc(d->send_cnt[p][c]));
+            GSB_TRY(d->send_idx[p][c].alloc(d->send_cnt[p][c]));
+            GSB_TRY(d->sendbuf[p][c].alloc((int64_t)d->send_cnt[p][c] * GSB_MAX_RHS));
+        }
+    GSB_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < 2; ++p)
+        if (d->has_peer(p))
+            for (int c = 0; c < 2; ++c) {
+                if (d->need_cnt[p][c])
+                    GSB_NCCL(g_nccl.Send(need_ids[p][c].p, d->need_cnt[p][c], ncclInt32, d->peer_rank(p), d->comm, st));
+                if (d->send_cnt[p][c])
+                    GSB_NCCL(g_nccl.Recv(req_ids[p][c].p, d->send_cnt[p][c], ncclInt32, d->peer_rank(p), d->comm, st));
+            }
+    GSB_NCCL(g_nccl.GroupEnd());
+    GSB_CUDA(cudaMemsetAsync(mm.p + 3, 0, sizeof(int), st));
+    for (int p = 0; p < 2; ++p)
+        for (int c = 0; c < 2; ++c)
+            if (d->send_cnt[p][c]) {
+                d_ids_to_local<<<(d->send_cnt[p][c] + 255) / 256, 256, 0, st>>>(req_ids[p][c].p, d->send_cnt[p][c], row0,
+                                                                             n_local, d->iperm.p, d->send_idx[p][c].p,
+                                                                             mm.p + 3);
+                GSB_KERNEL_CHECK();
+            }
+    GSB_CUDA(cudaMemcpyAsync(&h_bad, mm.p + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (h_bad) {
+        gsb_set_error("dist: a neighbour requested rows this rank does not own (strips thinner than the halo?)");
+        return GSB_ERR_SHAPE;
+    }
+    d->ws_nrhs = 0;
+    d->built = true;
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_poisson_strip(gsb_dist *d, int W, int H, int y0, int y1) {
+    if (!d || W < 1 || H < 1 || y0 < 0 || y1 > H || y0 >= y1) {
+        gsb_set_error("dist_poisson_strip: bad argument");
+        return GSB_ERR_ARG;
+    }
+    const int64_t n_global = (int64_t)W * H;
+    if (n_global > INT32_MAX - 1) {
+        gsb_set_error("dist_poisson_strip: %d x %d exceeds the int32 column range", W, H);
+        return GSB_ERR_OVERFLOW;
+    }
+    GSB_TRY(gsb_set_device(d->device));
+    cudaStream_t st = gsb_cur_stream();
+    const int64_t p0 = (int64_t)y0 * W, p1 = (int64_t)y1 * W;
+    const int n_local = (int)(p1 - p0);
+    GSB_TRY(d->nat_rp.alloc((int64_t)n_local + 1));
+    GSB_TRY(gsb_poisson_launch_row_len(W, H, p0, p1, d->nat_rp.p, st));
+    GSB_TRY(gsb_exclusive_scan_i32(d->nat_rp.p, d->nat_rp.p, (int64_t)n_local + 1, nullptr, st));
+    int nnz = 0;
+    GSB_CUDA(cudaMemcpyAsync(&nnz, d->nat_rp.p + n_local, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    GSB_TRY(d->nat_cg.alloc(nnz));
+    GSB_TRY(d->nat_va.alloc(nnz));
+    GSB_TRY(gsb_poisson_launch_fill(W, H, p0, p1, d->nat_rp.p, d->nat_cg.p, d->nat_va.p, st));
+    return dist_build(d, p0, n_local, n_global, W);
+}
+
+extern "C" int gsb_dist_matrix_rows(gsb_dist *d, const double *values, const int *row_off, const int *col_idx,
+                                    int64_t row0, int n_local, int64_t n_global, int grid_width) {
+    if (!d || !row_off || n_local <= 0 || row0 < 0 || row0 + n_local > n_global || grid_width < 1) {
+        gsb_set_error("dist_matrix_rows: bad argument");
+        return GSB_ERR_ARG;
+    }
+    if (n_global > INT32_MAX - 1) return GSB_ERR_OVERFLOW;
+    const int nnz = row_off[n_local] - row_off[0];
+    if (nnz < 0 || (nnz > 0 && (!values || !col_idx))) return GSB_ERR_ARG;
+    GSB_TRY(gsb_set_device(d->device));
+    cudaStream_t st = gsb_cur_stream();
+    GSB_TRY(d->nat_rp.alloc((int64_t)n_local + 1));
+    GSB_TRY(d->nat_cg.alloc(nnz));
+    GSB_TRY(d->nat_va.alloc(nnz));
+    if (row_off[0] != 0) {
+        gsb_set_error("dist_matrix_rows: row_off must start at 0 (offsets are local to the strip)");
+        return GSB_ERR_ARG;
+    }
+    GSB_CUDA(cudaMemcpyAsync(d->nat_rp.p, row_off, sizeof(int) * (size_t)(n_local + 1), cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        GSB_CUDA(cudaMemcpyAsync(d->nat_cg.p, col_idx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        GSB_CUDA(cudaMemcpyAsync(d->nat_va.p, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+    return dist_build(d, row0, n_local, n_global, grid_width);
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve
+// ---------------------------------------------------------------------------------------------
+static int dist_exchange(gsb_dist *d, int c, int nrhs, cudaStream_t st, int64_t *launches) {
+    bool any = false;
+    for (int p = 0; p < 2; ++p) {
+        if (!d->has_peer(p)) continue;
+        if (d->send_cnt[p][c]) {
+            d_pack<<<(d->send_cnt[p][c] + 255) / 256, 256, 0, st>>>(d->xw.p, d->ld, d->send_idx[p][c].p,
+                                                                   d->send_cnt[p][c], nrhs, d->sendbuf[p][c].p);
+            GSB_KERNEL_CHECK();
+            ++*launches;
+        }
+        any = any || d->send_cnt[p][c] || d->need_cnt[p][c];
+    }
+    if (!any) return GSB_OK;
+    GSB_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < 2; ++p) {
+        if (!d->has_peer(p)) continue;
+        const int peer = d->peer_rank(p);
+        for (int r = 0; r < nrhs; ++r) {
+            if (d->send_cnt[p][c])
+                GSB_NCCL(g_nccl.Send(d->sendbuf[p][c].p + (size_t)r * d->send_cnt[p][c], d->send_cnt[p][c], ncclFloat64,
+                                     peer, d->comm, st));
+            if (d->need_cnt[p][c])
+                GSB_NCCL(g_nccl.Recv(d->xw.p + r * d->ld + d->ghost_start[p][c], d->need_cnt[p][c], ncclFloat64, peer,
+                                     d->comm, st));
+        }
+    }
+    GSB_NCCL(g_nccl.GroupEnd());
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int nrhs, double epsilon,
+                                         int max_iteration, const gsb_gs_options *opts_in, double *x_dev,
+                                         gsb_gs_stats *stats) {
+    if (!d || !b_dev || !x_dev || nrhs < 1 || nrhs > GSB_MAX_RHS) return GSB_ERR_ARG;
+    if (!d->built) {
+        gsb_set_error("dist_gauss_seidel: no matrix on this rank yet");
+        return GSB_ERR_STATE;
+    }
+    GSB_TRY(gsb_set_device(d->device));
+    cudaStream_t st = gsb_cur_stream();
+    gsb_gs_options opts;
+    gsb_gs_default_options(&opts);
+    if (opts_in) opts = *opts_in;
+    if (opts.check_every < 1) opts.check_every = 1;
+    const int n_local = d->n_local;
+    const int64_t ld = d->ld;
+    const int nb0 = gsb_phase_blocks(d->color_start[1] - d->color_start[0]);
+    const int nb1 = gsb_phase_blocks(d->color_start[2] - d->color_start[1]);
+    if (d->ws_nrhs < nrhs) {
+        GSB_TRY(d->xw.alloc(ld * nrhs));
+        GSB_TRY(d->bw.alloc(ld * nrhs));
+        GSB_TRY(d->partials.alloc((int64_t)(nb0 + nb1 + 1) * GSB_MAX_RHS));
+        d->ws_nrhs = nrhs;
+    }
+    if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));
+    if (!d->ctl_host) GSB_CUDA(cudaHostAlloc(&d->ctl_host, sizeof(GsCtl), cudaHostAllocDefault));
+    GsCtl *ctl = (GsCtl *)d->ctl.p;
+    GsCtl *hp = (GsCtl *)d->ctl_host;
+
+    int64_t launches = 0;
+    d_gather<<<(n_local + 255) / 256, 256, 0, st>>>(b_dev, n_local, d->perm.p, n_local, nrhs, ld, d->bw.p);
+    GSB_KERNEL_CHECK();
+    d_fill<<<gsb_blocks_for(ld * nrhs, 256 * 4, gsb_sm_count() * 16), 256, 0, st>>>(d->xw.p, ld * nrhs, 1.0);
+    GSB_KERNEL_CHECK();
+    launches += 2;
+    GsCtl h;
+    memset(&h, 0, sizeof(h));
+    h.max_iter = max_iteration;
+    h.check_every = opts.check_every;
+    h.epsilon = epsilon;
+    for (int r = 0; r < GSB_MAX_RHS; ++r) h.eps_last[r] = 10.0;
+    h.done = !(10.0 > epsilon && 0 < max_iteration) ? 1 : 0;
+    *hp = h;
+    GSB_CUDA(cudaMemcpyAsync(ctl, hp, sizeof(GsCtl), cudaMemcpyHostToDevice, st));
+
+    int batch = opts.batch_sweeps;
+    if (batch <= 0) {
+        double bytes = 12.0 * (double)d->nnz_local + (4.0 + 24.0 * nrhs) * (double)n_local;
+        double est_ms = bytes / 3.0e9 + 0.05;
+        batch = (int)(4.0 / est_ms);
+        if (batch < 4) batch = 4;
+        if (batch > 128) batch = 128;
+    }
+    cudaEvent_t ev0, ev1;
+    GSB_CUDA(cudaEventCreate(&ev0));
+    GSB_CUDA(cudaEventCreate(&ev1));
+    GSB_CUDA(cudaEventRecord(ev0, st));
+    int issued = 0, status = GSB_OK;
+    while (!h.done && status == GSB_OK) {
+        int todo = max_iteration - issued;
+        if (todo > batch) todo = batch;
+        if (todo <= 0) todo = 1;
+        for (int s = 0; s < todo && status == GSB_OK; ++s) {
+            const int sweep_no = issued + s + 1;
+            const bool check = (sweep_no % opts.check_every) == 0 || sweep_no == max_iteration;
+            int poff = 0;
+            for (int c = 0; c < 2 && status == GSB_OK; ++c) {
+                const int r0 = d->color_start[c], r1 = d->color_start[c + 1];
+                if (r1 > r0) {
+                    status = gsb_launch_phase(d->rp.p, d->ci.p, d->va.p, d->bw.p, d->xw.p, ld, r0, r1, nrhs, check,
+                                              opts.kernel, ctl, d->partials.p + (size_t)poff * nrhs, st);
+                    poff += gsb_phase_blocks(r1 - r0);
+                    ++launches;
+                }
+                if (status == GSB_OK) status = dist_exchange(d, c, nrhs, st, &launches);
+            }
+            if (status != GSB_OK) break;
+            if (check) {
+                status = gsb_launch_end_sweep(ctl, d->partials.p, poff, nrhs, 1, 1, st);
+                if (status == GSB_OK && d->world > 1) {
+                    ncclResult_t r = g_nccl.AllReduce(ctl->eps_last, ctl->eps_last, nrhs, ncclFloat64, ncclSum, d->comm, st);
+                    if (r != ncclSuccess) {
+                        gsb_set_error("ncclAllReduce -> %s", g_nccl.GetErrorString(r));
+                        status = GSB_ERR_NCCL;
+                    }
+                }
+                if (status == GSB_OK) status = gsb_launch_end_sweep(ctl, d->partials.p, 0, nrhs, 1, 2, st);
+                launches += 2;
+            } else {
+                status = gsb_launch_end_sweep(ctl, d->partials.p, 0, nrhs, 0, 2, st);
+                ++launches;
+            }
+        }
+        issued += todo;
+        if (status != GSB_OK) break;
+        cudaError_t ce = cudaMemcpyAsync(hp, ctl, sizeof(GsCtl), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+            gsb_set_error("dist sweep batch failed: %s", cudaGetErrorString(ce));
+            status = GSB_ERR_CUDA;
+            break;
+        }
+        h = *hp;
+    }
+    cudaEventRecord(ev1, st);
+    cudaEventSynchronize(ev1);
+    float solve_ms = 0.f;
+    cudaEventElapsedTime(&solve_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (status != GSB_OK) return status;
+    d_scatter<<<(n_local + 255) / 256, 256, 0, st>>>(d->xw.p, ld, d->perm.p, n_local, nrhs, n_local, x_dev);
+    GSB_KERNEL_CHECK();
+    ++launches;
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->sweeps = h.sweeps;
+        stats->n_colors = 2;
+        stats->ordering_used = GSB_ORDER_REDBLACK;
+        stats->kernel_used = 1;
+        stats->kernel_launches = launches;
+        for (int r = 0; r < nrhs; ++r) stats->last_eps[r] = h.eps_last[r];
+        stats->solve_ms = solve_ms;
+    }
+    return GSB_OK;
+}
+
+// ||b - A x||_2 over all strips: x's ghost values are fetched from the neighbours first
+__global__ void __launch_bounds__(256) d_resid(const int *__restrict__ rp, const int *__restrict__ ci,
+                                               const double *__restrict__ va, const double *__restrict__ b,
+                                               const double *__restrict__ x, int n_local, double *__restrict__ acc) {
+    double s2 = 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_local; i += gridDim.x * 256) {
+        double s = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) s += va[k] * x[ci[k]];
+        double r = b[i] - s;
+        s2 += r * r;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s2 += __shfl_down_sync(0xffffffffu, s2, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s2);
+}
+
+extern "C" int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const double *x_dev, double *out) {
+    if (!d || !b_dev || !x_dev || !out) return GSB_ERR_ARG;
+    if (!d->built) return GSB_ERR_STATE;
+    GSB_TRY(gsb_set_device(d->device));
+    cudaStream_t st = gsb_cur_stream();
+    const int n_local = d->n_local;
+    const int64_t ld = d->ld;
+    if (d->ws_nrhs < 1) {
+        GSB_TRY(d->xw.alloc(ld));
+        GSB_TRY(d->bw.alloc(ld));
+        GSB_TRY(d->partials.alloc((int64_t)(gsb_phase_blocks(n_local) + 2) * GSB_MAX_RHS));
+        d->ws_nrhs = 1;
+    }
+    int64_t launches = 0;
+    d_gather<<<(n_local + 255) / 256, 256, 0, st>>>(x_dev, n_local, d->perm.p, n_local, 1, ld, d->xw.p);
+    GSB_KERNEL_CHECK();
+    d_gather<<<(n_local + 255) / 256, 256, 0, st>>>(b_dev, n_local, d->perm.p, n_local, 1, ld, d->bw.p);
+    GSB_KERNEL_CHECK();
+    for (int c = 0; c < 2; ++c) GSB_TRY(dist_exchange(d, c, 1, st, &launches));
+    DevBuf<double> acc;
+    GSB_TRY(acc.alloc(1));
+    GSB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), st));
+    d_resid<<<gsb_blocks_for(n_local, 256, gsb_sm_count() * 8), 256, 0, st>>>(d->rp.p, d->ci.p, d->va.p, d->bw.p,
+                                                                             d->xw.p, n_local, acc.p);
+    GSB_KERNEL_CHECK();
+    if (d->world > 1) GSB_NCCL(g_nccl.AllReduce(acc.p, acc.p, 1, ncclFloat64, ncclSum, d->comm, st));
+    double h = 0.0;
+    GSB_CUDA(cudaMemcpyAsync(&h, acc.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    *out = sqrt(h);
+    return GSB_OK;
+}

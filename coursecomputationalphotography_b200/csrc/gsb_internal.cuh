@@ -1,0 +1,178 @@
+// gsb_internal.cuh -- shared declarations of libgsb200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/gsb200.h"
+
+#define GSB_SM_COUNT_FALLBACK 148
+
+void gsb_set_error(const char *fmt, ...);
+int gsb_current_device();
+cudaStream_t gsb_cur_stream();
+int gsb_sm_count();
+int gsb_ensure_device(); // GSB_OK or GSB_ERR_NO_DEVICE
+
+#define GSB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            gsb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+            return (e_ == cudaErrorMemoryAllocation) ? GSB_ERR_ALLOC : GSB_ERR_CUDA;                \
+        }                                                                                           \
+    } while (0)
+
+#define GSB_TRY(call)                 \
+    do {                              \
+        int s_ = (call);              \
+        if (s_ != GSB_OK) return s_;  \
+    } while (0)
+
+#define GSB_KERNEL_CHECK()                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                        \
+        if (e_ != cudaSuccess) {                                                                    \
+            gsb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_));\
+            return GSB_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+// Device buffer with RAII; freed on the owning device.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    int64_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(int64_t count) {
+        release();
+        if (count <= 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, sizeof(T) * (size_t)count);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            gsb_set_error("cudaMalloc(%lld bytes) -> %s", (long long)(sizeof(T) * (size_t)count),
+                          cudaGetErrorString(e));
+            cudaGetLastError();
+            return GSB_ERR_ALLOC;
+        }
+        n = count;
+        return GSB_OK;
+    }
+    void swap(DevBuf &o) {
+        T *tp = p; p = o.p; o.p = tp;
+        int64_t tn = n; n = o.n; o.n = tn;
+    }
+};
+
+// ---- device-wide primitives (gsb_prims.cu) ---------------------------------------------
+// exclusive prefix sum of int32 -> int32 (out may alias in); *total_dev (optional, device) gets the sum
+int gsb_exclusive_scan_i32(const int *in, int *out, int64_t n, int *total_dev, cudaStream_t st);
+// deterministic sum reduction helpers: result written to out_dev[0]
+int gsb_reduce_max_i32(const int *in, int64_t n, int *out_dev, cudaStream_t st);
+int gsb_l1_dist_dev(const double *a, const double *b, int64_t n, double *out_dev, cudaStream_t st);
+int gsb_dot_dev(const double *a, const double *b, int64_t n, double *out_dev, cudaStream_t st);
+// scratch for the deterministic reductions (per device, grown on demand)
+double *gsb_reduce_scratch(int64_t n_doubles);
+
+static inline int gsb_blocks_for(int64_t n, int threads, int max_blocks = 1 << 30) {
+    int64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+// ---- the matrix handle -------------------------------------------------------------------
+struct gsb_matrix {
+    int vtype = GSB_F64;
+    int device = 0;
+    // reference layout ("slack CSR"), device resident, natural row order.
+    // values are kept in the caller's element type for bit-exact download, plus an FP64 view
+    // for the solvers (same buffer when vtype == GSB_F64).
+    DevBuf<unsigned char> values_raw; // store * elem_size
+    DevBuf<double> values_f64;        // only when vtype == GSB_I32
+    DevBuf<int> cols, row_begin, row_nnz, row_left;
+    int64_t store = 0;
+    int n_rows = 0, n_cols = 0;
+    int64_t nnz = 0; // sum(row_nnz)
+    bool has_layout = false;
+
+    const double *vals() const {
+        return vtype == GSB_F64 ? (const double *)values_raw.p : values_f64.p;
+    }
+
+    // solver format: colour-major compact CSR (gsb_matrix.cu)
+    bool analyzed = false;
+    int ordering_used = 0;
+    int n_colors = 0;
+    int grid_width = 0;
+    int color_start[66];   // row ranges per colour in permuted order
+    DevBuf<int> perm;      // perm[new] = old
+    DevBuf<int> iperm;     // iperm[old] = new
+    DevBuf<int> colors;    // colour[old]
+    DevBuf<int> rp;        // n_rows+1
+    DevBuf<int> ci;        // nnz (permuted column ids, ascending per row)
+    DevBuf<double> va;     // nnz
+    // staged-kernel tiling (gsb_solve.cu)
+    DevBuf<int4> tiles;    // per tile: {row0, nrows, nnz0_aligned, nnz_count_aligned}
+    int tile_rows = 0;
+    int tiles_per_color[66];
+    int tile_start[66];
+    int max_row_nnz = 0;
+
+    // solver workspaces (lazily sized for nrhs)
+    DevBuf<double> xw, bw; // permuted x and b, nrhs * n_rows
+    int ws_nrhs = 0;
+    DevBuf<double> partials;   // per-block partial sums of the stop rule
+    DevBuf<unsigned char> ctl; // GsCtl
+    void *ctl_host = nullptr;  // pinned mirror
+    // cached CUDA graph of one batch
+    void *graph_exec = nullptr;
+    int graph_key[6] = {0, 0, 0, 0, 0, 0};
+
+    void drop_analysis();
+    ~gsb_matrix();
+};
+
+int gsb_matrix_finish_layout(gsb_matrix *m); // compute nnz, f64 view after the five arrays are set
+
+// gsb_assembly.cu: sorted COO (device pointers) -> slack CSR in m
+template <typename T>
+int gsb_assemble_sorted_device(gsb_matrix *m, const int *d_rows, const int *d_cols_in, const T *d_vals_in, int64_t n,
+                               int n_rows, int n_cols_override);
+
+// ---- solver control block + launchers shared by the single-GPU and the strip solver -------
+#define GSB_MAX_RHS 4
+struct GsCtl {
+    int done;
+    int sweeps;
+    int max_iter;
+    int check_every;
+    double epsilon;
+    double eps_last[GSB_MAX_RHS];
+};
+
+// one colour phase over rows [row0,row1) of a colour-major CSR; x and b have leading dimension ld
+int gsb_launch_phase(const int *rp, const int *ci, const double *va, const double *b, double *x, int64_t ld,
+                     int row0, int row1, int nrhs, bool check, int kernel, const GsCtl *ctl, double *partials,
+                     cudaStream_t st);
+int gsb_phase_blocks(int rows);
+// end of sweep.  mode 0: fold partials, bump the counter, decide (single GPU)
+//                mode 1: fold partials into ctl->eps_last only (strip solver, before the all-reduce)
+//                mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
+int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
+                         cudaStream_t st);
+
+// gsb_poisson.cu: rows [p0,p1) of the reference's Poisson matrix (global columns)
+int gsb_poisson_launch_row_len(int W, int H, int64_t p0, int64_t p1, int *len, cudaStream_t st);
+int gsb_poisson_launch_fill(int W, int H, int64_t p0, int64_t p1, const int *rp, int *ci, double *va,
+                            cudaStream_t st);

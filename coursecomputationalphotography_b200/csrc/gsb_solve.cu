@@ -1,0 +1,616 @@
+// gsb_solve.cu -- Gauss-Seidel sweeps, SpMV and the residual on the device.
+//
+// gaussSeidel (v2 :350-380) becomes: x = 1; repeat { for each colour: one phase kernel over the
+// colour's contiguous row range of the colour-major CSR; gs_end_sweep folds the per-block partial
+// L1 sums of the sweep's update in a fixed order, bumps the sweep counter and raises `done` }.
+// The stop decision lives on the device (GsCtl); the host enqueues batches of sweeps and reads
+// one small struct per batch.  After `done` is raised the remaining kernels of the batch return
+// at their first instruction, so the returned iterate is exactly the one the stop rule accepted.
+//
+// Arithmetic: products and sums are rounded separately (__dmul_rn/__dadd_rn, never an FMA) in
+// storage order, as the reference's x64 build does, so a sweep is bit-identical to the
+// reference's sweep over the permuted matrix.
+#include "gsb_internal.cuh"
+
+#include <cooperative_groups.h>
+#include <math.h>
+#include <new>
+
+#define GS_THREADS 256
+#define MAX_RHS GSB_MAX_RHS
+
+// ---------------------------------------------------------------------------------------------
+// block reduction helper (fixed order -> deterministic partials)
+// ---------------------------------------------------------------------------------------------
+template <int NRHS>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NRHS], double *__restrict__ out) {
+    __shared__ double ws[NRHS][GS_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+        double t = v[r];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+        if (lane == 0) ws[r][wid] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NRHS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < GS_THREADS / 32; ++w) s += ws[threadIdx.x][w];
+        out[threadIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1: row-per-thread, direct global loads
+// ---------------------------------------------------------------------------------------------
+template <int NRHS, bool CHECK>
+__global__ void __launch_bounds__(GS_THREADS)
+    gs_phase_direct(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                    const double *__restrict__ b, double *x, int64_t n, int row0, int row1,
+                    const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
+    if (*(volatile const int *)&ctl->done) return;
+    const int i = row0 + blockIdx.x * GS_THREADS + threadIdx.x;
+    double diff[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
+    if (i < row1) {
+        const int k0 = rp[i], k1 = rp[i + 1];
+        double sig[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+        double d = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const int c = ci[k];
+            const double v = va[k];
+            if (c == i) {
+                d = v;
+            } else {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, x[r * n + c]));
+            }
+        }
+        if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                const double xn = __ddiv_rn(__dsub_rn(b[r * n + i], sig[r]), d);
+                if (CHECK) diff[r] = fabs(xn - x[r * n + i]);
+                x[r * n + i] = xn;
+            }
+        }
+    }
+    if (CHECK) block_reduce_store<NRHS>(diff, partials + (size_t)blockIdx.x * NRHS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// end of sweep: fold the partials (fixed order), update the control block
+// ---------------------------------------------------------------------------------------------
+template <int NRHS>
+__global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *__restrict__ partials, int n_partials,
+                                                     int checked, int mode) {
+    if (ctl->done) return;
+    if (mode == 2) { // strip solver, after the all-reduce of eps_last
+        if (threadIdx.x == 0) {
+            bool all_ok = checked != 0;
+            if (checked)
+                for (int r = 0; r < NRHS; ++r)
+                    if (ctl->eps_last[r] > ctl->epsilon) all_ok = false;
+            const int cnt = ctl->sweeps + 1;
+            ctl->sweeps = cnt;
+            if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
+        }
+        return;
+    }
+    __shared__ double ws[NRHS][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (checked) {
+        double s[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += 1024) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) s[r] += partials[(size_t)i * NRHS + r];
+        }
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            double t = s[r];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+            if (lane == 0) ws[r][wid] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool all_ok = checked != 0;
+        if (checked) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                double t = 0.0;
+                for (int w = 0; w < 32; ++w) t += ws[r][w];
+                ctl->eps_last[r] = t;
+                if (t > ctl->epsilon) all_ok = false; // v2 :356: loop continues while eps > epsilon
+            }
+        }
+        if (mode == 1) return; // sums only; the decision follows the all-reduce
+        const int cnt = ctl->sweeps + 1;
+        ctl->sweeps = cnt;
+        if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
+    }
+}
+
+int gsb_phase_blocks(int rows) { return (rows + GS_THREADS - 1) / GS_THREADS; }
+
+template <int NRHS>
+static int launch_phase_t(const int *rp, const int *ci, const double *va, const double *b, double *x, int64_t ld,
+                          int row0, int row1, bool check, int kernel, const GsCtl *ctl, double *partials,
+                          cudaStream_t st) {
+    const int nb = gsb_phase_blocks(row1 - row0);
+    if (nb <= 0) return GSB_OK;
+    (void)kernel;
+    if (check)
+        gs_phase_direct<NRHS, true><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
+    else
+        gs_phase_direct<NRHS, false><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
+    GSB_KERNEL_CHECK();
+    return GSB_OK;
+}
+
+int gsb_launch_phase(const int *rp, const int *ci, const double *va, const double *b, double *x, int64_t ld,
+                     int row0, int row1, int nrhs, bool check, int kernel, const GsCtl *ctl, double *partials,
+                     cudaStream_t st) {
+    switch (nrhs) {
+        case 1: return launch_phase_t<1>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
+        case 2: return launch_phase_t<2>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
+        case 3: return launch_phase_t<3>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
+        case 4: return launch_phase_t<4>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
+    }
+    gsb_set_error("nrhs must be 1..%d", MAX_RHS);
+    return GSB_ERR_ARG;
+}
+
+int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
+                         cudaStream_t st) {
+    switch (nrhs) {
+        case 1: gs_end_sweep<1><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 2: gs_end_sweep<2><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 3: gs_end_sweep<3><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 4: gs_end_sweep<4><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        default: return GSB_ERR_ARG;
+    }
+    GSB_KERNEL_CHECK();
+    return GSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector permutation helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_perm(const double *__restrict__ src, const int *__restrict__ perm,
+                                                   int64_t n, int nrhs, double *__restrict__ dst) {
+    int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    int o = perm[p];
+    for (int r = 0; r < nrhs; ++r) dst[r * n + p] = src[r * n + o];
+}
+
+__global__ void __launch_bounds__(256) scatter_perm(const double *__restrict__ src, const int *__restrict__ perm,
+                                                    int64_t n, int nrhs, double *__restrict__ dst) {
+    int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    int o = perm[p];
+    for (int r = 0; r < nrhs; ++r) dst[r * n + o] = src[r * n + p];
+}
+
+__global__ void __launch_bounds__(256) fill_f64(double *__restrict__ p, int64_t n, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+extern "C" void gsb_gs_default_options(gsb_gs_options *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->ordering = GSB_ORDER_AUTO;
+    o->check_every = 1;
+    o->batch_sweeps = 0;
+    o->use_graph = -1;
+    o->kernel = 0;
+    o->compute_residual = 0;
+}
+
+static int phase_blocks(const gsb_matrix *m, int c) {
+    return gsb_phase_blocks(m->color_start[c + 1] - m->color_start[c]);
+}
+
+static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, int kernel, cudaStream_t st, int64_t *launches) {
+    GsCtl *ctl = (GsCtl *)m->ctl.p;
+    const int64_t n = m->n_rows;
+    int poff = 0;
+    for (int c = 0; c < m->n_colors; ++c) {
+        const int row0 = m->color_start[c], row1 = m->color_start[c + 1];
+        const int nb = phase_blocks(m, c);
+        if (nb == 0) continue;
+        GSB_TRY(gsb_launch_phase(m->rp.p, m->ci.p, m->va.p, m->bw.p, m->xw.p, n, row0, row1, nrhs, check, kernel, ctl,
+                                 m->partials.p + (size_t)poff * nrhs, st));
+        poff += nb;
+        ++*launches;
+    }
+    GSB_TRY(gsb_launch_end_sweep(ctl, m->partials.p, poff, nrhs, check ? 1 : 0, 0, st));
+    ++*launches;
+    return GSB_OK;
+}
+
+static int ensure_workspace(gsb_matrix *m, int nrhs) {
+    const int64_t n = m->n_rows;
+    if (m->ws_nrhs < nrhs) {
+        GSB_TRY(m->xw.alloc(n * nrhs));
+        GSB_TRY(m->bw.alloc(n * nrhs));
+        int total_blocks = 0;
+        for (int c = 0; c < m->n_colors; ++c) total_blocks += phase_blocks(m, c);
+        GSB_TRY(m->partials.alloc((int64_t)(total_blocks + 1) * MAX_RHS));
+        m->ws_nrhs = nrhs;
+        if (m->graph_exec) {
+            cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
+            m->graph_exec = nullptr;
+        }
+    }
+    if (!m->ctl.p) GSB_TRY(m->ctl.alloc(sizeof(GsCtl)));
+    if (!m->ctl_host) GSB_CUDA(cudaHostAlloc(&m->ctl_host, sizeof(GsCtl), cudaHostAllocDefault));
+    return GSB_OK;
+}
+
+// b_dev/x0_dev/x_dev: natural order device vectors (x0_dev may be null -> 1.0)
+static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_dev, int nrhs, double epsilon,
+                           int max_iteration, const gsb_gs_options *opts_in, double *x_dev, gsb_gs_stats *stats) {
+    gsb_gs_options opts;
+    gsb_gs_default_options(&opts);
+    if (opts_in) opts = *opts_in;
+    if (opts.check_every < 1) opts.check_every = 1;
+    cudaStream_t st = gsb_cur_stream();
+    double setup_ms = 0.0;
+    if (!m->analyzed) {
+        cudaEvent_t e0, e1;
+        GSB_CUDA(cudaEventCreate(&e0));
+        GSB_CUDA(cudaEventCreate(&e1));
+        GSB_CUDA(cudaEventRecord(e0, st));
+        int s = gsb_matrix_analyze(m, opts.ordering, nullptr);
+        if (s != GSB_OK) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return s;
+        }
+        GSB_CUDA(cudaEventRecord(e1, st));
+        GSB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        setup_ms = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    const int64_t n = m->n_rows;
+    GSB_TRY(ensure_workspace(m, nrhs));
+    const int nbv = (int)((n + 255) / 256);
+    gather_perm<<<nbv, 256, 0, st>>>(b_dev, m->perm.p, n, nrhs, m->bw.p);
+    GSB_KERNEL_CHECK();
+    if (x0_dev)
+        gather_perm<<<nbv, 256, 0, st>>>(x0_dev, m->perm.p, n, nrhs, m->xw.p);
+    else
+        fill_f64<<<gsb_blocks_for(n * nrhs, 256 * 4, gsb_sm_count() * 16), 256, 0, st>>>(m->xw.p, n * nrhs,
+                                                                                      1.0); // v2 :352
+    GSB_KERNEL_CHECK();
+    int64_t launches = 2;
+
+    GsCtl h;
+    memset(&h, 0, sizeof(h));
+    h.max_iter = max_iteration;
+    h.check_every = opts.check_every;
+    h.epsilon = epsilon;
+    for (int r = 0; r < MAX_RHS; ++r) h.eps_last[r] = 10.0;          // v2 :354
+    h.done = !(10.0 > epsilon && 0 < max_iteration) ? 1 : 0;          // v2 :356
+    GsCtl *hp = (GsCtl *)m->ctl_host;
+    *hp = h;
+    GSB_CUDA(cudaMemcpyAsync(m->ctl.p, hp, sizeof(GsCtl), cudaMemcpyHostToDevice, st));
+
+    int batch = opts.batch_sweeps;
+    if (batch <= 0) {
+        // aim at ~2 ms of sweeps per host round trip, assuming ~3 TB/s effective
+        double bytes = 12.0 * (double)m->nnz + (4.0 + 24.0 * nrhs) * (double)n;
+        double est_ms = bytes / 3.0e9 + 0.004 * (m->n_colors + 1);
+        batch = (int)(2.0 / est_ms);
+        if (batch < 4) batch = 4;
+        if (batch > 256) batch = 256;
+    }
+    bool use_graph = opts.use_graph == 1 || (opts.use_graph == -1 && n * (int64_t)m->n_colors < (int64_t)1 << 20);
+    if (opts.check_every != 1) use_graph = false; // keep the captured batch simple: one sweep shape
+
+    cudaEvent_t ev0, ev1;
+    GSB_CUDA(cudaEventCreate(&ev0));
+    GSB_CUDA(cudaEventCreate(&ev1));
+    GSB_CUDA(cudaEventRecord(ev0, st));
+    int status = GSB_OK;
+    int issued = 0;
+    while (!h.done && status == GSB_OK) {
+        int todo = max_iteration - issued;
+        if (todo > batch) todo = batch;
+        if (todo <= 0) todo = 1; // cannot happen (done would be set) -- guards an endless loop
+        if (use_graph) {
+            int key[6] = {nrhs, batch, 1, 1, m->n_colors, 1};
+            if (!m->graph_exec || memcmp(key, m->graph_key, sizeof(key)) != 0) {
+                if (m->graph_exec) {
+                    cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
+                    m->graph_exec = nullptr;
+                }
+                cudaGraph_t g = nullptr;
+                int64_t dummy = 0;
+                GSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                for (int s = 0; s < batch && status == GSB_OK; ++s) status = enqueue_sweep(m, nrhs, true, opts.kernel, st, &dummy);
+                cudaError_t ce = cudaStreamEndCapture(st, &g);
+                if (status != GSB_OK) break;
+                if (ce != cudaSuccess) {
+                    gsb_set_error("graph capture failed: %s", cudaGetErrorString(ce));
+                    status = GSB_ERR_CUDA;
+                    break;
+                }
+                cudaGraphExec_t ge = nullptr;
+                ce = cudaGraphInstantiate(&ge, g, 0);
+                cudaGraphDestroy(g);
+                if (ce != cudaSuccess) {
+                    gsb_set_error("graph instantiate failed: %s", cudaGetErrorString(ce));
+                    status = GSB_ERR_CUDA;
+                    break;
+                }
+                m->graph_exec = ge;
+                memcpy(m->graph_key, key, sizeof(key));
+            }
+            // the graph always holds `batch` sweeps; max_iter is enforced on the device
+            cudaError_t ce = cudaGraphLaunch((cudaGraphExec_t)m->graph_exec, st);
+            if (ce != cudaSuccess) {
+                gsb_set_error("graph launch failed: %s", cudaGetErrorString(ce));
+                status = GSB_ERR_CUDA;
+                break;
+            }
+            launches += (int64_t)batch * (m->n_colors + 1);
+            issued += batch;
+        } else {
+            for (int s = 0; s < todo && status == GSB_OK; ++s) {
+                bool check = ((issued + s + 1) % opts.check_every) == 0 || (issued + s + 1) == max_iteration;
+                status = enqueue_sweep(m, nrhs, check, opts.kernel, st, &launches);
+            }
+            issued += todo;
+        }
+        if (status != GSB_OK) break;
+        cudaError_t ce = cudaMemcpyAsync(hp, m->ctl.p, sizeof(GsCtl), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+            gsb_set_error("sweep batch failed: %s", cudaGetErrorString(ce));
+            status = GSB_ERR_CUDA;
+            break;
+        }
+        h = *hp;
+    }
+    cudaEventRecord(ev1, st);
+    cudaEventSynchronize(ev1);
+    float solve_ms = 0.f;
+    cudaEventElapsedTime(&solve_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (status != GSB_OK) return status;
+
+    scatter_perm<<<nbv, 256, 0, st>>>(m->xw.p, m->perm.p, n, nrhs, x_dev);
+    GSB_KERNEL_CHECK();
+    ++launches;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->sweeps = h.sweeps;
+        stats->n_colors = m->n_colors;
+        stats->ordering_used = m->ordering_used;
+        stats->kernel_used = 1;
+        stats->kernel_launches = launches;
+        for (int r = 0; r < MAX_RHS; ++r) stats->last_eps[r] = r < nrhs ? h.eps_last[r] : 0.0;
+        stats->solve_ms = solve_ms;
+        stats->setup_ms = setup_ms;
+        if (opts.compute_residual) {
+            for (int r = 0; r < nrhs; ++r)
+                GSB_TRY(gsb_residual_l2_dev(m, b_dev + r * n, x_dev + r * n, &stats->residual_l2[r]));
+        }
+    }
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+static int gs_check_args(gsb_matrix *m, const double *b, int nrhs, double *x) {
+    if (!m || !b || !x || nrhs < 1 || nrhs > MAX_RHS) {
+        gsb_set_error("gauss_seidel: bad argument (nrhs must be 1..%d)", MAX_RHS);
+        return GSB_ERR_ARG;
+    }
+    if (!m->has_layout) {
+        gsb_set_error("gauss_seidel: matrix holds no layout yet");
+        return GSB_ERR_STATE;
+    }
+    if (m->n_rows != m->n_cols) {
+        gsb_set_error("gauss_seidel: matrix must be square (have %d x %d)", m->n_rows, m->n_cols);
+        return GSB_ERR_SHAPE;
+    }
+    return gsb_set_device(m->device);
+}
+
+extern "C" int gsb_gauss_seidel_dev(gsb_matrix *m, const double *b_dev, int nrhs, double epsilon, int max_iteration,
+                                    const gsb_gs_options *opts, double *x_dev, gsb_gs_stats *stats) {
+    GSB_TRY(gs_check_args(m, b_dev, nrhs, x_dev));
+    return gs_solve_device(m, b_dev, nullptr, nrhs, epsilon, max_iteration, opts, x_dev, stats);
+}
+
+static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, double epsilon, int max_iteration,
+                   const gsb_gs_options *opts, double *x_out, gsb_gs_stats *stats) {
+    GSB_TRY(gs_check_args(m, b, nrhs, x_out));
+    cudaStream_t st = gsb_cur_stream();
+    const int64_t n = m->n_rows;
+    DevBuf<double> db, dx;
+    GSB_TRY(db.alloc(n * nrhs));
+    GSB_TRY(dx.alloc(n * nrhs));
+    size_t bytes = sizeof(double) * (size_t)(n * nrhs);
+    GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    const double *x0_dev = nullptr;
+    if (x0) {
+        GSB_CUDA(cudaMemcpyAsync(dx.p, x0, bytes, cudaMemcpyHostToDevice, st));
+        x0_dev = dx.p;
+    }
+    // x0 lives in dx and the result is scattered into dx: gs_solve_device permutes x0 into its
+    // workspace before it writes dx, so the aliasing is safe.
+    GSB_TRY(gs_solve_device(m, db.p, x0_dev, nrhs, epsilon, max_iteration, opts, dx.p, stats));
+    GSB_CUDA(cudaMemcpyAsync(x_out, dx.p, bytes, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+extern "C" int gsb_gauss_seidel(gsb_matrix *m, const double *b, int nrhs, double epsilon, int max_iteration,
+                                const gsb_gs_options *opts, double *x_out, gsb_gs_stats *stats) {
+    return gs_host(m, b, nullptr, nrhs, epsilon, max_iteration, opts, x_out, stats);
+}
+
+extern "C" int gsb_gauss_seidel_x0(gsb_matrix *m, const double *b, const double *x0, int nrhs, double epsilon,
+                                   int max_iteration, const gsb_gs_options *opts, double *x_out,
+                                   gsb_gs_stats *stats) {
+    if (!x0) return GSB_ERR_ARG;
+    return gs_host(m, b, x0, nrhs, epsilon, max_iteration, opts, x_out, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A7: SpMV over the reference layout, storage order, unfused (bit-exact with applyToVector)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spmv_row_thread(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                       const int *__restrict__ row_begin,
+                                                       const int *__restrict__ row_nnz, int n_rows,
+                                                       const double *__restrict__ in, double *__restrict__ out) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rows) return;
+    int k = row_begin[i];
+    const int e = k + row_nnz[i];
+    double s = 0.0;
+    for (; k < e; ++k) s = __dadd_rn(s, __dmul_rn(vals[k], in[cols[k]]));
+    out[i] = s;
+}
+
+// residual partials: (b_i - (A x)_i)^2.  Rows with > 8 entries on average go row-per-warp
+// (lanes stride the row, shuffle reduction); the norm is a diagnostic, not a parity quantity.
+__global__ void __launch_bounds__(256) resid_row_thread(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                        const int *__restrict__ row_begin,
+                                                        const int *__restrict__ row_nnz, int n_rows,
+                                                        const double *__restrict__ b, const double *__restrict__ x,
+                                                        double *__restrict__ partial) {
+    double acc = 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_rows; i += gridDim.x * 256) {
+        int k = row_begin[i];
+        const int e = k + row_nnz[i];
+        double s = 0.0;
+        for (; k < e; ++k) s += vals[k] * x[cols[k]];
+        double r = b[i] - s;
+        acc += r * r;
+    }
+    double a1[1] = {acc};
+    block_reduce_store<1>(a1, partial + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) resid_row_warp(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                      const int *__restrict__ row_begin,
+                                                      const int *__restrict__ row_nnz, int n_rows,
+                                                      const double *__restrict__ b, const double *__restrict__ x,
+                                                      double *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * 256) >> 5;
+    double acc = 0.0;
+    for (int i = warp; i < n_rows; i += nwarps) {
+        const int k0 = row_begin[i], e = k0 + row_nnz[i];
+        double s = 0.0;
+        for (int k = k0 + lane; k < e; k += 32) s += vals[k] * x[cols[k]];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+        if (lane == 0) {
+            double r = b[i] - s;
+            acc += r * r;
+        }
+    }
+    double a1[1] = {acc};
+    block_reduce_store<1>(a1, partial + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) finish_sqrt(const double *__restrict__ partial, int np, double *out) {
+    __shared__ double ws[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += 256) s += partial[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        out[0] = sqrt(t);
+    }
+}
+
+static int spmv_check(gsb_matrix *m, const void *a, const void *b) {
+    if (!m || !a || !b) return GSB_ERR_ARG;
+    if (!m->has_layout) {
+        gsb_set_error("spmv: matrix holds no layout yet");
+        return GSB_ERR_STATE;
+    }
+    return gsb_set_device(m->device);
+}
+
+extern "C" int gsb_spmv_dev(gsb_matrix *m, const double *in_dev, double *out_dev) {
+    GSB_TRY(spmv_check(m, in_dev, out_dev));
+    cudaStream_t st = gsb_cur_stream();
+    spmv_row_thread<<<(m->n_rows + 255) / 256, 256, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p,
+                                                            m->n_rows, in_dev, out_dev);
+    GSB_KERNEL_CHECK();
+    return GSB_OK;
+}
+
+extern "C" int gsb_spmv(gsb_matrix *m, const double *in, double *out) {
+    GSB_TRY(spmv_check(m, in, out));
+    cudaStream_t st = gsb_cur_stream();
+    DevBuf<double> di, dout;
+    GSB_TRY(di.alloc(m->n_cols));
+    GSB_TRY(dout.alloc(m->n_rows));
+    GSB_CUDA(cudaMemcpyAsync(di.p, in, sizeof(double) * (size_t)m->n_cols, cudaMemcpyHostToDevice, st));
+    GSB_TRY(gsb_spmv_dev(m, di.p, dout.p));
+    GSB_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * (size_t)m->n_rows, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+extern "C" int gsb_residual_l2_dev(gsb_matrix *m, const double *b_dev, const double *x_dev, double *out) {
+    GSB_TRY(spmv_check(m, b_dev, x_dev));
+    if (!out) return GSB_ERR_ARG;
+    cudaStream_t st = gsb_cur_stream();
+    const int n = m->n_rows;
+    const bool by_warp = m->nnz > (int64_t)8 * n;
+    int nb = gsb_blocks_for(by_warp ? (int64_t)n * 32 : n, 256, gsb_sm_count() * 8);
+    double *scratch = gsb_reduce_scratch(nb + 1);
+    if (!scratch) return GSB_ERR_ALLOC;
+    if (by_warp)
+        resid_row_warp<<<nb, 256, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, n, b_dev, x_dev, scratch);
+    else
+        resid_row_thread<<<nb, 256, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, n, b_dev, x_dev,
+                                            scratch);
+    GSB_KERNEL_CHECK();
+    finish_sqrt<<<1, 256, 0, st>>>(scratch, nb, scratch + nb);
+    GSB_KERNEL_CHECK();
+    GSB_CUDA(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+extern "C" int gsb_residual_l2(gsb_matrix *m, const double *b, const double *x, double *out) {
+    GSB_TRY(spmv_check(m, b, x));
+    cudaStream_t st = gsb_cur_stream();
+    DevBuf<double> db, dx;
+    GSB_TRY(db.alloc(m->n_rows));
+    GSB_TRY(dx.alloc(m->n_cols));
+    GSB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * (size_t)m->n_rows, cudaMemcpyHostToDevice, st));
+    GSB_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * (size_t)m->n_cols, cudaMemcpyHostToDevice, st));
+    return gsb_residual_l2_dev(m, db.p, dx.p, out);
+}

@@ -1,0 +1,198 @@
+"""Synthetic inputs for the five BASELINE.json configurations, numpy only.
+
+Everything here is input generation: images, gradients as the reference computes them
+(GradientAt, project/src/PhotoMontage/PhotoMontage.cpp:399-408: forward differences of 8-bit
+pixels stored as float32), masks, and CSR systems.  Fixed seeds; the same arrays feed the GPU
+path, the oracle and the compiled reference.
+"""
+import numpy as np
+
+
+# ---- C1: lab3 Gauss-Seidel on a diagonally dominant sparse system -------------------------------
+def diag_dominant_system(n=10_000, off_per_row=4, seed=42):
+    """Sorted COO (rows, cols, vals) with `off_per_row` distinct random off-diagonals per row,
+    values U(-1,1), diagonal = sum|off| + 1; x* ~ U(-100,100); b = A x*."""
+    rng = np.random.default_rng(seed)
+    cols = np.empty((n, off_per_row + 1), np.int64)
+    for k in range(off_per_row):
+        cols[:, k] = rng.integers(0, n, n)
+    cols[:, off_per_row] = np.arange(n)
+    vals = rng.uniform(-1.0, 1.0, (n, off_per_row + 1))
+    # drop duplicate columns inside a row (keep the first), and clashes with the diagonal
+    order = np.argsort(cols, axis=1, kind="stable")
+    cols = np.take_along_axis(cols, order, 1)
+    vals = np.take_along_axis(vals, order, 1)
+    is_diag = cols == np.arange(n)[:, None]
+    dup = np.zeros_like(is_diag)
+    dup[:, 1:] = cols[:, 1:] == cols[:, :-1]
+    # among equal columns keep exactly one; if the diagonal is among them keep a single entry as diagonal
+    keep = ~dup
+    vals = np.where(keep, vals, 0.0)
+    offsum = np.where(keep & ~is_diag, np.abs(vals), 0.0).sum(1)
+    first_diag = is_diag & keep
+    vals = np.where(first_diag, (offsum + 1.0)[:, None], vals)
+    rows = np.repeat(np.arange(n), off_per_row + 1).reshape(n, -1)
+    m = keep.ravel()
+    r, c, v = rows.ravel()[m], cols.ravel()[m], vals.ravel()[m]
+    xstar = rng.uniform(-100.0, 100.0, n)
+    b = np.zeros(n)
+    np.add.at(b, r, v * xstar[c])
+    return r.astype(np.int32), c.astype(np.int32), v.astype(np.float64), b, xstar
+
+
+def coo_to_csr(rows, cols, vals, n):
+    ro = np.zeros(n + 1, np.int64)
+    np.add.at(ro, rows.astype(np.int64) + 1, 1)
+    return np.cumsum(ro).astype(np.int32), cols.astype(np.int32), vals.astype(np.float64)
+
+
+# ---- images and gradients -------------------------------------------------------------------------
+def synth_image(W, H, channels=1, seed=7):
+    """uint8 image: smooth low-frequency field plus a vertical seam step (two 'exposures')."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = np.empty((channels, H, W), np.uint8)
+    for c in range(channels):
+        ph = rng.uniform(0, 2 * np.pi, 4)
+        f = (110 + 60 * np.sin(2 * np.pi * x / max(W, 2) * 1.5 + ph[0]) * np.cos(2 * np.pi * y / max(H, 2) + ph[1])
+             + 25 * np.sin(2 * np.pi * (x + 2 * y) / max(W + H, 2) * 3 + ph[2]))
+        seam = W // 2 + (8 * np.sin(2 * np.pi * y / max(H, 2) * 2 + ph[3])).astype(np.int64)
+        f = f + np.where(x >= seam, 28.0 + 4 * c, 0.0)
+        f += rng.integers(-3, 4, (H, W))
+        out[c] = np.clip(f, 0, 255).astype(np.uint8)
+    return out
+
+
+def forward_gradients(img):
+    """GradientAt over y < H-1, x < W-1 (PhotoMontage.cpp:399-425): float32 arrays (C, H, W); the last
+    row/column stay 0 (never read by the system)."""
+    img = img.astype(np.int32)
+    gx = np.zeros(img.shape, np.float32)
+    gy = np.zeros(img.shape, np.float32)
+    gx[:, :-1, :-1] = (img[:, :-1, 1:] - img[:, :-1, :-1]).astype(np.float32)
+    gy[:, :-1, :-1] = (img[:, 1:, :-1] - img[:, :-1, :-1]).astype(np.float32)
+    return gx, gy
+
+
+def seamless_gradients(img, seed=7):
+    """Gradients of the two half-images with the seam step removed: what gradient-domain fusion feeds the
+    solver (the blended result should not show the exposure step)."""
+    gx, gy = forward_gradients(img)
+    big = np.abs(gx) > 20
+    gx = np.where(big, 0.0, gx).astype(np.float32)
+    return gx, gy
+
+
+# ---- Dirichlet-masked 5-point blend (C2/C3 converged-parity systems) ---------------------------------
+def blob_mask(W, H, coverage=0.30, max_thickness=48, seed=11):
+    """Union of random axis-aligned ellipses with semi-axes <= max_thickness/2, never touching the frame."""
+    rng = np.random.default_rng(seed)
+    mask = np.zeros((H, W), bool)
+    target = coverage * W * H
+    r_max = max(2, max_thickness // 2)
+    guard = 0
+    while mask.sum() < target and guard < 200000:
+        guard += 1
+        ry, rx = rng.integers(max(2, r_max // 3), r_max + 1, 2)
+        if H - 2 * ry - 2 <= 1 or W - 2 * rx - 2 <= 1:
+            break
+        cy = rng.integers(ry + 1, H - ry - 1)
+        cx = rng.integers(rx + 1, W - rx - 1)
+        yy, xx = np.ogrid[-ry:ry + 1, -rx:rx + 1]
+        e = (yy / ry) ** 2 + (xx / rx) ** 2 <= 1.0
+        mask[cy - ry:cy + ry + 1, cx - rx:cx + rx + 1] |= e
+    mask[0, :] = mask[-1, :] = False
+    mask[:, 0] = mask[:, -1] = False
+    return mask
+
+
+def masked_poisson_system(mask, guide, target):
+    """5-point Dirichlet system over the pixels with mask==1:
+       4 v_p - sum_{q in N(p) & mask} v_q = sum_{q in N(p)} (g_p - g_q) + sum_{q in N(p) \\ mask} t_q
+    guide/target: (C, H, W) arrays (uint8 or float).  Returns CSR (row_off, col_idx, values), b (C, n),
+    pixel index of every unknown, and the parity colouring (x+y)&1 of the unknowns."""
+    H, W = mask.shape
+    g = guide.astype(np.float64)
+    t = target.astype(np.float64)
+    C = g.shape[0]
+    idx = -np.ones((H, W), np.int64)
+    ys, xs = np.nonzero(mask)
+    n = ys.size
+    idx[ys, xs] = np.arange(n)
+    b = np.zeros((C, n))
+    ent_r, ent_c, ent_v = [], [], []
+    # neighbour order up, left, (diag), right, down == ascending compact index
+    for dy, dx in ((-1, 0), (0, -1), (0, 1), (1, 0)):
+        qy, qx = ys + dy, xs + dx
+        inside = mask[qy, qx]
+        b += g[:, ys, xs] - g[:, qy, qx]
+        b += np.where(inside, 0.0, t[:, qy, qx])
+        ent_r.append(np.arange(n)[inside])
+        ent_c.append(idx[qy, qx][inside])
+        ent_v.append(np.full(inside.sum(), -1.0))
+    ent_r.append(np.arange(n))
+    ent_c.append(np.arange(n))
+    ent_v.append(np.full(n, 4.0))
+    r = np.concatenate(ent_r)
+    c = np.concatenate(ent_c)
+    v = np.concatenate(ent_v)
+    order = np.lexsort((c, r))
+    r, c, v = r[order], c[order], v[order]
+    ro, ci, va = coo_to_csr(r, c, v, n)
+    colors = ((ys + xs) & 1).astype(np.int32)
+    return ro, ci, va, b, (ys * W + xs), colors
+
+
+# ---- C5: random sparse SPD -----------------------------------------------------------------------
+def random_spd_system(n=1_000_000, pairs_per_row=13, seed=5):
+    """~2*pairs_per_row+1 nnz/row: symmetric random pattern, off-diagonals U(-1,0), diagonal = sum|off| + 1.
+    Returns CSR and b = A x* with x* ~ U(-1,1)."""
+    rng = np.random.default_rng(seed)
+    i = np.repeat(np.arange(n, dtype=np.int64), pairs_per_row)
+    j = rng.integers(0, n, i.size)
+    keep = i != j
+    i, j = i[keep], j[keep]
+    v = rng.uniform(-1.0, 0.0, i.size)
+    r = np.concatenate([i, j])
+    c = np.concatenate([j, i])
+    v = np.concatenate([v, v])
+    key = r * n + c
+    order = np.argsort(key, kind="stable")
+    key, v = key[order], v[order]
+    first = np.ones(key.size, bool)
+    first[1:] = key[1:] != key[:-1]
+    # merge duplicates by summing
+    seg = np.cumsum(first) - 1
+    vs = np.zeros(seg[-1] + 1)
+    np.add.at(vs, seg, v)
+    key = key[first]
+    r, c = key // n, key % n
+    diag = np.zeros(n)
+    np.add.at(diag, r, np.abs(vs))
+    diag += 1.0
+    r = np.concatenate([r, np.arange(n)])
+    c = np.concatenate([c, np.arange(n)])
+    vs = np.concatenate([vs, diag])
+    order = np.lexsort((c, r))
+    r, c, vs = r[order], c[order], vs[order]
+    ro, ci, va = coo_to_csr(r, c, vs, n)
+    xstar = rng.uniform(-1.0, 1.0, n)
+    b = np.zeros(n)
+    np.add.at(b, r, vs * xstar[c])
+    return ro, ci, va, b, xstar
+
+
+# ---- numpy restatement of the reference Poisson stencil (host-side reference for generators) ----------
+def poisson_nnz(W, H):
+    return (W * H - 1) + 4 * (W - 1) * (H - 1)
+
+
+def strip_bounds(H, world):
+    """Row-strip partition of an H-row image over `world` ranks: [y0, y1) per rank, as even as possible."""
+    base, rem = divmod(H, world)
+    out, y = [], 0
+    for r in range(world):
+        h = base + (1 if r < rem else 0)
+        out.append((y, y + h))
+        y += h
+    return out

@@ -1,0 +1,235 @@
+/* gsb200.h -- C ABI of libgsb200.so: the B200 (sm_100a) implementation of the reference's
+ * SparseMatrix container + Gauss-Seidel hot path.
+ *
+ * "v1" = labs/lab3/src/OpenCVHW1/sparse-matrix.h, "v2" = labs/lab8/src/OpenCVHW1/sparse-matrix.h
+ * (== project/src/PhotoMontage/sparse-matrix.h) of linwe2012/CourseComputationalPhotography.
+ * Every entry point names the reference member it replaces.  The reference has no FFI layer
+ * (it is a header-only C++17 template), so this is the boundary a maintainer would bind the
+ * class's method bodies to; include/sparse-matrix.h is that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - every function returns a gsb_status (0 = ok); gsb_last_error() gives the text of the
+ *     last failure on the calling thread.
+ *   - pointers are HOST pointers unless the function name ends in _dev, in which case vector
+ *     arguments are DEVICE pointers on the matrix's device and the call is asynchronous on
+ *     the library stream only until it needs the stop-rule scalar (it then synchronises).
+ *   - element type: the reference instantiates SparseMatrix<int> (lab3) and
+ *     SparseMatrix<double> (lab8/project).  `vtype` selects which; solver arithmetic is
+ *     always FP64 exactly as the reference promotes T to double (v2 :364-373).
+ *   - index type: int32 (reference default IndexType=int, v2 :107,119).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     GSB_ERR_NO_DEVICE.
+ */
+#ifndef GSB200_H
+#define GSB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gsb_status {
+    GSB_OK = 0,
+    GSB_ERR_ARG = 1,        /* null pointer, negative size, nrhs out of range ...           */
+    GSB_ERR_SHAPE = 2,      /* vector length / matrix shape mismatch, non-square solve       */
+    GSB_ERR_UNSORTED = 3,   /* sorted-COO contract violated (rows not non-decreasing)        */
+    GSB_ERR_CUDA = 4,       /* a CUDA runtime call or kernel failed                          */
+    GSB_ERR_NCCL = 5,       /* NCCL missing or a NCCL call failed                            */
+    GSB_ERR_NO_DEVICE = 6,  /* no usable CUDA device                                         */
+    GSB_ERR_ALLOC = 7,      /* host or device allocation failed                              */
+    GSB_ERR_COLORING = 8,   /* supplied/requested ordering is not a proper colouring         */
+    GSB_ERR_OVERFLOW = 9,   /* sizes exceed the int32 index range                            */
+    GSB_ERR_STATE = 10      /* handle not in the state the call needs (e.g. empty matrix)    */
+} gsb_status;
+
+enum { GSB_F64 = 0, GSB_I32 = 1 };                       /* vtype */
+enum { GSB_ORDER_AUTO = 0, GSB_ORDER_REDBLACK = 1, GSB_ORDER_MULTICOLOR = 2, GSB_ORDER_USER = 3,
+       GSB_ORDER_NATURAL_PARITY = 4 /* colour = row index & 1 (strip-local parity, see dist) */ };
+
+typedef struct gsb_matrix gsb_matrix; /* opaque: device-resident slack CSR + solver format */
+typedef struct gsb_dist gsb_dist;     /* opaque: one rank of a row-strip multi-GPU solve    */
+
+const char *gsb_last_error(void);
+int gsb_version(void);
+int gsb_device_count(int *count);
+int gsb_set_device(int device);       /* device used by handles created afterwards (default 0) */
+void *gsb_stream(void);               /* the library's cudaStream_t on the current device      */
+
+/* ---------------------------------------------------------------------------------------
+ * Container: assembly
+ * ------------------------------------------------------------------------------------- */
+int gsb_matrix_create(gsb_matrix **out, int vtype);
+int gsb_matrix_destroy(gsb_matrix *m);
+
+/* A1  initializeFromVector(rows, cols&&, vals&&)            v1 :209-255, v2 :265-319
+ * Sorted COO (by row, then col; explicit zeros allowed) -> slack CSR, on the device.
+ * n_rows = rows[n-1]+1, n_cols = max(cols)+1.  Layout is bit-exact with the reference:
+ * row_begin[r] = #entries with row<r, row_nnz[r] = nonzeros of r, row_left[r] = explicit
+ * zeros of r, live slots = the nonzeros in input order, slack slots keep the input entry
+ * that was at that position.  vals: double* (GSB_F64) or int32_t* (GSB_I32). */
+int gsb_matrix_assemble_sorted_coo(gsb_matrix *m, const int *rows, const int *cols, const void *vals,
+                                   int64_t n);
+
+/* initializeFromTriplets(Triplet*, cnt)                      v2 :249-263 (crashes upstream)
+ * Unsorted COO -> compact CSR by a device radix sort on (row, col): the last duplicate of a
+ * coordinate wins (the reference's repeated insert() semantics), zeros are dropped, columns
+ * ascend, no slack. */
+int gsb_matrix_assemble_coo(gsb_matrix *m, const int *rows, const int *cols, const void *vals, int64_t n,
+                            int n_rows, int n_cols);
+
+/* A3  initializeFromEigenRowMajor(values,n_values,row_offset,n_row_offset,col_offset,
+ *                                 n_col_offset,non_zeros,n_non_zeros)      v2 :537-620
+ * CSR import; nnz_per_row == NULL is the compressed (Poisson) case.  Reproduces the
+ * reference's treatment of trailing empty rows (:608-614) and of given per-row counts. */
+int gsb_matrix_import_csr(gsb_matrix *m, const void *values, int n_values, const int *row_off,
+                          int n_row_off, const int *col_idx, int n_col_off, const int *nnz_per_row,
+                          int n_nnz_per_row);
+
+/* Raw layout upload: the five reference arrays as they stand on the host (used by the C++
+ * mirror after insert() edits the host copy; A5 v2 :183-247 stays on the host). */
+int gsb_matrix_upload(gsb_matrix *m, const void *values, const int *cols, int64_t store,
+                      const int *row_begin, const int *row_nnz, const int *row_left, int n_rows, int n_cols);
+
+int gsb_matrix_shape(const gsb_matrix *m, int64_t *store, int *n_rows, int *n_cols, int64_t *nnz);
+/* Copy the five reference arrays back (any pointer may be NULL). values: vtype elements. */
+int gsb_matrix_download(const gsb_matrix *m, void *values, int *cols, int *row_begin, int *row_nnz,
+                        int *row_left);
+
+/* Stateless forms of A1/A3 (create + assemble + download + destroy). Output arrays: values/cols
+ * sized n (A1) or n_values (A3); row arrays sized n_rows. */
+int gsb_csr_from_sorted_coo(int vtype, const int *rows, const int *cols, const void *vals, int64_t n,
+                            void *values_out, int *cols_out, int *row_begin, int *row_nnz, int *row_left,
+                            int *n_rows, int *n_cols);
+int gsb_csr_import(int vtype, const void *values, int n_values, const int *row_off, int n_row_off,
+                   const int *col_idx, int n_col_off, const int *nnz_per_row, int n_nnz_per_row,
+                   void *values_out, int *cols_out, int *row_begin, int *row_nnz, int *row_left);
+
+/* A4  at(row,col) / coeff(row,col)                          v2 :162-178, :627-645
+ * Batched lookup on the device copy: out[k] = at(rows[k], cols[k]) as double. */
+int gsb_matrix_at(const gsb_matrix *m, const int *rows, const int *cols, int64_t count, double *out);
+
+/* ---------------------------------------------------------------------------------------
+ * Ordering: colouring + colour-major reorder of the solver format
+ * ------------------------------------------------------------------------------------- */
+/* ordering: GSB_ORDER_*.  user_colors (host, n_rows ints, colours 0..k-1) only for _USER.
+ * AUTO = 5-point grid probe -> red-black, else greedy multicolour.  Called implicitly (AUTO)
+ * by the first solve if the caller did not. */
+int gsb_matrix_analyze(gsb_matrix *m, int ordering, const int *user_colors);
+int gsb_matrix_coloring(const gsb_matrix *m, int *n_colors, int *ordering_used, int *grid_width);
+/* perm[new] = old row; colors[old row] = colour.  Either may be NULL. */
+int gsb_matrix_ordering(const gsb_matrix *m, int *perm, int *colors);
+
+/* ---------------------------------------------------------------------------------------
+ * Solver (A6-A8)
+ * ------------------------------------------------------------------------------------- */
+typedef struct gsb_gs_options {
+    int ordering;        /* GSB_ORDER_* used if the matrix has not been analysed yet (default AUTO)  */
+    int check_every;     /* evaluate the stop rule every k-th sweep; 1 = every sweep (reference)     */
+    int batch_sweeps;    /* sweeps enqueued between host reads of the stop flag; 0 = library default */
+    int use_graph;       /* 1 = replay a captured CUDA graph per batch; 0 = plain launches; -1 auto  */
+    int kernel;          /* 0 = auto; 1 = row-per-thread direct; 2 = staged (bulk-copy CSR tiles)     */
+    int compute_residual;/* 1 = also return ||b - A x||_2 per right-hand side in stats                */
+    int reserved[2];
+} gsb_gs_options;
+
+typedef struct gsb_gs_stats {
+    int sweeps;          /* cnt at exit (v2 :377)                                                     */
+    int n_colors;
+    int ordering_used;
+    int kernel_used;
+    int64_t kernel_launches; /* launches of this library's kernels enqueued by the call              */
+    double last_eps[4];  /* L1 norm of the last evaluated sweep update, per right-hand side (v2 :376) */
+    double residual_l2[4];
+    double solve_ms;     /* device time of the sweep loop (CUDA events on the library stream)         */
+    double setup_ms;     /* analysis/reorder time if it ran inside this call, else 0                  */
+} gsb_gs_stats;
+
+void gsb_gs_default_options(gsb_gs_options *o);
+
+/* A6  gaussSeidel(b, epsilon = 1e-6, max_iteration = 1000)   v1 :275-305, v2 :350-380
+ * x0 = 1.0; zero/absent diagonal rows are skipped; stop when the L1 norm of a sweep's update
+ * is <= epsilon or after max_iteration sweeps.  Ordering differs from the reference's
+ * lexicographic sweep (red-black / multicolour), so iterates differ; the fixed point does
+ * not.  nrhs in 1..4 right-hand sides share one pass over the matrix (b and x are
+ * nrhs * n_rows doubles, one vector after another); the loop stops when every right-hand
+ * side meets epsilon.  opts and stats may be NULL. */
+int gsb_gauss_seidel(gsb_matrix *m, const double *b, int nrhs, double epsilon, int max_iteration,
+                     const gsb_gs_options *opts, double *x_out, gsb_gs_stats *stats);
+int gsb_gauss_seidel_dev(gsb_matrix *m, const double *b_dev, int nrhs, double epsilon, int max_iteration,
+                         const gsb_gs_options *opts, double *x_dev, gsb_gs_stats *stats);
+/* EXTENSION (not in the reference API): same with an initial guess x0. */
+int gsb_gauss_seidel_x0(gsb_matrix *m, const double *b, const double *x0, int nrhs, double epsilon,
+                        int max_iteration, const gsb_gs_options *opts, double *x_out, gsb_gs_stats *stats);
+
+/* A7  applyToVector(in, out)                                 v1 :307-318, v2 :382-393
+ * out = A * in over the live entries in storage order (bit-exact with the reference's
+ * unfused multiply-add). in: n_cols doubles, out: n_rows doubles. */
+int gsb_spmv(gsb_matrix *m, const double *in, double *out);
+int gsb_spmv_dev(gsb_matrix *m, const double *in_dev, double *out_dev);
+/* ||b - A x||_2 (the residual norm reported beside every parity number) */
+int gsb_residual_l2(gsb_matrix *m, const double *b, const double *x, double *out);
+int gsb_residual_l2_dev(gsb_matrix *m, const double *b_dev, const double *x_dev, double *out);
+
+/* A8  manhattonDist / dotProd / veclen2 / vecadd / vecsub / vecmul   v2 :45-105 */
+int gsb_l1_dist(const double *a, const double *b, int64_t n, double *out);
+int gsb_dot(const double *a, const double *b, int64_t n, double *out);
+int gsb_axpy(const double *a, const double *b, double scale_b, int64_t n, double *out); /* a+scale*b */
+int gsb_vecmul(const double *a, const double *b, int64_t n, double *out);               /* a .* b    */
+
+/* N1  conjugateGradient(b, eps, max_iter, initialize)        v2 :396-434
+ *     conjugateGradientEigen(b, eps, max_iter) (Jacobi-PCG)  v2 :472-535
+ * x0 may be NULL (zero start).  iters = loop count at exit. */
+int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
+                           const double *x0, double *x_out, int *iters);
+int gsb_conjugate_gradient_jacobi(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
+                                  double *x_out, int *iters);
+
+/* ---------------------------------------------------------------------------------------
+ * Poisson system (A9, A10; "next" rows N2/N4): built on the device, no Eigen
+ * ------------------------------------------------------------------------------------- */
+/* A9  SolveChannel front half: PhotoMontage.cpp:541-597 == hw8_pa.cc:911-967.
+ * Builds A^T*A of the forward-difference system for a W x H image straight into `m`
+ * (compressed CSR, ascending columns, == what initializeFromEigenRowMajor receives). */
+int gsb_poisson_matrix(gsb_matrix *m, int W, int H);
+/* A^T*b for nch channels: gx, gy = nch*H*W float32 gradients (host), constraint[nch];
+ * b_out = nch*W*H doubles (host). */
+int gsb_poisson_rhs(int W, int H, int nch, const float *gx, const float *gy, const double *constraint,
+                    double *b_out);
+int gsb_poisson_rhs_dev(int W, int H, int nch, const float *gx_dev, const float *gy_dev,
+                        const double *constraint, double *b_dev);
+/* A10 write-back: uchar(clamp(x, 0, 255)), truncating. PhotoMontage.cpp:617-626 */
+int gsb_writeback_u8(const double *x, int64_t n, unsigned char *out);
+int gsb_writeback_u8_dev(const double *x_dev, int64_t n, unsigned char *out_dev);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU row strips: one rank per GPU, halo exchange per colour phase
+ * ------------------------------------------------------------------------------------- */
+#define GSB_UNIQUE_ID_BYTES 128
+/* rank 0 fills id (ncclGetUniqueId); the caller broadcasts it to the other ranks by any
+ * means (torch.distributed in bench.py) before gsb_dist_init. */
+int gsb_dist_unique_id(unsigned char id[GSB_UNIQUE_ID_BYTES]);
+int gsb_dist_init(gsb_dist **out, const unsigned char id[GSB_UNIQUE_ID_BYTES], int rank, int world,
+                  int device);
+int gsb_dist_finalize(gsb_dist *d);
+/* Reference-faithful full-grid Poisson matrix (A9) for the image rows [y0, y1) owned by this
+ * rank, generated on the device (config C4: 16384^2 never exists on one host). */
+int gsb_dist_poisson_strip(gsb_dist *d, int W, int H, int y0, int y1);
+/* General form: this rank's rows [row0, row0+n_local) of a square n_global system, compressed
+ * CSR with GLOBAL column indices; colours = parity of (col % grid_width + col / grid_width). */
+int gsb_dist_matrix_rows(gsb_dist *d, const double *values, const int *row_off, const int *col_idx,
+                         int64_t row0, int n_local, int64_t n_global, int grid_width);
+/* b_dev / x_dev: nrhs vectors of n_local doubles on this rank's device. Collective. */
+int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int nrhs, double epsilon,
+                              int max_iteration, const gsb_gs_options *opts, double *x_dev,
+                              gsb_gs_stats *stats);
+int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const double *x_dev, double *out);
+
+/* Pinned host memory for callers that want full-rate PCIe copies (bench.py e2e leg). */
+int gsb_host_alloc(void **ptr, int64_t bytes);
+int gsb_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H */

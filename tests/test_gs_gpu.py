@@ -1,0 +1,284 @@
+"""GPU parity tests of the Gauss-Seidel path (A6-A8) through the C ABI, against the CPU oracle.
+
+Two kinds of statement (BASELINE.json north_star):
+  1. per-sweep bit-exactness: multicolour GS on the device == the oracle's lexicographic GS on the
+     symmetrically permuted matrix P A P^T, for the same number of sweeps;
+  2. converged parity: the fixed point matches the oracle's natural-order solution within
+     max-abs <= 1e-4 * 255 (image range), with residual norms reported.
+"""
+import numpy as np
+import pytest
+
+from helpers import oracle_from_csr, permuted_csr
+
+pytestmark = pytest.mark.gpu
+
+TOL_IMAGE = 1e-4 * 255.0  # north_star: max-abs <= 1e-4 relative to the image range
+
+
+def _poisson_rhs_for(pkg, wl, W, H, C=1, seed=7):
+    img = wl.synth_image(W, H, C, seed=seed)
+    gx, gy = wl.seamless_gradients(img)
+    b = pkg.poisson_rhs(W, H, gx if C > 1 else gx[0], gy if C > 1 else gy[0], img[:, 0, 0].astype(np.float64))
+    return img, b
+
+
+def test_known_answer_4x4(gsb, oracle_mod):
+    """labs/lab3/src/OpenCVHW1/main6.cc:238-249: expected print `1 2 -1 1`."""
+    A = [10, -1, 2, 0, -1, 11, -1, 3, 2, -1, 10, -1, 0, 3, -1, 8]
+    b = np.array([6, 25, -11, 15], np.float64)
+    sp = gsb.SparseMatrix(np.int32)
+    sp.initialize(4, 4, A)
+    x = sp.gaussSeidel(b)
+    assert np.allclose(x, [1, 2, -1, 1], atol=1e-6)
+    o = oracle_mod.Oracle().init_dense(4, 4, A)
+    xo, sw, _ = o.gauss_seidel(b)
+    assert np.abs(x - xo).max() < 1e-6
+    assert sp.last_stats.sweeps > 0 and sp.last_stats.last_eps[0] <= 1e-6
+    # dense 4x4: every row touches every other one -> 4 colours, i.e. the lexicographic order itself
+    info = sp.coloring()
+    assert info["n_colors"] == 4
+    perm, _ = sp.ordering()
+    if np.array_equal(perm, np.arange(4)):
+        assert np.array_equal(x, xo) and sp.last_stats.sweeps == sw
+
+
+@pytest.mark.parametrize("W,H", [(16, 12), (33, 17), (64, 64), (2, 2), (5, 1), (1, 7)])
+@pytest.mark.parametrize("sweeps", [1, 7])
+def test_redblack_poisson_bitexact_vs_oracle_on_permuted(gsb, oracle_mod, W, H, sweeps):
+    from coursecomputationalphotography_b200 import workloads as wl
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    img, b = _poisson_rhs_for(gsb, wl, W, H)
+    x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=sweeps)
+    info = sp.coloring()
+    assert info["ordering"] == gsb._lib.ORDER_REDBLACK and info["n_colors"] <= 2
+    perm, colors = sp.ordering()
+    ro, ci, va = oracle_mod.poisson_csr(W, H)
+    pro, pci, pva = permuted_csr(ro, ci, va, perm)
+    o = oracle_from_csr(oracle_mod, pro, pci, pva)
+    xp, sw, _ = o.gauss_seidel(b[perm], 0.0, sweeps)
+    xo = np.empty_like(xp)
+    xo[perm] = xp
+    assert np.array_equal(x, xo), "device sweep differs from the oracle on P A P^T (max %g)" % np.abs(x - xo).max()
+    # the empty last row is skipped: x stays at 1.0 (v2 :360-363)
+    if W > 1 and H > 1:
+        assert x[-1] == 1.0
+
+
+def test_multicolor_random_bitexact_and_converged(gsb, oracle_mod):
+    from coursecomputationalphotography_b200 import workloads as wl
+    n = 5000
+    r, c, v, b, xstar = wl.diag_dominant_system(n, 4, seed=3)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromVector(r, c, v)
+    x5 = sp.gaussSeidel(b, epsilon=0.0, max_iteration=5)
+    info = sp.coloring()
+    assert info["ordering"] == gsb._lib.ORDER_MULTICOLOR and 2 <= info["n_colors"] <= 64
+    perm, colors = sp.ordering()
+    ro, ci, va = wl.coo_to_csr(r, c, v, n)
+    # proper colouring: no row reads an unknown of its own colour
+    rows = np.repeat(np.arange(n), np.diff(ro))
+    off = rows != ci
+    assert not np.any(colors[rows[off]] == colors[ci[off]])
+    pro, pci, pva = permuted_csr(ro, ci, va, perm)
+    o = oracle_from_csr(oracle_mod, pro, pci, pva)
+    xp, _, _ = o.gauss_seidel(b[perm], 0.0, 5)
+    xo = np.empty_like(xp)
+    xo[perm] = xp
+    assert np.array_equal(x5, xo)
+    # converged parity against the natural-order oracle (reference defaults)
+    x = sp.gaussSeidel(b)
+    on = oracle_from_csr(oracle_mod, ro, ci, va)
+    xn, sw, _ = on.gauss_seidel(b)
+    assert np.abs(x - xn).max() <= 1e-6
+    assert np.abs(x - xstar).max() <= 1e-6
+    assert abs(sp.last_stats.sweeps - sw) <= 6  # ordering changes the count slightly, not the fixed point
+    assert sp.residual(b, x) <= 1e-5
+
+
+def test_masked_blend_converged_parity_user_colors(gsb, oracle_mod):
+    """Dirichlet-masked 5-point blend (SURVEY 8d C3 at 192^2): converged solution vs the oracle."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    W = H = 192
+    mask = wl.blob_mask(W, H, 0.30, 24, seed=11)
+    guide = wl.synth_image(W, H, 3, seed=7)
+    target = wl.synth_image(W, H, 3, seed=9)
+    ro, ci, va, b, pix, colors = wl.masked_poisson_system(mask, guide, target)
+    n = len(pix)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
+    info = sp.analyze(gsb._lib.ORDER_USER, colors)
+    assert info["n_colors"] == 2
+    x = sp.gaussSeidel(b, epsilon=1e-7, max_iteration=20000)
+    assert sp.last_stats.sweeps < 20000
+    o = oracle_from_csr(oracle_mod, ro, ci, va)
+    for ch in range(3):
+        xo, sw, _ = o.gauss_seidel(b[ch], 1e-7, 20000)
+        err = np.abs(x[ch] - xo).max()
+        r_gpu, r_cpu = sp.residual(b[ch], x[ch]), np.linalg.norm(b[ch] - o.spmv(xo))
+        print("ch%d: max-abs %.3e  ||r|| gpu %.3e cpu %.3e  sweeps gpu %d cpu %d" %
+              (ch, err, r_gpu, r_cpu, sp.last_stats.sweeps, sw))
+        assert err <= TOL_IMAGE
+        assert np.array_equal(gsb.writeback_u8(x[ch]), oracle_mod.writeback_u8(xo)) or err < TOL_IMAGE
+    # automatic ordering on the same (irregular) system also converges to the same point
+    sp2 = gsb.SparseMatrix(np.float64)
+    sp2.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
+    x2 = sp2.gaussSeidel(b[0], epsilon=1e-7, max_iteration=20000)
+    assert np.abs(x2 - x[0]).max() <= TOL_IMAGE
+
+
+def test_multi_rhs_equals_single_rhs(gsb):
+    from coursecomputationalphotography_b200 import workloads as wl
+    W, H = 48, 40
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
+    x3 = sp.gaussSeidel(b, epsilon=0.0, max_iteration=9)
+    for ch in range(3):
+        x1 = sp.gaussSeidel(b[ch], epsilon=0.0, max_iteration=9)
+        assert np.array_equal(x1, x3[ch])
+    b4 = np.concatenate([b, b[:1]])
+    x4 = sp.gaussSeidel(b4, epsilon=0.0, max_iteration=9)
+    assert np.array_equal(x4[:3], x3) and np.array_equal(x4[3], x3[0])
+
+
+def test_stop_rule_semantics(gsb):
+    from coursecomputationalphotography_b200 import workloads as wl
+    r, c, v, b, _ = wl.diag_dominant_system(2000, 4, seed=5)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromVector(r, c, v)
+    # eps starts at 10 (v2 :354): epsilon >= 10 or max_iteration <= 0 means no sweep at all, x stays 1.0
+    x = sp.gaussSeidel(b, epsilon=10.0)
+    assert sp.last_stats.sweeps == 0 and np.all(x == 1.0)
+    x = sp.gaussSeidel(b, max_iteration=0)
+    assert sp.last_stats.sweeps == 0 and np.all(x == 1.0)
+    # max_iteration caps the count exactly, whatever the batching
+    for k in (1, 3, 5):
+        for opts in (gsb.SparseMatrix.options(use_graph=0, batch_sweeps=2),
+                     gsb.SparseMatrix.options(use_graph=1, batch_sweeps=4)):
+            sp.gaussSeidel(b, epsilon=0.0, max_iteration=k, options=opts)
+            assert sp.last_stats.sweeps == k
+    # the accepted iterate is the one the rule fired on: graph / plain / different batch sizes agree bitwise
+    xa = sp.gaussSeidel(b, options=gsb.SparseMatrix.options(use_graph=0, batch_sweeps=1))
+    sa = sp.last_stats.sweeps
+    xb = sp.gaussSeidel(b, options=gsb.SparseMatrix.options(use_graph=1, batch_sweeps=16))
+    sb = sp.last_stats.sweeps
+    xc = sp.gaussSeidel(b, options=gsb.SparseMatrix.options(use_graph=0, batch_sweeps=7))
+    assert sa == sb == sp.last_stats.sweeps and np.array_equal(xa, xb) and np.array_equal(xa, xc)
+    assert sp.last_stats.last_eps[0] <= 1e-6
+    # check_every = 4: stops at a multiple of 4 that is >= the every-sweep count
+    sp.gaussSeidel(b, options=gsb.SparseMatrix.options(check_every=4))
+    assert sp.last_stats.sweeps % 4 == 0 and sa <= sp.last_stats.sweeps < sa + 4
+
+
+def test_zero_diagonal_rows_are_skipped(gsb, oracle_mod):
+    # 3x3: row 1 has no diagonal entry -> x[1] stays 1.0 (v2 :360-363)
+    rows = np.array([0, 0, 1, 2, 2], np.int32)
+    cols = np.array([0, 1, 0, 1, 2], np.int32)
+    vals = np.array([4.0, 1.0, 2.0, 1.0, 5.0])
+    b = np.array([1.0, 2.0, 3.0])
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromVector(rows, cols, vals)
+    x = sp.gaussSeidel(b)
+    o = oracle_mod.Oracle().init_from_vector(rows, cols, vals)
+    xo, _, _ = o.gauss_seidel(b)
+    assert x[1] == 1.0 and np.allclose(x, xo, atol=1e-12)
+
+
+def test_x0_extension_and_errors(gsb):
+    from coursecomputationalphotography_b200 import workloads as wl
+    r, c, v, b, xstar = wl.diag_dominant_system(500, 4, seed=8)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromVector(r, c, v)
+    x = sp.gaussSeidel(b, x0=xstar)
+    assert sp.last_stats.sweeps <= 2 and np.abs(x - xstar).max() < 1e-9
+    with pytest.raises(ValueError):
+        sp.gaussSeidel(b[:-1])
+    rect = gsb.SparseMatrix(np.float64)
+    rect.initializeFromVector([0, 1], [0, 3], [1.0, 2.0])  # 2 x 4
+    with pytest.raises(gsb.GsbError) as e:
+        rect.gaussSeidel(np.ones(4))
+    assert e.value.status == 2  # GSB_ERR_SHAPE
+    bad = gsb.SparseMatrix(np.float64)
+    bad.initialize(3, 3, [2, 1, 0, 1, 2, 1, 0, 1, 2])
+    with pytest.raises(gsb.GsbError) as e:
+        bad.analyze(gsb._lib.ORDER_USER, [0, 0, 1])  # rows 0 and 1 are coupled
+    assert e.value.status == 8  # GSB_ERR_COLORING
+
+
+def test_spmv_bitexact_and_vector_helpers(gsb, oracle_mod):
+    from coursecomputationalphotography_b200 import workloads as wl
+    rng = np.random.default_rng(0)
+    r, c, v, b, _ = wl.diag_dominant_system(3000, 6, seed=2)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromVector(r, c, v)
+    o = oracle_mod.Oracle().init_from_vector(r, c, v)
+    vin = rng.standard_normal(3000)
+    assert np.array_equal(sp.applyToVector(vin), o.spmv(vin))
+    a, bb = rng.standard_normal(100001), rng.standard_normal(100001)
+    assert gsb.manhattonDist([1, 2, 3, 10], [2, 1, 3, 8]) == 4.0  # main6.cc:233-235
+    assert abs(gsb.manhattonDist(a, bb) - oracle_mod.l1_dist(a, bb)) <= 1e-9 * np.abs(a - bb).sum()
+    assert abs(gsb.dotProd(a, bb) - float(np.dot(a, bb))) <= 1e-9 * np.abs(a * bb).sum()
+    assert np.array_equal(gsb.vecadd(a, bb, 0.37), a + 0.37 * bb)
+    assert np.array_equal(gsb.vecsub(a, bb), a - bb)
+    assert np.array_equal(gsb.vecmul(a, bb), a * bb)
+
+
+def test_cg_and_pcg_vs_oracle(gsb, oracle_mod):
+    from coursecomputationalphotography_b200 import workloads as wl
+    A = [10, -1, 2, 0, -1, 11, -1, 3, 2, -1, 10, -1, 0, 3, -1, 8]
+    b = np.array([6, 25, -11, 15], np.float64)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initialize(4, 4, A)
+    assert np.allclose(sp.conjugateGradient(b), [1, 2, -1, 1], atol=1e-12)  # main6.cc:251-253
+    assert np.allclose(sp.conjugateGradientEigen(b), [1, 2, -1, 1], atol=1e-12)
+    # Poisson 32x24 with the composite as the initial guess (PhotoMontage.cpp:599-613)
+    W, H = 32, 24
+    img, bp = _poisson_rhs_for(gsb, wl, W, H)
+    sp2 = gsb.SparseMatrix(np.float64)
+    sp2.poisson(W, H)
+    ro, ci, va = oracle_mod.poisson_csr(W, H)
+    o = oracle_from_csr(oracle_mod, ro, ci, va)
+    init = img[0].astype(np.float64).ravel()
+    x = sp2.conjugateGradient(bp, 1e-10, 50, init)
+    xo, it = o.cg(bp, 1e-10, 50, init)
+    assert np.abs(x - xo).max() < 1e-6 * 255
+    xj = sp2.conjugateGradientEigen(bp, 1e-10, 400)
+    xjo, _ = o.pcg(bp, 1e-10, 400)
+    assert np.abs(xj[:-1] - xjo[:-1]).max() < 1e-5 * 255
+
+
+def test_full_size_properties_4096(gsb):
+    """BASELINE configs[2] size: 4096^2 x 3 channels.  Size-independent properties instead of an oracle run."""
+    import ctypes as C
+    from coursecomputationalphotography_b200 import workloads as wl
+    W = H = 4096
+    n = W * H
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    assert sp._nnz == wl.poisson_nnz(W, H) == 83_853_315
+    # (1) a constant image is a fixed point: b = A*const (only the pin row is nonzero) -> x stays const
+    rng = np.random.default_rng(1)
+    b = np.zeros((3, n))
+    b[:, 0] = 1.0  # pin v(0,0) = 1, zero gradients: the solution is the all-ones start vector
+    x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=3)
+    assert sp.last_stats.sweeps == 3 and np.all(x == 1.0)
+    assert sp.last_stats.last_eps[0] == 0.0
+    # (2) linearity of one sweep chain is not exact in floating point, but the residual must fall
+    #     monotonically for an SPD system under GS: compare ||b-Ax|| after 2 and after 12 sweeps
+    img = wl.synth_image(W, H, 1, seed=3)
+    gx, gy = wl.seamless_gradients(img)
+    b1 = gsb.poisson_rhs(W, H, gx[0], gy[0], float(img[0, 0, 0]))
+    xa = sp.gaussSeidel(b1, epsilon=0.0, max_iteration=2)
+    ra = sp.residual(b1, xa)
+    xb = sp.gaussSeidel(b1, epsilon=0.0, max_iteration=12)
+    rb = sp.residual(b1, xb)
+    assert rb < ra
+    # (3) red-black: two colours, both half the grid; empty corner row untouched
+    info = sp.coloring()
+    assert info["n_colors"] == 2 and info["grid_width"] == W
+    assert xb[-1] == 1.0
+    # (4) the A-energy error decreases: applyToVector parity with the residual kernel
+    Ax = sp.applyToVector(xb)
+    assert abs(np.linalg.norm(b1 - Ax) - rb) <= 1e-9 * max(rb, 1.0)
