@@ -105,6 +105,7 @@ struct gsb_dist {
     DevBuf<unsigned char> ctl;
     void *ctl_host = nullptr;
     int ws_nrhs = 0;
+    GsbPlan plan;
     int peer_rank(int p) const { return p == 0 ? rank - 1 : rank + 1; }
     bool has_peer(int p) const { return p == 0 ? rank > 0 : rank < world - 1; }
 };
@@ -424,8 +425,8 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     d_perm_len<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(d->perm.p, d->nat_rp.p, n_local, d->rp.p);
     GSB_KERNEL_CHECK();
     GSB_TRY(gsb_exclusive_scan_i32(d->rp.p, d->rp.p, (int64_t)n_local + 1, nullptr, st));
-    GSB_TRY(d->ci.alloc(nnz));
-    GSB_TRY(d->va.alloc(nnz));
+    GSB_TRY(d->ci.alloc((int64_t)nnz + 8));
+    GSB_TRY(d->va.alloc((int64_t)nnz + 8));
     GSB_CUDA(cudaMemsetAsync(mm.p + 2, 0, sizeof(int), st));
     d_fill_rows<<<(n_local + 127) / 128, 128, 0, st>>>(d->perm.p, d->iperm.p, d->nat_rp.p, d->nat_cg.p, d->nat_va.p,
                                                       n_local, row0, row1, halo_lo, W, map_lo.p, map_hi.p, d->rp.p,
@@ -595,12 +596,13 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     if (opts.check_every < 1) opts.check_every = 1;
     const int n_local = d->n_local;
     const int64_t ld = d->ld;
-    const int nb0 = gsb_phase_blocks(d->color_start[1] - d->color_start[0]);
-    const int nb1 = gsb_phase_blocks(d->color_start[2] - d->color_start[1]);
+    if (!d->plan.valid || d->plan.requested != opts.kernel) {
+        GSB_TRY(gsb_plan_build(&d->plan, d->rp.p, d->color_start, 2, opts.kernel, st));
+        GSB_TRY(d->partials.alloc((int64_t)(d->plan.total_blocks() + 1) * GSB_MAX_RHS));
+    }
     if (d->ws_nrhs < nrhs) {
         GSB_TRY(d->xw.alloc(ld * nrhs));
         GSB_TRY(d->bw.alloc(ld * nrhs));
-        GSB_TRY(d->partials.alloc((int64_t)(nb0 + nb1 + 1) * GSB_MAX_RHS));
         d->ws_nrhs = nrhs;
     }
     if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));
@@ -648,9 +650,9 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             for (int c = 0; c < 2 && status == GSB_OK; ++c) {
                 const int r0 = d->color_start[c], r1 = d->color_start[c + 1];
                 if (r1 > r0) {
-                    status = gsb_launch_phase(d->rp.p, d->ci.p, d->va.p, d->bw.p, d->xw.p, ld, r0, r1, nrhs, check,
-                                              opts.kernel, ctl, d->partials.p + (size_t)poff * nrhs, st);
-                    poff += gsb_phase_blocks(r1 - r0);
+                    status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->bw.p, d->xw.p, ld, nrhs, check,
+                                             ctl, d->partials.p + (size_t)poff * nrhs, st);
+                    poff += d->plan.blocks[c];
                     ++launches;
                 }
                 if (status == GSB_OK) status = dist_exchange(d, c, nrhs, st, &launches);
@@ -699,7 +701,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         stats->sweeps = h.sweeps;
         stats->n_colors = 2;
         stats->ordering_used = GSB_ORDER_REDBLACK;
-        stats->kernel_used = 1;
+        stats->kernel_used = d->plan.kernel;
         stats->kernel_launches = launches;
         for (int r = 0; r < nrhs; ++r) stats->last_eps[r] = h.eps_last[r];
         stats->solve_ms = solve_ms;
@@ -733,7 +735,6 @@ extern "C" int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const 
     if (d->ws_nrhs < 1) {
         GSB_TRY(d->xw.alloc(ld));
         GSB_TRY(d->bw.alloc(ld));
-        GSB_TRY(d->partials.alloc((int64_t)(gsb_phase_blocks(n_local) + 2) * GSB_MAX_RHS));
         d->ws_nrhs = 1;
     }
     int64_t launches = 0;

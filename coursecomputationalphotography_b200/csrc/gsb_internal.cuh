@@ -138,6 +138,7 @@ struct gsb_matrix {
     // cached CUDA graph of one batch
     void *graph_exec = nullptr;
     int graph_key[6] = {0, 0, 0, 0, 0, 0};
+    struct GsbPlan *plan = nullptr; // colour-phase launch plan (gsb_phase.cu)
 
     void drop_analysis();
     ~gsb_matrix();
@@ -161,11 +162,27 @@ struct GsCtl {
     double eps_last[GSB_MAX_RHS];
 };
 
-// one colour phase over rows [row0,row1) of a colour-major CSR; x and b have leading dimension ld
-int gsb_launch_phase(const int *rp, const int *ci, const double *va, const double *b, double *x, int64_t ld,
-                     int row0, int row1, int nrhs, bool check, int kernel, const GsCtl *ctl, double *partials,
-                     cudaStream_t st);
-int gsb_phase_blocks(int rows);
+// how the colour phases of one colour-major CSR are launched (gsb_phase.cu)
+struct GsbPlan {
+    bool valid = false;
+    int requested = 0;  // kernel the caller asked for (0 auto)
+    int kernel = 1;     // resolved: 1 = row-per-thread direct, 2 = bulk-copy staged tiles
+    int tile_rows = 256;
+    int cap = 0;        // shared-memory capacity of one tile, in CSR entries
+    int smem_bytes = 0;
+    int n_colors = 0;
+    int blocks[66];     // CTAs (== partial-sum slots) per colour phase
+    int tile_off[66];   // offset of the colour's segment in tile_k
+    int color_start[66];
+    DevBuf<int> tile_k; // per colour: CSR offset at every tile boundary (blocks[c] + 1 entries)
+    int total_blocks() const;
+};
+int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colors, int kernel_request,
+                   cudaStream_t st);
+// one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles
+int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
+                    double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
+                    cudaStream_t st);
 // end of sweep.  mode 0: fold partials, bump the counter, decide (single GPU)
 //                mode 1: fold partials into ctl->eps_last only (strip solver, before the all-reduce)
 //                mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
@@ -176,3 +193,26 @@ int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int
 int gsb_poisson_launch_row_len(int W, int H, int64_t p0, int64_t p1, int *len, cudaStream_t st);
 int gsb_poisson_launch_fill(int W, int H, int64_t p0, int64_t p1, const int *rp, int *ci, double *va,
                             cudaStream_t st);
+
+#ifdef __CUDACC__
+// fixed-order block reduction of NRHS values per thread -> out[0..NRHS) (deterministic partials)
+template <int NRHS, int THREADS>
+__device__ __forceinline__ void gsb_block_reduce_store(double (&v)[NRHS], double *__restrict__ out) {
+    __shared__ double ws[NRHS][THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+        double t = v[r];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+        if (lane == 0) ws[r][wid] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NRHS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) s += ws[threadIdx.x][w];
+        out[threadIdx.x] = s;
+    }
+}
+#endif

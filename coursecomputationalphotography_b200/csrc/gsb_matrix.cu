@@ -33,6 +33,9 @@ void gsb_matrix::drop_analysis() {
         graph_exec = nullptr;
     }
     memset(graph_key, 0, sizeof(graph_key));
+    delete plan;
+    plan = nullptr;
+    partials.release();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,8 +290,8 @@ static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
     perm_row_len<<<(n + 1 + 255) / 256, 256, 0, st>>>(m->perm.p, m->row_nnz.p, n, m->rp.p);
     GSB_KERNEL_CHECK();
     GSB_TRY(gsb_exclusive_scan_i32(m->rp.p, m->rp.p, (int64_t)n + 1, nullptr, st));
-    GSB_TRY(m->ci.alloc(m->nnz));
-    GSB_TRY(m->va.alloc(m->nnz));
+    GSB_TRY(m->ci.alloc(m->nnz + 8)); // +8: the staged kernel's 16-byte aligned bulk copies may over-read
+    GSB_TRY(m->va.alloc(m->nnz + 8));
     perm_fill_rows<<<(n + 127) / 128, 128, 0, st>>>(m->perm.p, m->iperm.p, m->row_begin.p, m->row_nnz.p, m->cols.p,
                                                    m->vals(), n, m->rp.p, m->ci.p, m->va.p);
     GSB_KERNEL_CHECK();

@@ -1,0 +1,398 @@
+// gsb_phase.cu -- the Gauss-Seidel colour-phase kernels and their launch plan.
+//
+// A colour phase updates the contiguous row range [row0,row1) of a colour-major CSR; rows of one
+// colour never read each other, so every row is independent inside the phase:
+//     x_i <- (b_i - sum_{j != i} a_ij x_j) / a_ii        (v2 :359-374, zero diagonal -> row skipped)
+// Products and sums are rounded separately, in storage order (no FMA), as the reference's build does.
+//
+// Two kernels:
+//   gs_phase_direct  row per thread, CSR read straight from global memory.  Simple; latency bound
+//                    (three dependent load levels, 40-byte-stride accesses to values/columns).
+//   gs_phase_staged  one CTA per tile of <= 256 rows.  The tile's slice of `values` and `columns` is
+//                    one contiguous span of the CSR arrays, so an elected thread fetches it with two
+//                    1-D bulk async copies (cp.async.bulk, the TMA engine, completion on an mbarrier)
+//                    into shared memory while all threads issue their coalesced row-pointer / b / x_old
+//                    loads.  Rows are then walked out of shared memory and only the x gathers touch
+//                    global memory; for short rows all gathers of a row are issued before the first is
+//                    consumed.  HBM sees long contiguous bursts instead of 32-byte sectors.
+// The stop rule's L1 update norm is accumulated per block into `partials` (fixed order, no atomics).
+#include "gsb_internal.cuh"
+
+#define GS_THREADS 256
+#define GS_TILE_CAP_MAX 6144 // CSR entries per tile that still leave >= 3 CTAs per SM (72 KB each)
+#define GS_UNROLL 6          // rows up to this length take the gather-prefetch path (5-point rows have <= 5)
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1: row per thread, direct global loads
+// ---------------------------------------------------------------------------------------------
+template <int NRHS, bool CHECK>
+__global__ void __launch_bounds__(GS_THREADS)
+    gs_phase_direct(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                    const double *__restrict__ b, double *x, int64_t n, int row0, int row1,
+                    const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
+    if (*(volatile const int *)&ctl->done) return;
+    const int i = row0 + blockIdx.x * GS_THREADS + threadIdx.x;
+    double diff[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
+    if (i < row1) {
+        const int k0 = rp[i], k1 = rp[i + 1];
+        double sig[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+        double d = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const int c = ci[k];
+            const double v = va[k];
+            if (c == i) {
+                d = v;
+            } else {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, x[r * n + c]));
+            }
+        }
+        if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                const double xn = __ddiv_rn(__dsub_rn(b[r * n + i], sig[r]), d);
+                if (CHECK) diff[r] = fabs(xn - x[r * n + i]);
+                x[r * n + i] = xn;
+            }
+        }
+    }
+    if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)blockIdx.x * NRHS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2: bulk-copy staged CSR tiles
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+template <int NRHS, bool CHECK>
+__global__ void __launch_bounds__(GS_THREADS, 4)
+    gs_phase_staged(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                    const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int tile_rows,
+                    const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
+                    double *__restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *va_s = reinterpret_cast<double *>(smem_raw + 16);
+    int *ci_s = reinterpret_cast<int *>(smem_raw + 16 + (size_t)cap * 8);
+    if (*(volatile const int *)&ctl->done) return;
+
+    const int t = blockIdx.x;
+    const int r_begin = row0 + t * tile_rows;
+    const int r_end = min(r_begin + tile_rows, row1);
+    const int k0 = tile_k[t], k1 = tile_k[t + 1];
+    const int kv0 = k0 & ~1, kc0 = k0 & ~3; // 16-byte aligned starts of the two spans
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+        const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+        mbar_expect_tx(mbar, bytes_v + bytes_c);
+        if (bytes_v) bulk_g2s(va_s, va + kv0, bytes_v, mbar);
+        if (bytes_c) bulk_g2s(ci_s, ci + kc0, bytes_c, mbar);
+    }
+    // coalesced per-row loads overlap the bulk copies
+    const int i = r_begin + threadIdx.x;
+    const bool valid = threadIdx.x < tile_rows && i < r_end;
+    int rs = 0, re = 0;
+    double bb[NRHS], xo[NRHS], diff[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) bb[r] = xo[r] = diff[r] = 0.0;
+    if (valid) {
+        rs = rp[i];
+        re = rp[i + 1];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            bb[r] = b[r * n + i];
+            if (CHECK) xo[r] = x[r * n + i];
+        }
+    }
+    mbar_wait(mbar, 0);
+
+    if (valid) {
+        const int len = re - rs;
+        const double *vrow = va_s + (rs - kv0);
+        const int *crow = ci_s + (rs - kc0);
+        double sig[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+        double d = 0.0;
+        if (len <= GS_UNROLL) {
+            int cc[GS_UNROLL];
+            double vv[GS_UNROLL], xg[GS_UNROLL][NRHS];
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j) {
+                const bool on = j < len;
+                cc[j] = on ? crow[j] : i;
+                vv[j] = on ? vrow[j] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j) { // every gather of the row is in flight before the first use
+                const bool off = j < len && cc[j] != i;
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? x[r * n + cc[j]] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j) {
+                if (j < len) {
+                    if (cc[j] == i) {
+                        d = vv[j];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(vv[j], xg[j][r]));
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < len; ++j) {
+                const int c = crow[j];
+                const double v = vrow[j];
+                if (c == i) {
+                    d = v;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, x[r * n + c]));
+                }
+            }
+        }
+        if (d != 0.0) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                const double xn = __ddiv_rn(__dsub_rn(bb[r], sig[r]), d);
+                if (CHECK) diff[r] = fabs(xn - xo[r]);
+                x[r * n + i] = xn;
+            }
+        }
+    }
+    if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)blockIdx.x * NRHS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// end of sweep: fold the partials (fixed order), update the control block
+//   mode 0: fold, bump the counter, decide (single GPU)
+//   mode 1: fold into ctl->eps_last only (strip solver, before the all-reduce)
+//   mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
+// ---------------------------------------------------------------------------------------------
+template <int NRHS>
+__global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *__restrict__ partials, int n_partials,
+                                                     int checked, int mode) {
+    if (ctl->done) return;
+    if (mode == 2) {
+        if (threadIdx.x == 0) {
+            bool all_ok = checked != 0;
+            if (checked)
+                for (int r = 0; r < NRHS; ++r)
+                    if (ctl->eps_last[r] > ctl->epsilon) all_ok = false;
+            const int cnt = ctl->sweeps + 1;
+            ctl->sweeps = cnt;
+            if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
+        }
+        return;
+    }
+    __shared__ double ws[NRHS][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (checked) {
+        double s[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += 1024) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) s[r] += partials[(size_t)i * NRHS + r];
+        }
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            double t = s[r];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+            if (lane == 0) ws[r][wid] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool all_ok = checked != 0;
+        if (checked) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                double t = 0.0;
+                for (int w = 0; w < 32; ++w) t += ws[r][w];
+                ctl->eps_last[r] = t;
+                if (t > ctl->epsilon) all_ok = false; // v2 :356: the loop continues while eps > epsilon
+            }
+        }
+        if (mode == 1) return;
+        const int cnt = ctl->sweeps + 1;
+        ctl->sweeps = cnt;
+        if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
+    }
+}
+
+int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
+                         cudaStream_t st) {
+    switch (nrhs) {
+        case 1: gs_end_sweep<1><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 2: gs_end_sweep<2><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 3: gs_end_sweep<3><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 4: gs_end_sweep<4><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        default: return GSB_ERR_ARG;
+    }
+    GSB_KERNEL_CHECK();
+    return GSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch plan
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, int row0, int row1, int tile_rows,
+                                                   int ntiles, int *__restrict__ out, int *__restrict__ max_nnz) {
+    int t = blockIdx.x * 256 + threadIdx.x;
+    if (t > ntiles) return;
+    int r = min(row0 + t * tile_rows, row1);
+    int k = rp[r];
+    out[t] = k;
+    if (t < ntiles) {
+        int r2 = min(row0 + (t + 1) * tile_rows, row1);
+        atomicMax(max_nnz, rp[r2] - k);
+    }
+}
+
+int GsbPlan::total_blocks() const {
+    int s = 0;
+    for (int c = 0; c < n_colors; ++c) s += blocks[c];
+    return s;
+}
+
+int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colors, int kernel_request,
+                   cudaStream_t st) {
+    p->n_colors = n_colors;
+    p->requested = kernel_request;
+    for (int c = 0; c <= n_colors; ++c) p->color_start[c] = color_start[c];
+    p->kernel = 1;
+    p->tile_rows = GS_THREADS;
+    p->smem_bytes = 0;
+    if (kernel_request != 1) {
+        DevBuf<int> mx;
+        GSB_TRY(mx.alloc(1));
+        for (int tile_rows = GS_THREADS; tile_rows >= 32; tile_rows >>= 1) {
+            int total = 0;
+            for (int c = 0; c < n_colors; ++c) {
+                int rows = color_start[c + 1] - color_start[c];
+                p->blocks[c] = (rows + tile_rows - 1) / tile_rows;
+                p->tile_off[c] = total;
+                total += p->blocks[c] + 1;
+            }
+            GSB_TRY(p->tile_k.alloc(total));
+            GSB_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), st));
+            for (int c = 0; c < n_colors; ++c) {
+                if (!p->blocks[c]) continue;
+                plan_tile_k<<<(p->blocks[c] + 1 + 255) / 256, 256, 0, st>>>(rp, color_start[c], color_start[c + 1],
+                                                                          tile_rows, p->blocks[c],
+                                                                          p->tile_k.p + p->tile_off[c], mx.p);
+                GSB_KERNEL_CHECK();
+            }
+            int h = 0;
+            GSB_CUDA(cudaMemcpyAsync(&h, mx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GSB_CUDA(cudaStreamSynchronize(st));
+            if (h <= GS_TILE_CAP_MAX) {
+                p->kernel = 2;
+                p->tile_rows = tile_rows;
+                p->cap = ((h + 8) + 3) & ~3;
+                p->smem_bytes = 16 + p->cap * 12;
+                break;
+            }
+        }
+        if (p->kernel != 2 && kernel_request == 2) {
+            gsb_set_error("staged kernel needs <= %d entries per 32 rows; use kernel 0/1", GS_TILE_CAP_MAX);
+            return GSB_ERR_ARG;
+        }
+    }
+    if (p->kernel == 1) {
+        p->tile_k.release();
+        for (int c = 0; c < n_colors; ++c)
+            p->blocks[c] = (color_start[c + 1] - color_start[c] + GS_THREADS - 1) / GS_THREADS;
+    }
+    p->valid = true;
+    return GSB_OK;
+}
+
+template <int NRHS>
+static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
+                         double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials, cudaStream_t st) {
+    const int nb = p->blocks[c];
+    if (nb <= 0) return GSB_OK;
+    const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
+    if (p->kernel == 2) {
+        auto kt = gs_phase_staged<NRHS, true>;
+        auto kf = gs_phase_staged<NRHS, false>;
+        if (p->smem_bytes > 48 * 1024) {
+            static bool set_t[8] = {false}, set_f[8] = {false};
+            bool &flag = check ? set_t[NRHS] : set_f[NRHS];
+            if (!flag) {
+                GSB_CUDA(cudaFuncSetAttribute(check ? (const void *)kt : (const void *)kf,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 16 + GS_TILE_CAP_MAX * 12 + 256));
+                flag = true;
+            }
+        }
+        const int *tk = p->tile_k.p + p->tile_off[c];
+        if (check)
+            kt<<<nb, GS_THREADS, p->smem_bytes, st>>>(rp, ci, va, b, x, ld, row0, row1, p->tile_rows, tk, p->cap, ctl,
+                                                       partials);
+        else
+            kf<<<nb, GS_THREADS, p->smem_bytes, st>>>(rp, ci, va, b, x, ld, row0, row1, p->tile_rows, tk, p->cap, ctl,
+                                                       partials);
+    } else {
+        if (check)
+            gs_phase_direct<NRHS, true><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
+        else
+            gs_phase_direct<NRHS, false><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
+    }
+    GSB_KERNEL_CHECK();
+    return GSB_OK;
+}
+
+int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
+                    double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
+                    cudaStream_t st) {
+    switch (nrhs) {
+        case 1: return plan_launch_t<1>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
+        case 2: return plan_launch_t<2>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
+        case 3: return plan_launch_t<3>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
+        case 4: return plan_launch_t<4>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
+    }
+    gsb_set_error("nrhs must be 1..%d", GSB_MAX_RHS);
+    return GSB_ERR_ARG;
+}

@@ -16,171 +16,7 @@
 #include <math.h>
 #include <new>
 
-#define GS_THREADS 256
 #define MAX_RHS GSB_MAX_RHS
-
-// ---------------------------------------------------------------------------------------------
-// block reduction helper (fixed order -> deterministic partials)
-// ---------------------------------------------------------------------------------------------
-template <int NRHS>
-__device__ __forceinline__ void block_reduce_store(double (&v)[NRHS], double *__restrict__ out) {
-    __shared__ double ws[NRHS][GS_THREADS / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) {
-        double t = v[r];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
-        if (lane == 0) ws[r][wid] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x < NRHS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < GS_THREADS / 32; ++w) s += ws[threadIdx.x][w];
-        out[threadIdx.x] = s;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernel 1: row-per-thread, direct global loads
-// ---------------------------------------------------------------------------------------------
-template <int NRHS, bool CHECK>
-__global__ void __launch_bounds__(GS_THREADS)
-    gs_phase_direct(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                    const double *__restrict__ b, double *x, int64_t n, int row0, int row1,
-                    const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
-    if (*(volatile const int *)&ctl->done) return;
-    const int i = row0 + blockIdx.x * GS_THREADS + threadIdx.x;
-    double diff[NRHS];
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
-    if (i < row1) {
-        const int k0 = rp[i], k1 = rp[i + 1];
-        double sig[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
-        double d = 0.0;
-        for (int k = k0; k < k1; ++k) {
-            const int c = ci[k];
-            const double v = va[k];
-            if (c == i) {
-                d = v;
-            } else {
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, x[r * n + c]));
-            }
-        }
-        if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) {
-                const double xn = __ddiv_rn(__dsub_rn(b[r * n + i], sig[r]), d);
-                if (CHECK) diff[r] = fabs(xn - x[r * n + i]);
-                x[r * n + i] = xn;
-            }
-        }
-    }
-    if (CHECK) block_reduce_store<NRHS>(diff, partials + (size_t)blockIdx.x * NRHS);
-}
-
-// ---------------------------------------------------------------------------------------------
-// end of sweep: fold the partials (fixed order), update the control block
-// ---------------------------------------------------------------------------------------------
-template <int NRHS>
-__global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *__restrict__ partials, int n_partials,
-                                                     int checked, int mode) {
-    if (ctl->done) return;
-    if (mode == 2) { // strip solver, after the all-reduce of eps_last
-        if (threadIdx.x == 0) {
-            bool all_ok = checked != 0;
-            if (checked)
-                for (int r = 0; r < NRHS; ++r)
-                    if (ctl->eps_last[r] > ctl->epsilon) all_ok = false;
-            const int cnt = ctl->sweeps + 1;
-            ctl->sweeps = cnt;
-            if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
-        }
-        return;
-    }
-    __shared__ double ws[NRHS][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (checked) {
-        double s[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
-        for (int i = threadIdx.x; i < n_partials; i += 1024) {
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) s[r] += partials[(size_t)i * NRHS + r];
-        }
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            double t = s[r];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
-            if (lane == 0) ws[r][wid] = t;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        bool all_ok = checked != 0;
-        if (checked) {
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) {
-                double t = 0.0;
-                for (int w = 0; w < 32; ++w) t += ws[r][w];
-                ctl->eps_last[r] = t;
-                if (t > ctl->epsilon) all_ok = false; // v2 :356: loop continues while eps > epsilon
-            }
-        }
-        if (mode == 1) return; // sums only; the decision follows the all-reduce
-        const int cnt = ctl->sweeps + 1;
-        ctl->sweeps = cnt;
-        if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
-    }
-}
-
-int gsb_phase_blocks(int rows) { return (rows + GS_THREADS - 1) / GS_THREADS; }
-
-template <int NRHS>
-static int launch_phase_t(const int *rp, const int *ci, const double *va, const double *b, double *x, int64_t ld,
-                          int row0, int row1, bool check, int kernel, const GsCtl *ctl, double *partials,
-                          cudaStream_t st) {
-    const int nb = gsb_phase_blocks(row1 - row0);
-    if (nb <= 0) return GSB_OK;
-    (void)kernel;
-    if (check)
-        gs_phase_direct<NRHS, true><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
-    else
-        gs_phase_direct<NRHS, false><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
-    GSB_KERNEL_CHECK();
-    return GSB_OK;
-}
-
-int gsb_launch_phase(const int *rp, const int *ci, const double *va, const double *b, double *x, int64_t ld,
-                     int row0, int row1, int nrhs, bool check, int kernel, const GsCtl *ctl, double *partials,
-                     cudaStream_t st) {
-    switch (nrhs) {
-        case 1: return launch_phase_t<1>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
-        case 2: return launch_phase_t<2>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
-        case 3: return launch_phase_t<3>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
-        case 4: return launch_phase_t<4>(rp, ci, va, b, x, ld, row0, row1, check, kernel, ctl, partials, st);
-    }
-    gsb_set_error("nrhs must be 1..%d", MAX_RHS);
-    return GSB_ERR_ARG;
-}
-
-int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
-                         cudaStream_t st) {
-    switch (nrhs) {
-        case 1: gs_end_sweep<1><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        case 2: gs_end_sweep<2><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        case 3: gs_end_sweep<3><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        case 4: gs_end_sweep<4><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        default: return GSB_ERR_ARG;
-    }
-    GSB_KERNEL_CHECK();
-    return GSB_OK;
-}
 
 // ---------------------------------------------------------------------------------------------
 // vector permutation helpers
@@ -219,20 +55,15 @@ extern "C" void gsb_gs_default_options(gsb_gs_options *o) {
     o->compute_residual = 0;
 }
 
-static int phase_blocks(const gsb_matrix *m, int c) {
-    return gsb_phase_blocks(m->color_start[c + 1] - m->color_start[c]);
-}
-
-static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, int kernel, cudaStream_t st, int64_t *launches) {
+static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, cudaStream_t st, int64_t *launches) {
     GsCtl *ctl = (GsCtl *)m->ctl.p;
     const int64_t n = m->n_rows;
     int poff = 0;
     for (int c = 0; c < m->n_colors; ++c) {
-        const int row0 = m->color_start[c], row1 = m->color_start[c + 1];
-        const int nb = phase_blocks(m, c);
+        const int nb = m->plan->blocks[c];
         if (nb == 0) continue;
-        GSB_TRY(gsb_launch_phase(m->rp.p, m->ci.p, m->va.p, m->bw.p, m->xw.p, n, row0, row1, nrhs, check, kernel, ctl,
-                                 m->partials.p + (size_t)poff * nrhs, st));
+        GSB_TRY(gsb_plan_launch(m->plan, c, m->rp.p, m->ci.p, m->va.p, m->bw.p, m->xw.p, n, nrhs, check, ctl,
+                                m->partials.p + (size_t)poff * nrhs, st));
         poff += nb;
         ++*launches;
     }
@@ -241,19 +72,27 @@ static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, int kernel, cudaSt
     return GSB_OK;
 }
 
-static int ensure_workspace(gsb_matrix *m, int nrhs) {
+static void drop_graph(gsb_matrix *m) {
+    if (m->graph_exec) {
+        cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
+        m->graph_exec = nullptr;
+    }
+}
+
+static int ensure_workspace(gsb_matrix *m, int nrhs, int kernel_request, cudaStream_t st) {
     const int64_t n = m->n_rows;
+    if (!m->plan) m->plan = new (std::nothrow) GsbPlan();
+    if (!m->plan) return GSB_ERR_ALLOC;
+    if (!m->plan->valid || m->plan->requested != kernel_request) {
+        GSB_TRY(gsb_plan_build(m->plan, m->rp.p, m->color_start, m->n_colors, kernel_request, st));
+        GSB_TRY(m->partials.alloc((int64_t)(m->plan->total_blocks() + 1) * MAX_RHS));
+        drop_graph(m);
+    }
     if (m->ws_nrhs < nrhs) {
         GSB_TRY(m->xw.alloc(n * nrhs));
         GSB_TRY(m->bw.alloc(n * nrhs));
-        int total_blocks = 0;
-        for (int c = 0; c < m->n_colors; ++c) total_blocks += phase_blocks(m, c);
-        GSB_TRY(m->partials.alloc((int64_t)(total_blocks + 1) * MAX_RHS));
         m->ws_nrhs = nrhs;
-        if (m->graph_exec) {
-            cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
-            m->graph_exec = nullptr;
-        }
+        drop_graph(m);
     }
     if (!m->ctl.p) GSB_TRY(m->ctl.alloc(sizeof(GsCtl)));
     if (!m->ctl_host) GSB_CUDA(cudaHostAlloc(&m->ctl_host, sizeof(GsCtl), cudaHostAllocDefault));
@@ -289,7 +128,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         cudaEventDestroy(e1);
     }
     const int64_t n = m->n_rows;
-    GSB_TRY(ensure_workspace(m, nrhs));
+    GSB_TRY(ensure_workspace(m, nrhs, opts.kernel, st));
     const int nbv = (int)((n + 255) / 256);
     gather_perm<<<nbv, 256, 0, st>>>(b_dev, m->perm.p, n, nrhs, m->bw.p);
     GSB_KERNEL_CHECK();
@@ -335,7 +174,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         if (todo > batch) todo = batch;
         if (todo <= 0) todo = 1; // cannot happen (done would be set) -- guards an endless loop
         if (use_graph) {
-            int key[6] = {nrhs, batch, 1, 1, m->n_colors, 1};
+            int key[6] = {nrhs, batch, 1, m->plan->kernel, m->n_colors, 1};
             if (!m->graph_exec || memcmp(key, m->graph_key, sizeof(key)) != 0) {
                 if (m->graph_exec) {
                     cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
@@ -344,7 +183,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
                 cudaGraph_t g = nullptr;
                 int64_t dummy = 0;
                 GSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                for (int s = 0; s < batch && status == GSB_OK; ++s) status = enqueue_sweep(m, nrhs, true, opts.kernel, st, &dummy);
+                for (int s = 0; s < batch && status == GSB_OK; ++s) status = enqueue_sweep(m, nrhs, true, st, &dummy);
                 cudaError_t ce = cudaStreamEndCapture(st, &g);
                 if (status != GSB_OK) break;
                 if (ce != cudaSuccess) {
@@ -375,7 +214,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         } else {
             for (int s = 0; s < todo && status == GSB_OK; ++s) {
                 bool check = ((issued + s + 1) % opts.check_every) == 0 || (issued + s + 1) == max_iteration;
-                status = enqueue_sweep(m, nrhs, check, opts.kernel, st, &launches);
+                status = enqueue_sweep(m, nrhs, check, st, &launches);
             }
             issued += todo;
         }
@@ -405,7 +244,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         stats->sweeps = h.sweeps;
         stats->n_colors = m->n_colors;
         stats->ordering_used = m->ordering_used;
-        stats->kernel_used = 1;
+        stats->kernel_used = m->plan->kernel;
         stats->kernel_launches = launches;
         for (int r = 0; r < MAX_RHS; ++r) stats->last_eps[r] = r < nrhs ? h.eps_last[r] : 0.0;
         stats->solve_ms = solve_ms;
@@ -509,7 +348,7 @@ __global__ void __launch_bounds__(256) resid_row_thread(const double *__restrict
         acc += r * r;
     }
     double a1[1] = {acc};
-    block_reduce_store<1>(a1, partial + blockIdx.x);
+    gsb_block_reduce_store<1, 256>(a1, partial + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) resid_row_warp(const double *__restrict__ vals, const int *__restrict__ cols,
@@ -533,7 +372,7 @@ __global__ void __launch_bounds__(256) resid_row_warp(const double *__restrict__
         }
     }
     double a1[1] = {acc};
-    block_reduce_store<1>(a1, partial + blockIdx.x);
+    gsb_block_reduce_store<1, 256>(a1, partial + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) finish_sqrt(const double *__restrict__ partial, int np, double *out) {

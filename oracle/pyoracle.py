@@ -198,12 +198,13 @@ def l1_dist(a, b):
 def poisson_csr(W, H):
     """Closed-form A^T*A of the reference's forward-difference system (compressed CSR)."""
     L = _oracle()
-    nnz = L.orc_poisson_nnz(W, H)
+    nnz = max(int(L.orc_poisson_nnz(W, H)), 1)  # the closed form holds for W,H >= 2; 1-pixel-wide grids keep only the pin
     ro = np.empty(W * H + 1, np.int32)
     ci = np.empty(nnz, np.int32)
     va = np.empty(nnz, np.float64)
     L.orc_poisson_csr(W, H, ro, ci, va)
-    return ro, ci, va
+    k = int(ro[-1])
+    return ro, ci[:k].copy(), va[:k].copy()
 
 
 def poisson_rhs(W, H, gx, gy, constraint):

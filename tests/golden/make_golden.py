@@ -60,9 +60,13 @@ img = wl.synth_image(W, H, 1, seed=7)
 gx, gy = wl.forward_gradients(img)
 bp = pyoracle.poisson_rhs(W, H, gx[0], gy[0], float(img[0, 0, 0]))
 ref = pyoracle.Ref(2, "f64").import_csr(va, ro[:-1], ci, W * H)
+sgx, sgy = wl.seamless_gradients(img)
+bs = pyoracle.poisson_rhs(W, H, sgx[0], sgy[0], float(img[0, 0, 0]))
 out["poisson_8x6"] = {"b": hx(bp), "gs": {str(k): hx(ref.gauss_seidel(bp, 0.0, k)) for k in (1, 10, 100)},
-                      "spmv_of_b": hx(ref.spmv(bp)), "cg_50_init": hx(ref.cg(bp, 1e-10, 50, img[0].ravel().astype(float))),
-                      "pcg_180": hx(ref.pcg(bp, 1e-16, 180))}
+                      "spmv_of_b": hx(ref.spmv(bp)), "b_seamless": hx(bs),
+                      "cg_12": hx(ref.cg(bp, 1e-10, 12)),
+                      "cg_8_init": hx(ref.cg(bs, 1e-10, 8, img[0].ravel().astype(float))),
+                      "pcg_10": hx(ref.pcg(bs, 1e-10, 10))}
 
 # --- uncompressed import (per-row counts) and trailing empty rows ---------------------------------
 rng = np.random.default_rng(4)
