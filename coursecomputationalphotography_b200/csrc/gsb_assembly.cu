@@ -3,7 +3,7 @@
 //   initializeFromEigenRowMajor   -> gsb_matrix_import_csr
 //   at / coeff                    -> gsb_matrix_at                    (batched)
 // plus raw upload/download of the five layout arrays.  Layout parity with the reference is
-// bit-exact; tests/test_assembly_gpu.py checks it against oracle/ and the compiled reference.
+// bit-exact; tests/test_assembly_gpu.py checks it against the CPU checker and the compiled reference.
 #include "gsb_internal.cuh"
 
 #include <new>

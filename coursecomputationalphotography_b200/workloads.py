@@ -3,7 +3,7 @@
 Everything here is input generation: images, gradients as the reference computes them
 (GradientAt, project/src/PhotoMontage/PhotoMontage.cpp:399-408: forward differences of 8-bit
 pixels stored as float32), masks, and CSR systems.  Fixed seeds; the same arrays feed the GPU
-path, the oracle and the compiled reference.
+path and the CPU checkers used by tests/ and bench.py.
 """
 import numpy as np
 

@@ -35,9 +35,9 @@ def test_known_answer_4x4(gsb, oracle_mod):
     xo, sw, _ = o.gauss_seidel(b)
     assert np.abs(x - xo).max() < 1e-6
     assert sp.last_stats.sweeps > 0 and sp.last_stats.last_eps[0] <= 1e-6
-    # dense 4x4: every row touches every other one -> 4 colours, i.e. the lexicographic order itself
+    # rows 0 and 3 are not coupled (a03 = a30 = 0): 3 colours suffice, 4 is the lexicographic order itself
     info = sp.coloring()
-    assert info["n_colors"] == 4
+    assert info["n_colors"] in (3, 4)
     perm, _ = sp.ordering()
     if np.array_equal(perm, np.arange(4)):
         assert np.array_equal(x, xo) and sp.last_stats.sweeps == sw
@@ -263,7 +263,8 @@ def test_full_size_properties_4096(gsb):
     b = np.zeros((3, n))
     b[:, 0] = 1.0  # pin v(0,0) = 1, zero gradients: the solution is the all-ones start vector
     x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=3)
-    assert sp.last_stats.sweeps == 3 and np.all(x == 1.0)
+    # the update is exactly zero, so eps = 0 and `eps > epsilon` (v2 :356) already fails after one sweep
+    assert sp.last_stats.sweeps == 1 and np.all(x == 1.0)
     assert sp.last_stats.last_eps[0] == 0.0
     # (2) linearity of one sweep chain is not exact in floating point, but the residual must fall
     #     monotonically for an SPD system under GS: compare ||b-Ax|| after 2 and after 12 sweeps
