@@ -421,7 +421,7 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     d->ld = base;
 
     // 5. colour-major local CSR
-    GSB_TRY(d->rp.alloc((int64_t)n_local + 1));
+    GSB_TRY(d->rp.alloc((int64_t)n_local + 1 + 8));
     d_perm_len<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(d->perm.p, d->nat_rp.p, n_local, d->rp.p);
     GSB_KERNEL_CHECK();
     GSB_TRY(gsb_exclusive_scan_i32(d->rp.p, d->rp.p, (int64_t)n_local + 1, nullptr, st));
@@ -601,8 +601,8 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         GSB_TRY(d->partials.alloc((int64_t)(d->plan.total_blocks() + 1) * GSB_MAX_RHS));
     }
     if (d->ws_nrhs < nrhs) {
-        GSB_TRY(d->xw.alloc(ld * nrhs));
-        GSB_TRY(d->bw.alloc(ld * nrhs));
+        GSB_TRY(d->xw.alloc(ld * nrhs + 8));
+        GSB_TRY(d->bw.alloc(ld * nrhs + 8));
         d->ws_nrhs = nrhs;
     }
     if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));

@@ -286,7 +286,7 @@ static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
         gsb_set_error("internal: colour classes cover %d of %d rows", base, n);
         return GSB_ERR_COLORING;
     }
-    GSB_TRY(m->rp.alloc((int64_t)n + 1));
+    GSB_TRY(m->rp.alloc((int64_t)n + 1 + 8)); // +8: aligned bulk copies may over-read
     perm_row_len<<<(n + 1 + 255) / 256, 256, 0, st>>>(m->perm.p, m->row_nnz.p, n, m->rp.p);
     GSB_KERNEL_CHECK();
     GSB_TRY(gsb_exclusive_scan_i32(m->rp.p, m->rp.p, (int64_t)n + 1, nullptr, st));

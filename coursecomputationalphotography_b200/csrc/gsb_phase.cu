@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                     const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int tile_rows,
                     const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
                     double *__restrict__ partials) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
     double *va_s = reinterpret_cast<double *>(smem_raw + 16);
     int *ci_s = reinterpret_cast<int *>(smem_raw + 16 + (size_t)cap * 8);
@@ -200,6 +200,173 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         }
     }
     if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)blockIdx.x * NRHS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 3: persistent CTAs, ring of bulk-copy stages
+//
+// gs_phase_staged still exposes one bulk-copy latency plus one gather latency per CTA lifetime.  Here
+// a CTA stays resident, walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... and keeps STAGES tiles
+// in flight: while tile k is computed, the bulk copies of tile k+1 (values, columns, row offsets, and
+// the b / x_old planes -- every per-tile input is a contiguous span) are already landing in the next
+// stage.  The only non-bulk global traffic is the x gathers (read-only path) and the x stores.
+// ---------------------------------------------------------------------------------------------
+#define GS_RING_STAGES 2
+
+struct RingLayout {
+    int va_off, b_off, xo_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
+};
+
+__host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check) {
+    RingLayout L;
+    L.plane = GS_THREADS + 2;
+    L.va_off = 0;
+    L.b_off = L.va_off + cap * 8;
+    L.xo_off = L.b_off + nrhs * L.plane * 8;
+    L.ci_off = L.xo_off + (check ? nrhs * L.plane * 8 : 0);
+    L.rp_off = L.ci_off + cap * 4;
+    L.hdr_off = L.rp_off + (GS_THREADS + 8) * 4;
+    L.stage_bytes = L.hdr_off + 16;
+    return L;
+}
+
+template <int NRHS, bool CHECK>
+__global__ void __launch_bounds__(GS_THREADS, 3)
+    gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                  const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
+                  const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
+                  double *__restrict__ partials) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (ctl->done) return; // written only by gs_end_sweep, i.e. constant for the lifetime of this kernel
+    const RingLayout L = ring_layout(cap, NRHS, CHECK);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    unsigned char *stage0 = smem_raw + 64;
+    const int tid = threadIdx.x;
+
+    auto issue = [&](int t, int s) { // thread 0 only
+        unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+        const int r_begin = row0 + t * GS_THREADS;
+        const int rows = min(GS_THREADS, row1 - r_begin);
+        const int k0 = tile_k[t], k1 = tile_k[t + 1];
+        const int kv0 = k0 & ~1, kc0 = k0 & ~3;
+        const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+        const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+        const int ra = r_begin & ~3;
+        const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
+        uint32_t bytes_p[NRHS];
+        uint32_t total = bytes_v + bytes_c + bytes_r;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            const int64_t e0 = r * n + r_begin;
+            const int64_t ea = e0 & ~(int64_t)1;
+            bytes_p[r] = (uint32_t)(((e0 + rows + 1) & ~(int64_t)1) - ea) * 8u;
+            total += bytes_p[r] * (CHECK ? 2u : 1u);
+        }
+        reinterpret_cast<int *>(st + L.hdr_off)[0] = k0;
+        mbar_expect_tx(&full[s], total);
+        if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
+        if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
+        bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            const int64_t ea = (r * n + r_begin) & ~(int64_t)1;
+            bulk_g2s(st + L.b_off + r * L.plane * 8, b + ea, bytes_p[r], &full[s]);
+            if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + ea, bytes_p[r], &full[s]);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GS_RING_STAGES; ++s) mbar_init(&full[s], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GS_RING_STAGES; ++s) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    int k = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+        const int s = k % GS_RING_STAGES;
+        const uint32_t parity = (uint32_t)(k / GS_RING_STAGES) & 1u;
+        unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+        const int r_begin = row0 + t * GS_THREADS;
+        const int rows = min(GS_THREADS, row1 - r_begin);
+        mbar_wait(&full[s], parity);
+
+        const int k0 = reinterpret_cast<const int *>(st + L.hdr_off)[0];
+        const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
+        const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
+        const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
+        const int i = r_begin + tid;
+        const bool valid = tid < rows;
+        double diff[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
+        if (valid) {
+            const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
+            const double *vrow = va_s + rs;
+            const int *crow = ci_s + rs;
+            double sig[NRHS];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+            double d = 0.0;
+            if (len <= GS_UNROLL) {
+                int cc[GS_UNROLL];
+                double xg[GS_UNROLL][NRHS];
+#pragma unroll
+                for (int j = 0; j < GS_UNROLL; ++j) cc[j] = j < len ? crow[j] : i;
+#pragma unroll
+                for (int j = 0; j < GS_UNROLL; ++j) { // all gathers of the row in flight before the first use
+                    const bool off = cc[j] != i;
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? __ldg(x + r * n + cc[j]) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < GS_UNROLL; ++j) {
+                    if (j < len) {
+                        const double v = vrow[j];
+                        if (cc[j] == i) {
+                            d = v;
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xg[j][r]));
+                        }
+                    }
+                }
+            } else {
+                for (int j = 0; j < len; ++j) {
+                    const int c = crow[j];
+                    const double v = vrow[j];
+                    if (c == i) {
+                        d = v;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, __ldg(x + r * n + c)));
+                    }
+                }
+            }
+            if (d != 0.0) {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    const int po = (int)((r * n + r_begin) & 1) + tid;
+                    const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
+                    const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
+                    if (CHECK) diff[r] = fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
+                    x[r * n + i] = xn;
+                }
+            }
+        }
+        if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
+        __syncthreads(); // every thread is done with stage s (and with the reduction scratch)
+        if (tid == 0) {
+            const int tn = t + GS_RING_STAGES * gridDim.x;
+            if (tn < ntiles) issue(tn, s);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -332,8 +499,16 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colo
                 p->tile_rows = tile_rows;
                 p->cap = ((h + 8) + 3) & ~3;
                 p->smem_bytes = 16 + p->cap * 12;
+                // the ring kernel needs full 256-row tiles and STAGES stages within the 227 KB limit
+                if (tile_rows == GS_THREADS && kernel_request != 2 &&
+                    64 + GS_RING_STAGES * ring_layout(p->cap, GSB_MAX_RHS, true).stage_bytes <= 200 * 1024)
+                    p->kernel = 3;
                 break;
             }
+        }
+        if (p->kernel != 3 && kernel_request == 3) {
+            gsb_set_error("ring kernel unavailable for this matrix (rows too long); use kernel 0/1/2");
+            return GSB_ERR_ARG;
         }
         if (p->kernel != 2 && kernel_request == 2) {
             gsb_set_error("staged kernel needs <= %d entries per 32 rows; use kernel 0/1", GS_TILE_CAP_MAX);
@@ -355,7 +530,28 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     const int nb = p->blocks[c];
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
-    if (p->kernel == 2) {
+    if (p->kernel == 3) {
+        auto kt = gs_phase_ring<NRHS, true>;
+        auto kf = gs_phase_ring<NRHS, false>;
+        const int smem = 64 + GS_RING_STAGES * ring_layout(p->cap, NRHS, check).stage_bytes;
+        static int set_t[8] = {0}, set_f[8] = {0};
+        int &have = check ? set_t[NRHS] : set_f[NRHS];
+        if (smem > 48 * 1024 && have < smem) {
+            GSB_CUDA(cudaFuncSetAttribute(check ? (const void *)kt : (const void *)kf,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            have = smem;
+        }
+        int per_sm = (220 * 1024) / (smem + 1024);
+        if (per_sm > 3) per_sm = 3;
+        if (per_sm < 1) per_sm = 1;
+        int grid = gsb_sm_count() * per_sm;
+        if (grid > nb) grid = nb;
+        const int *tk = p->tile_k.p + p->tile_off[c];
+        if (check)
+            kt<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);
+        else
+            kf<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);
+    } else if (p->kernel == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;
         if (p->smem_bytes > 48 * 1024) {

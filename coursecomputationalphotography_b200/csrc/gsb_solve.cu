@@ -89,8 +89,8 @@ static int ensure_workspace(gsb_matrix *m, int nrhs, int kernel_request, cudaStr
         drop_graph(m);
     }
     if (m->ws_nrhs < nrhs) {
-        GSB_TRY(m->xw.alloc(n * nrhs));
-        GSB_TRY(m->bw.alloc(n * nrhs));
+        GSB_TRY(m->xw.alloc(n * nrhs + 8)); // +8: aligned bulk copies may over-read
+        GSB_TRY(m->bw.alloc(n * nrhs + 8));
         m->ws_nrhs = nrhs;
         drop_graph(m);
     }
