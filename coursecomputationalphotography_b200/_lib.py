@@ -78,6 +78,8 @@ SIGNATURES = {
     "gsb_poisson_matrix": [_vp, _i, _i],
     "gsb_poisson_rhs": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "gsb_poisson_rhs_dev": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "gsb_poisson_rhs_rows": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "gsb_poisson_rhs_rows_dev": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "gsb_writeback_u8": [_vp, _i64, _vp],
     "gsb_writeback_u8_dev": [_vp, _i64, _vp],
     "gsb_dist_unique_id": [_vp],

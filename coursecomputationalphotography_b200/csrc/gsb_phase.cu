@@ -18,6 +18,8 @@
 // The stop rule's L1 update norm is accumulated per block into `partials` (fixed order, no atomics).
 #include "gsb_internal.cuh"
 
+#include <stdlib.h>
+
 #define GS_THREADS 256
 #define GS_TILE_CAP_MAX 6144 // CSR entries per tile that still leave >= 3 CTAs per SM (72 KB each)
 #define GS_UNROLL 6          // rows up to this length take the gather-prefetch path (5-point rows have <= 5)
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 // the b / x_old planes -- every per-tile input is a contiguous span) are already landing in the next
 // stage.  The only non-bulk global traffic is the x gathers (read-only path) and the x stores.
 // ---------------------------------------------------------------------------------------------
-#define GS_RING_STAGES 2
+#define GS_RING_STAGES_DEFAULT 2
+#define GS_RING_STAGES_MAX 4
 
 struct RingLayout {
     int va_off, b_off, xo_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
@@ -230,8 +233,8 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check)
     return L;
 }
 
-template <int NRHS, bool CHECK>
-__global__ void __launch_bounds__(GS_THREADS, 3)
+template <int NRHS, bool CHECK, int STAGES>
+__global__ void __launch_bounds__(GS_THREADS, 4)
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
                   const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
@@ -277,12 +280,12 @@ __global__ void __launch_bounds__(GS_THREADS, 3)
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GS_RING_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     }
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GS_RING_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             const int t = blockIdx.x + s * gridDim.x;
             if (t < ntiles) issue(t, s);
         }
@@ -290,8 +293,8 @@ __global__ void __launch_bounds__(GS_THREADS, 3)
 
     int k = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
-        const int s = k % GS_RING_STAGES;
-        const uint32_t parity = (uint32_t)(k / GS_RING_STAGES) & 1u;
+        const int s = k % STAGES;
+        const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(GS_THREADS, 3)
         if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
         __syncthreads(); // every thread is done with stage s (and with the reduction scratch)
         if (tid == 0) {
-            const int tn = t + GS_RING_STAGES * gridDim.x;
+            const int tn = t + STAGES * gridDim.x;
             if (tn < ntiles) issue(tn, s);
         }
     }
@@ -501,7 +504,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colo
                 p->smem_bytes = 16 + p->cap * 12;
                 // the ring kernel needs full 256-row tiles and STAGES stages within the 227 KB limit
                 if (tile_rows == GS_THREADS && kernel_request != 2 &&
-                    64 + GS_RING_STAGES * ring_layout(p->cap, GSB_MAX_RHS, true).stage_bytes <= 200 * 1024)
+                    64 + 2 * ring_layout(p->cap, GSB_MAX_RHS, true).stage_bytes <= 200 * 1024)
                     p->kernel = 3;
                 break;
             }
@@ -531,26 +534,43 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
     if (p->kernel == 3) {
-        auto kt = gs_phase_ring<NRHS, true>;
-        auto kf = gs_phase_ring<NRHS, false>;
-        const int smem = 64 + GS_RING_STAGES * ring_layout(p->cap, NRHS, check).stage_bytes;
-        static int set_t[8] = {0}, set_f[8] = {0};
-        int &have = check ? set_t[NRHS] : set_f[NRHS];
-        if (smem > 48 * 1024 && have < smem) {
-            GSB_CUDA(cudaFuncSetAttribute(check ? (const void *)kt : (const void *)kf,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            have = smem;
+        // tuning knobs (defaults measured on B200, see profiles/README.md); overridable for experiments
+        static int env_stages = -1, env_ctas = -1;
+        if (env_stages < 0) {
+            const char *e = getenv("GSB_RING_STAGES");
+            env_stages = e ? atoi(e) : 0;
+            e = getenv("GSB_RING_CTAS");
+            env_ctas = e ? atoi(e) : 0;
         }
-        int per_sm = (220 * 1024) / (smem + 1024);
-        if (per_sm > 3) per_sm = 3;
+        const int stage_bytes = ring_layout(p->cap, NRHS, check).stage_bytes;
+        int stages = env_stages ? env_stages : GS_RING_STAGES_DEFAULT;
+        if (stages < 2) stages = 2;
+        if (stages > GS_RING_STAGES_MAX) stages = GS_RING_STAGES_MAX;
+        while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
+        const int smem = 64 + stages * stage_bytes;
+        int per_sm = (225 * 1024) / (smem + 1024);
+        const int want = env_ctas ? env_ctas : 3;
+        if (per_sm > want) per_sm = want;
+        if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
         const int *tk = p->tile_k.p + p->tile_off[c];
-        if (check)
-            kt<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);
-        else
-            kf<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);
+#define GSB_RING_LAUNCH(ST)                                                                                      \
+    {                                                                                                            \
+        auto kern = check ? (void (*)(const int *, const int *, const double *, const double *, double *, int64_t, \
+                                      int, int, int, const int *, int, const GsCtl *, double *))                 \
+                                gs_phase_ring<NRHS, true, ST>                                                   \
+                          : gs_phase_ring<NRHS, false, ST>;                                                     \
+        static int have[2] = {0, 0};                                                                             \
+        if (smem > 48 * 1024 && have[check ? 1 : 0] < smem) {                                                    \
+            GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            have[check ? 1 : 0] = smem;                                                                          \
+        }                                                                                                        \
+        kern<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);    \
+    }
+        if (stages == 2) GSB_RING_LAUNCH(2) else if (stages == 3) GSB_RING_LAUNCH(3) else GSB_RING_LAUNCH(4)
+#undef GSB_RING_LAUNCH
     } else if (p->kernel == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;

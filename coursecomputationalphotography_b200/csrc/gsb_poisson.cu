@@ -125,57 +125,78 @@ extern "C" int gsb_poisson_matrix(gsb_matrix *m, int W, int H) {
 
 // A^T*b, summed in ascending equation order (gy above, gx left, gx here, gy here, pin) with
 // separate roundings -- the order a row-major sparse product visits column p of A.
-__global__ void __launch_bounds__(256) poisson_rhs_kernel(int W, int H, int nch, const float *__restrict__ gx,
-                                                          const float *__restrict__ gy, double c0, double c1,
-                                                          double c2, double c3, double *__restrict__ b) {
-    const int64_t n = (int64_t)W * H;
-    int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (p >= n) return;
+// Rows [y0,y1) of the image; gx/gy hold image rows [ybase, y1) (ybase = max(y0-1,0)), one plane per channel.
+__global__ void __launch_bounds__(256) poisson_rhs_kernel(int W, int H, int y0, int y1, int ybase, int nch,
+                                                          const float *__restrict__ gx, const float *__restrict__ gy,
+                                                          double c0, double c1, double c2, double c3,
+                                                          double *__restrict__ b) {
+    const int64_t n_local = (int64_t)W * (y1 - y0);
+    const int64_t plane = (int64_t)W * (y1 - ybase);
+    int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= n_local) return;
+    const int64_t p = (int64_t)y0 * W + q;               // global pixel
+    const int64_t g = p - (int64_t)ybase * W;            // index inside the gradient planes
     int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
     PoissonEdges e = poisson_edges(x, y, W, H);
     for (int ch = 0; ch < nch; ++ch) {
-        const float *GX = gx + ch * n, *GY = gy + ch * n;
+        const float *GX = gx + ch * plane, *GY = gy + ch * plane;
         double s = 0.0;
-        if (e.u) s = __dadd_rn(s, (double)GY[p - W]);
-        if (e.l) s = __dadd_rn(s, (double)GX[p - 1]);
-        if (e.r) s = __dsub_rn(s, (double)GX[p]);
-        if (e.d) s = __dsub_rn(s, (double)GY[p]);
+        if (e.u) s = __dadd_rn(s, (double)GY[g - W]);
+        if (e.l) s = __dadd_rn(s, (double)GX[g - 1]);
+        if (e.r) s = __dsub_rn(s, (double)GX[g]);
+        if (e.d) s = __dsub_rn(s, (double)GY[g]);
         if (p == 0) s = __dadd_rn(s, ch == 0 ? c0 : ch == 1 ? c1 : ch == 2 ? c2 : c3);
-        b[ch * n + p] = s;
+        b[ch * n_local + q] = s;
     }
 }
 
-extern "C" int gsb_poisson_rhs_dev(int W, int H, int nch, const float *gx_dev, const float *gy_dev,
-                                   const double *constraint, double *b_dev) {
-    if (W < 1 || H < 1 || nch < 1 || nch > 4 || !gx_dev || !gy_dev || !constraint || !b_dev) return GSB_ERR_ARG;
+extern "C" int gsb_poisson_rhs_rows_dev(int W, int H, int y0, int y1, int nch, const float *gx_rows_dev,
+                                        const float *gy_rows_dev, const double *constraint, double *b_dev) {
+    if (W < 1 || H < 1 || y0 < 0 || y1 > H || y0 >= y1 || nch < 1 || nch > 4 || !gx_rows_dev || !gy_rows_dev ||
+        !constraint || !b_dev)
+        return GSB_ERR_ARG;
     GSB_TRY(gsb_ensure_device());
     cudaStream_t st = gsb_cur_stream();
-    const int64_t n = (int64_t)W * H;
+    const int64_t n_local = (int64_t)W * (y1 - y0);
+    const int ybase = y0 > 0 ? y0 - 1 : 0;
     double c[4] = {0, 0, 0, 0};
     for (int i = 0; i < nch; ++i) c[i] = constraint[i];
-    poisson_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, H, nch, gx_dev, gy_dev, c[0], c[1], c[2], c[3],
-                                                                   b_dev);
+    poisson_rhs_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(W, H, y0, y1, ybase, nch, gx_rows_dev,
+                                                                         gy_rows_dev, c[0], c[1], c[2], c[3], b_dev);
     GSB_KERNEL_CHECK();
     return GSB_OK;
 }
 
-extern "C" int gsb_poisson_rhs(int W, int H, int nch, const float *gx, const float *gy, const double *constraint,
-                               double *b_out) {
-    if (W < 1 || H < 1 || nch < 1 || nch > 4 || !gx || !gy || !constraint || !b_out) return GSB_ERR_ARG;
+extern "C" int gsb_poisson_rhs_rows(int W, int H, int y0, int y1, int nch, const float *gx_rows, const float *gy_rows,
+                                    const double *constraint, double *b_out) {
+    if (W < 1 || H < 1 || y0 < 0 || y1 > H || y0 >= y1 || nch < 1 || nch > 4 || !gx_rows || !gy_rows || !constraint ||
+        !b_out)
+        return GSB_ERR_ARG;
     GSB_TRY(gsb_ensure_device());
     cudaStream_t st = gsb_cur_stream();
-    const int64_t n = (int64_t)W * H * nch;
+    const int ybase = y0 > 0 ? y0 - 1 : 0;
+    const int64_t ng = (int64_t)W * (y1 - ybase) * nch, nb = (int64_t)W * (y1 - y0) * nch;
     DevBuf<float> dgx, dgy;
     DevBuf<double> db;
-    GSB_TRY(dgx.alloc(n));
-    GSB_TRY(dgy.alloc(n));
-    GSB_TRY(db.alloc(n));
-    GSB_CUDA(cudaMemcpyAsync(dgx.p, gx, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
-    GSB_CUDA(cudaMemcpyAsync(dgy.p, gy, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
-    GSB_TRY(gsb_poisson_rhs_dev(W, H, nch, dgx.p, dgy.p, constraint, db.p));
-    GSB_CUDA(cudaMemcpyAsync(b_out, db.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    GSB_TRY(dgx.alloc(ng));
+    GSB_TRY(dgy.alloc(ng));
+    GSB_TRY(db.alloc(nb));
+    GSB_CUDA(cudaMemcpyAsync(dgx.p, gx_rows, sizeof(float) * (size_t)ng, cudaMemcpyHostToDevice, st));
+    GSB_CUDA(cudaMemcpyAsync(dgy.p, gy_rows, sizeof(float) * (size_t)ng, cudaMemcpyHostToDevice, st));
+    GSB_TRY(gsb_poisson_rhs_rows_dev(W, H, y0, y1, nch, dgx.p, dgy.p, constraint, db.p));
+    GSB_CUDA(cudaMemcpyAsync(b_out, db.p, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
     return GSB_OK;
+}
+
+extern "C" int gsb_poisson_rhs_dev(int W, int H, int nch, const float *gx_dev, const float *gy_dev,
+                                   const double *constraint, double *b_dev) {
+    return gsb_poisson_rhs_rows_dev(W, H, 0, H, nch, gx_dev, gy_dev, constraint, b_dev);
+}
+
+extern "C" int gsb_poisson_rhs(int W, int H, int nch, const float *gx, const float *gy, const double *constraint,
+                               double *b_out) {
+    return gsb_poisson_rhs_rows(W, H, 0, H, nch, gx, gy, constraint, b_out);
 }
 
 // A10: uchar(max(min(v, 255), 0)), truncating (PhotoMontage.cpp:622)

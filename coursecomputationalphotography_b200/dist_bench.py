@@ -1,0 +1,116 @@
+"""The N > 1 leg of bench.py: 4096^2 x 3-channel Poisson system split into row strips, one rank per GPU."""
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run(args, pkg, wl, dist, rank, world, local):
+    import torch
+    from . import strips
+    from bench import ClockSampler, algorithmic_bytes_per_sweep, peaks
+
+    L = pkg.load()
+    dev = torch.device("cuda", local)
+    uid = strips.broadcast_unique_id(dist, rank, dev)
+    W = H = args.size
+    ch = args.channels
+    y0, y1 = wl.strip_bounds(H, world)[rank]
+    solver = strips.StripSolver(uid, rank, world, local)
+    solver.poisson_strip(W, H, y0, y1)
+    n_local = W * (y1 - y0)
+    n = W * H
+    nnz = wl.poisson_nnz(W, H)
+    b_host = strips.strip_rhs(W, H, ch, y0, y1)
+    b_dev = torch.from_numpy(b_host).to(dev)
+    x_dev = torch.empty_like(b_dev)
+    opts = pkg.SparseMatrix.options(check_every=args.check_every, kernel=args.kernel)
+    stream = torch.cuda.ExternalStream(L.gsb_stream())
+
+    def step():
+        return solver.gauss_seidel_dev(b_dev.data_ptr(), x_dev.data_ptr(), ch, 0.0, args.sweeps, opts)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, solve_ms, sweeps_done = 0, 0.0, 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = step()
+        launches += st.kernel_launches
+        solve_ms += st.solve_ms
+        sweeps_done += st.sweeps
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1), solve_ms, float(launches)], device=dev, dtype=torch.float64)
+    mx = ms.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = ms.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    total_ms, solve_ms_max = float(mx[0]), float(mx[1])
+    clocks = sampler.stop() if rank == 0 else None
+    resid = [solver.residual_dev(b_dev[c].data_ptr(), x_dev[c].data_ptr()) for c in range(ch)]
+
+    # e2e: public API with host buffers: strip matrix generation + b H2D + sweeps + x D2H, every step
+    e2e = None
+    if not args.no_e2e:
+        bh = torch.from_numpy(b_host).pin_memory()
+        xh = torch.empty_like(bh).pin_memory()
+        steps_e2e = max(1, args.e2e_steps)
+        t_acc = 0.0
+        for it in range(steps_e2e + 1):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            solver.poisson_strip(W, H, y0, y1)
+            bd = bh.to(dev, non_blocking=True)
+            torch.cuda.synchronize()
+            xd = torch.empty_like(bd)
+            solver.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, args.sweeps, opts)
+            xh.copy_(xd)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if it > 0:
+                t_acc += time.perf_counter() - t0
+        tt = torch.tensor([t_acc], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nnz * ch * args.sweeps * steps_e2e / float(tt[0]) / 1e9, "unit": "Gnnz/s",
+               "h2d_bytes_per_step": int(b_host.nbytes) * world, "d2h_bytes_per_step": int(b_host.nbytes) * world,
+               "ms_per_step": float(tt[0]) / steps_e2e * 1e3, "steps": steps_e2e,
+               "includes": "strip matrix generation + ordering + halo setup + b H2D + sweeps + x D2H (all ranks)"}
+
+    if rank == 0:
+        assert sweeps_done == args.sweeps * args.steps
+        value = nnz * ch * sweeps_done / (total_ms * 1e-3) / 1e9
+        peak, peak_src = peaks()
+        abytes = algorithmic_bytes_per_sweep(nnz, n, ch) / world  # per GPU
+        per_launch_ms = solve_ms_max / (sweeps_done * 2)
+        achieved = (abytes / 2) / (per_launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "gauss_seidel_throughput", "value": value, "unit": "Gnnz/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2]), %d row strips" % (W, H, ch, world),
+                       "n": n, "nnz": int(nnz), "sweeps_per_step": args.sweeps, "ordering": "red-black (global parity)",
+                       "check_every": args.check_every, "halo": "1 image row per neighbour per colour phase, NCCL send/recv",
+                       "l2": "per-GPU working set %.2f GB per sweep" % (abytes / 1e9),
+                       "sweeps_per_s": sweeps_done / (total_ms * 1e-3), "residual_l2": resid},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "gs_phase per GPU incl. halo exchange gaps", "peak_source": peak_src,
+                         "avg_launch_ms": per_launch_ms},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sm[2]), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    solver.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -47,18 +47,31 @@ def coo_to_csr(rows, cols, vals, n):
 
 
 # ---- images and gradients -------------------------------------------------------------------------
-def synth_image(W, H, channels=1, seed=7):
-    """uint8 image: smooth low-frequency field plus a vertical seam step (two 'exposures')."""
+def _pixel_noise(x, y, c, seed):
+    """Deterministic per-pixel noise in -3..3 (integer hash), so any row range can be generated on its own."""
+    h = (x.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + y.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+         + np.uint64((c * 0x165667B19E3779F9 + seed * 0x27D4EB2F165667C5) & 0xFFFFFFFFFFFFFFFF))
+    h ^= h >> np.uint64(29)
+    h *= np.uint64(0xBF58476D1CE4E5B9)
+    h ^= h >> np.uint64(32)
+    return (h % np.uint64(7)).astype(np.int64) - 3
+
+
+def synth_image(W, H, channels=1, seed=7, y0=0, y1=None):
+    """uint8 image rows [y0, y1) of a W x H picture: smooth low-frequency field plus a wavy vertical seam
+    step (two 'exposures') plus per-pixel noise.  Every pixel depends only on (x, y, channel, seed)."""
+    y1 = H if y1 is None else y1
     rng = np.random.default_rng(seed)
-    y, x = np.mgrid[0:H, 0:W].astype(np.float64)
-    out = np.empty((channels, H, W), np.uint8)
+    y, x = np.mgrid[y0:y1, 0:W].astype(np.float64)
+    yi, xi = np.mgrid[y0:y1, 0:W]
+    out = np.empty((channels, y1 - y0, W), np.uint8)
     for c in range(channels):
         ph = rng.uniform(0, 2 * np.pi, 4)
         f = (110 + 60 * np.sin(2 * np.pi * x / max(W, 2) * 1.5 + ph[0]) * np.cos(2 * np.pi * y / max(H, 2) + ph[1])
              + 25 * np.sin(2 * np.pi * (x + 2 * y) / max(W + H, 2) * 3 + ph[2]))
         seam = W // 2 + (8 * np.sin(2 * np.pi * y / max(H, 2) * 2 + ph[3])).astype(np.int64)
         f = f + np.where(x >= seam, 28.0 + 4 * c, 0.0)
-        f += rng.integers(-3, 4, (H, W))
+        f += _pixel_noise(xi, yi, c, seed)
         out[c] = np.clip(f, 0, 255).astype(np.uint8)
     return out
 
@@ -81,6 +94,30 @@ def seamless_gradients(img, seed=7):
     big = np.abs(gx) > 20
     gx = np.where(big, 0.0, gx).astype(np.float32)
     return gx, gy
+
+
+def strip_gradients(W, H, channels, y0, y1, seed=7):
+    """Seam-free forward gradients for image rows [ya, y1) with ya = max(y0-1, 0): what the strip solver's
+    right-hand side generator (gsb_poisson_rhs_rows) needs for the strip [y0, y1).  Returns gx, gy, ya and
+    the image's pixel (0,0) per channel (the pin constraint)."""
+    ya = max(y0 - 1, 0)
+    yb = min(y1 + 1, H)
+    img = synth_image(W, H, channels, seed=seed, y0=ya, y1=yb).astype(np.int32)
+    rows = y1 - ya
+    gx = np.zeros((channels, rows, W), np.float32)
+    gy = np.zeros((channels, rows, W), np.float32)
+    gx[:, :, :-1] = (img[:, :rows, 1:] - img[:, :rows, :-1]).astype(np.float32)
+    ny = min(rows, img.shape[1] - 1)
+    gy[:, :ny, :] = (img[:, 1:ny + 1, :] - img[:, :ny, :]).astype(np.float32)
+    # rows/columns the reference never reads (x == W-1 or y == H-1) stay zero, as in forward_gradients
+    gx[:, :, -1] = 0
+    gy[:, :, -1] = 0
+    if y1 == H:
+        gx[:, -1, :] = 0
+        gy[:, -1, :] = 0
+    gx = np.where(np.abs(gx) > 20, 0.0, gx).astype(np.float32)
+    pin = synth_image(W, H, channels, seed=seed, y0=0, y1=1)[:, 0, 0].astype(np.float64)
+    return gx, gy, ya, pin
 
 
 # ---- Dirichlet-masked 5-point blend (C2/C3 converged-parity systems) ---------------------------------

@@ -198,6 +198,12 @@ int gsb_poisson_rhs(int W, int H, int nch, const float *gx, const float *gy, con
                     double *b_out);
 int gsb_poisson_rhs_dev(int W, int H, int nch, const float *gx_dev, const float *gy_dev,
                         const double *constraint, double *b_dev);
+/* Same for the image rows [y0, y1) of a strip (multi-GPU): gx_rows / gy_rows hold image rows
+ * [max(y0-1,0), y1) of the gradients, nch planes; b_out = nch * W*(y1-y0) doubles. */
+int gsb_poisson_rhs_rows(int W, int H, int y0, int y1, int nch, const float *gx_rows, const float *gy_rows,
+                         const double *constraint, double *b_out);
+int gsb_poisson_rhs_rows_dev(int W, int H, int y0, int y1, int nch, const float *gx_rows_dev,
+                             const float *gy_rows_dev, const double *constraint, double *b_dev);
 /* A10 write-back: uchar(clamp(x, 0, 255)), truncating. PhotoMontage.cpp:617-626 */
 int gsb_writeback_u8(const double *x, int64_t n, unsigned char *out);
 int gsb_writeback_u8_dev(const double *x_dev, int64_t n, unsigned char *out_dev);

@@ -1,0 +1,154 @@
+"""Worker for the multi-rank tests (launched by torch.distributed.run).
+
+  mode gpu : each rank owns one GPU and one row strip of a W x H Poisson system; the gathered solution must be
+             bit-identical to the single-GPU solve of the whole system on rank 0.
+  mode cpu : gloo, no GPU: checks the host-side logic of the decomposition -- strip bounds, per-strip
+             right-hand-side inputs, and that colour-consistent strips with a one-row halo exchange per colour
+             phase reproduce the single-domain red-black sweep exactly (numpy model of the data path).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from coursecomputationalphotography_b200 import workloads as wl  # noqa: E402
+
+
+def np_edges(W, H, y0, y1):
+    """Edge predicates of the reference's Poisson graph (PhotoMontage.cpp:551-592) for rows [y0, y1)."""
+    y, x = np.mgrid[y0:y1, 0:W]
+    l = (x >= 1) & (y < H - 1)
+    r = (x < W - 1) & (y < H - 1)
+    u = (y >= 1) & (x < W - 1)
+    d = (x < W - 1) & (y < H - 1)
+    return l, r, u, d, x, y
+
+
+def np_redblack_strip(W, H, y0, y1, b, sweeps, exchange):
+    """Red-black GS on rows [y0, y1) with ghost rows y0-1 and y1; `exchange(v, colour)` refreshes the ghosts.
+    Summation order up, left, right, down with separate roundings -- the device kernel's order."""
+    rows = y1 - y0
+    v = np.ones((rows + 2, W))  # v[1:-1] owned, v[0] / v[-1] ghosts
+    l, r, u, d, x, y = np_edges(W, H, y0, y1)
+    deg = l.astype(float) + r + u + d + ((x == 0) & (y == 0))
+    par = (x + y) & 1
+    for _ in range(sweeps):
+        for colour in (0, 1):
+            sig = np.zeros((rows, W))
+            sig = sig + np.where(u, -1.0 * v[0:-2], 0.0)
+            sig[:, 1:] = sig[:, 1:] + np.where(l[:, 1:], -1.0 * v[1:-1, :-1], 0.0)
+            sig[:, :-1] = sig[:, :-1] + np.where(r[:, :-1], -1.0 * v[1:-1, 1:], 0.0)
+            sig = sig + np.where(d, -1.0 * v[2:], 0.0)
+            upd = (par == colour) & (deg > 0)
+            new = (b - sig) / np.where(deg > 0, deg, 1.0)
+            v[1:-1] = np.where(upd, new, v[1:-1])
+            exchange(v, colour)
+    return v[1:-1]
+
+
+def cpu_mode(rank, world):
+    W, H, sweeps = 24, 19, 6
+    bounds = wl.strip_bounds(H, world)
+    assert bounds[0][0] == 0 and bounds[-1][1] == H
+    y0, y1 = bounds[rank]
+    # per-strip inputs equal the slices of the whole-image inputs
+    img = wl.synth_image(W, H, 1, seed=7)
+    gx, gy = wl.seamless_gradients(img)
+    sgx, sgy, ya, pin = wl.strip_gradients(W, H, 1, y0, y1)
+    assert np.array_equal(sgx[0], gx[0, ya:y1]) and np.array_equal(sgy[0], gy[0, ya:y1]) and pin[0] == img[0, 0, 0]
+
+    def rhs(y0, y1):
+        l, r, u, d, x, y = np_edges(W, H, y0, y1)
+        G = lambda a, yy, xx: a[0][np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)]
+        s = np.zeros((y1 - y0, W))
+        s = s + np.where(u, G(gy, y - 1, x), 0.0)
+        s = s + np.where(l, G(gx, y, x - 1), 0.0)
+        s = s - np.where(r, G(gx, y, x), 0.0)
+        s = s - np.where(d, G(gy, y, x), 0.0)
+        s = s + np.where((x == 0) & (y == 0), float(img[0, 0, 0]), 0.0)
+        return s
+
+    def exchange(v, colour):
+        reqs = []
+        up, down = rank - 1, rank + 1
+        send_up, send_dn = torch.from_numpy(v[1].copy()), torch.from_numpy(v[-2].copy())
+        recv_up, recv_dn = torch.empty(W, dtype=torch.float64), torch.empty(W, dtype=torch.float64)
+        if up >= 0:
+            reqs += [dist.isend(send_up, up), dist.irecv(recv_up, up)]
+        if down < world:
+            reqs += [dist.isend(send_dn, down), dist.irecv(recv_dn, down)]
+        for q in reqs:
+            q.wait()
+        if up >= 0:
+            v[0] = recv_up.numpy()
+        if down < world:
+            v[-1] = recv_dn.numpy()
+
+    mine = np_redblack_strip(W, H, y0, y1, rhs(y0, y1), sweeps, exchange)
+    whole = np_redblack_strip(W, H, 0, H, rhs(0, H), sweeps, lambda v, c: None)
+    assert np.array_equal(mine, whole[y0:y1]), "strip %d differs from the single-domain sweep" % rank
+    # stop-rule reduction: the global L1 norm is the sum of the strips' norms
+    t = torch.tensor([np.abs(mine - 1.0).sum()], dtype=torch.float64)
+    dist.all_reduce(t)
+    assert abs(float(t[0]) - np.abs(whole - 1.0).sum()) < 1e-9 * max(1.0, float(t[0]))
+    if rank == 0:
+        print("cpu strips ok: world %d" % world)
+
+
+def gpu_mode(rank, world, local):
+    import coursecomputationalphotography_b200 as pkg
+    from coursecomputationalphotography_b200 import strips
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pkg._lib.check(pkg.load().gsb_set_device(local), "gsb_set_device")
+    uid = strips.broadcast_unique_id(dist, rank, dev)
+    for (W, H, ch, sweeps, ce) in ((64, 48, 3, 9, 1), (301, 203, 1, 5, 2), (1024, 1024, 3, 6, 1)):
+        y0, y1 = wl.strip_bounds(H, world)[rank]
+        s = strips.StripSolver(uid, rank, world, local)
+        s.poisson_strip(W, H, y0, y1)
+        b = strips.strip_rhs(W, H, ch, y0, y1)
+        bd = torch.from_numpy(b).to(dev)
+        xd = torch.empty_like(bd)
+        opts = pkg.SparseMatrix.options(check_every=ce)
+        st = s.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, sweeps, opts)
+        assert st.sweeps == sweeps
+        res = s.residual_dev(bd[0].data_ptr(), xd[0].data_ptr())
+        parts = [torch.empty(ch, W * (b1 - a1), dtype=torch.float64, device=dev) for a1, b1 in wl.strip_bounds(H, world)]
+        dist.all_gather(parts, xd)
+        if rank == 0:
+            x_all = torch.cat(parts, dim=1).cpu().numpy()
+            img = wl.synth_image(W, H, ch, seed=7)
+            gx, gy = wl.seamless_gradients(img)
+            bf = pkg.poisson_rhs(W, H, gx, gy, img[:, 0, 0].astype(np.float64)).reshape(ch, W * H)
+            sp = pkg.SparseMatrix(np.float64)
+            sp.poisson(W, H)
+            xs = sp.gaussSeidel(bf if ch > 1 else bf[0], epsilon=0.0, max_iteration=sweeps, options=opts).reshape(ch, -1)
+            assert np.array_equal(x_all, xs), "%dx%d: %d-strip solve differs from the 1-GPU solve (max %g)" % (
+                W, H, world, np.abs(x_all - xs).max())
+            r1 = sp.residual(bf[0], xs[0])
+            assert abs(r1 - res) <= 1e-9 * max(1.0, r1), (r1, res)
+            print("gpu strips ok: %dx%dx%d world %d sweeps %d residual %.6e" % (W, H, ch, world, sweeps, res))
+        s.close()
+        dist.barrier()
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if mode == "cpu":
+        dist.init_process_group("gloo")
+        cpu_mode(rank, world)
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gpu_mode(rank, world, local)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
