@@ -548,13 +548,6 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (stages > GS_RING_STAGES_MAX) stages = GS_RING_STAGES_MAX;
         while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
         const int smem = 64 + stages * stage_bytes;
-        int per_sm = (225 * 1024) / (smem + 1024);
-        const int want = env_ctas ? env_ctas : 3;
-        if (per_sm > want) per_sm = want;
-        if (per_sm > 8) per_sm = 8;
-        if (per_sm < 1) per_sm = 1;
-        int grid = gsb_sm_count() * per_sm;
-        if (grid > nb) grid = nb;
         const int *tk = p->tile_k.p + p->tile_off[c];
 #define GSB_RING_LAUNCH(ST)                                                                                      \
     {                                                                                                            \
@@ -567,6 +560,17 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
             GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             have[check ? 1 : 0] = smem;                                                                          \
         }                                                                                                        \
+        static int occ[2] = {0, 0}, occ_smem[2] = {0, 0};                                                        \
+        if (!occ[check ? 1 : 0] || occ_smem[check ? 1 : 0] != smem) { /* resident CTAs per SM: a persistent grid */ \
+            int o = 0;                                                                                           \
+            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));    \
+            occ[check ? 1 : 0] = o < 1 ? 1 : o;                                                                  \
+            occ_smem[check ? 1 : 0] = smem;                                                                      \
+        }                                                                                                        \
+        int per_sm = occ[check ? 1 : 0];                                                                         \
+        if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;                                                    \
+        int grid = gsb_sm_count() * per_sm;                                                                      \
+        if (grid > nb) grid = nb;                                                                                \
         kern<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);    \
     }
         if (stages == 2) GSB_RING_LAUNCH(2) else if (stages == 3) GSB_RING_LAUNCH(3) else GSB_RING_LAUNCH(4)
