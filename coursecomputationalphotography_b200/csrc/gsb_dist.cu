@@ -418,7 +418,7 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
             base += cnt;
         }
     d->n_ghost = base - n_local;
-    d->ld = base;
+    d->ld = gsb_padded_ld(base);
 
     // 5. colour-major local CSR
     GSB_TRY(d->rp.alloc((int64_t)n_local + 1 + 8));
@@ -597,12 +597,12 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     const int n_local = d->n_local;
     const int64_t ld = d->ld;
     if (!d->plan.valid || d->plan.requested != opts.kernel) {
-        GSB_TRY(gsb_plan_build(&d->plan, d->rp.p, d->color_start, 2, opts.kernel, st));
+        GSB_TRY(gsb_plan_build(&d->plan, d->rp.p, d->ci.p, d->color_start, 2, opts.kernel, st));
         GSB_TRY(d->partials.alloc((int64_t)(d->plan.total_blocks() + 1) * GSB_MAX_RHS));
     }
     if (d->ws_nrhs < nrhs) {
-        GSB_TRY(d->xw.alloc(ld * nrhs + 8));
-        GSB_TRY(d->bw.alloc(ld * nrhs + 8));
+        GSB_TRY(d->xw.alloc(ld * nrhs + 128));
+        GSB_TRY(d->bw.alloc(ld * nrhs + 128));
         d->ws_nrhs = nrhs;
     }
     if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));
@@ -733,8 +733,8 @@ extern "C" int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const 
     const int n_local = d->n_local;
     const int64_t ld = d->ld;
     if (d->ws_nrhs < 1) {
-        GSB_TRY(d->xw.alloc(ld));
-        GSB_TRY(d->bw.alloc(ld));
+        GSB_TRY(d->xw.alloc(ld + 128));
+        GSB_TRY(d->bw.alloc(ld + 128));
         d->ws_nrhs = 1;
     }
     int64_t launches = 0;

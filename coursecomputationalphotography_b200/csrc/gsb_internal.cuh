@@ -175,10 +175,15 @@ struct GsbPlan {
     int tile_off[66];   // offset of the colour's segment in tile_k
     int color_start[66];
     DevBuf<int> tile_k; // per colour: CSR offset at every tile boundary (blocks[c] + 1 entries)
+    // kernel 4: per tile up to 4 windows of x columns (64-column granules) that cover every gather of the tile
+    DevBuf<int> tile_win; // 12 ints per tile: {nwin, lo[4], len[4], pad[3]}; same indexing as partial slots
+    int win_off[66];      // tile index of the colour's first tile
+    int wcap = 0;         // doubles per right-hand side reserved per stage for the windows
     int total_blocks() const;
 };
-int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colors, int kernel_request,
-                   cudaStream_t st);
+int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_start, int n_colors,
+                   int kernel_request, cudaStream_t st);
+static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles
 int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
                     double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,

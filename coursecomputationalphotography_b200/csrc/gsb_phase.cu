@@ -205,49 +205,61 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 3: persistent CTAs, ring of bulk-copy stages
+// kernels 3 and 4: persistent CTAs, ring of bulk-copy stages
 //
 // gs_phase_staged still exposes one bulk-copy latency plus one gather latency per CTA lifetime.  Here
 // a CTA stays resident, walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... and keeps STAGES tiles
 // in flight: while tile k is computed, the bulk copies of tile k+1 (values, columns, row offsets, and
 // the b / x_old planes -- every per-tile input is a contiguous span) are already landing in the next
-// stage.  The only non-bulk global traffic is the x gathers (read-only path) and the x stores.
+// stage.
+//   kernel 3 (WIN = false): the x gathers still go to global memory (read-only path).
+//   kernel 4 (WIN = true):  the columns a tile gathers from lie in a few contiguous windows of x (for a
+//       5-point grid in colour-major order: the neighbour colour's rows above, beside and below the
+//       tile).  The plan records up to 4 windows per tile (64-column granules); they are bulk-copied
+//       into the stage too, so the whole phase runs out of shared memory and HBM only sees TMA bursts
+//       plus the coalesced x stores.  Tiles whose gathers do not fit windows fall back to global gathers.
 // ---------------------------------------------------------------------------------------------
 #define GS_RING_STAGES_DEFAULT 2
 #define GS_RING_STAGES_MAX 4
+#define GS_WIN_MAX 4           // windows per tile
+#define GS_WIN_GRANULE 64      // columns per granule (512 bytes: keeps every window 16-byte aligned)
+#define GS_WIN_CAP_MAX 2048    // doubles per right-hand side per stage
+#define GS_WIN_DESC 12         // ints per tile descriptor
 
 struct RingLayout {
-    int va_off, b_off, xo_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
+    int va_off, b_off, xo_off, xw_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
 };
 
-__host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check) {
+__host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check, int wcap) {
     RingLayout L;
     L.plane = GS_THREADS + 2;
     L.va_off = 0;
     L.b_off = L.va_off + cap * 8;
     L.xo_off = L.b_off + nrhs * L.plane * 8;
-    L.ci_off = L.xo_off + (check ? nrhs * L.plane * 8 : 0);
+    L.xw_off = L.xo_off + (check ? nrhs * L.plane * 8 : 0);
+    L.ci_off = L.xw_off + nrhs * wcap * 8;
     L.rp_off = L.ci_off + cap * 4;
     L.hdr_off = L.rp_off + (GS_THREADS + 8) * 4;
-    L.stage_bytes = L.hdr_off + 16;
+    L.stage_bytes = L.hdr_off + 64;
     return L;
 }
 
-template <int NRHS, bool CHECK, int STAGES>
+template <int NRHS, bool CHECK, int STAGES, bool WIN>
 __global__ void __launch_bounds__(GS_THREADS, 4)
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
-                  const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
-                  double *__restrict__ partials) {
+                  const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
+                  const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (ctl->done) return; // written only by gs_end_sweep, i.e. constant for the lifetime of this kernel
-    const RingLayout L = ring_layout(cap, NRHS, CHECK);
+    const RingLayout L = ring_layout(cap, NRHS, CHECK, WIN ? wcap : 0);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     unsigned char *stage0 = smem_raw + 64;
     const int tid = threadIdx.x;
 
     auto issue = [&](int t, int s) { // thread 0 only
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+        int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
         const int k0 = tile_k[t], k1 = tile_k[t + 1];
@@ -256,25 +268,48 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
         const int ra = r_begin & ~3;
         const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
-        uint32_t bytes_p[NRHS];
-        uint32_t total = bytes_v + bytes_c + bytes_r;
+        const int ea = r_begin & ~1; // n (the leading dimension) is even: the same alignment for every plane
+        const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
+        uint32_t total = bytes_v + bytes_c + bytes_r + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
+        int nwin = 0, lo[GS_WIN_MAX], len[GS_WIN_MAX];
+        if (WIN) {
+            const int *wd = tile_win + (size_t)t * GS_WIN_DESC;
+            nwin = wd[0];
 #pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            const int64_t e0 = r * n + r_begin;
-            const int64_t ea = e0 & ~(int64_t)1;
-            bytes_p[r] = (uint32_t)(((e0 + rows + 1) & ~(int64_t)1) - ea) * 8u;
-            total += bytes_p[r] * (CHECK ? 2u : 1u);
+            for (int w = 0; w < GS_WIN_MAX; ++w) {
+                lo[w] = wd[1 + w];
+                len[w] = wd[1 + GS_WIN_MAX + w];
+                total += (uint32_t)NRHS * (uint32_t)len[w] * 8u;
+            }
         }
-        reinterpret_cast<int *>(st + L.hdr_off)[0] = k0;
+        hdr[0] = k0;
+        hdr[1] = nwin;
+#pragma unroll
+        for (int w = 0; w < GS_WIN_MAX; ++w) {
+            hdr[2 + w] = WIN ? lo[w] : 0;
+            hdr[2 + GS_WIN_MAX + w] = WIN ? len[w] : 0;
+        }
         mbar_expect_tx(&full[s], total);
         if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
         if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
         bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
-            const int64_t ea = (r * n + r_begin) & ~(int64_t)1;
-            bulk_g2s(st + L.b_off + r * L.plane * 8, b + ea, bytes_p[r], &full[s]);
-            if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + ea, bytes_p[r], &full[s]);
+            bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
+            if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
+        }
+        if (WIN) {
+            int base = 0;
+#pragma unroll
+            for (int w = 0; w < GS_WIN_MAX; ++w) {
+                if (len[w] > 0) {
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r)
+                        bulk_g2s(st + L.xw_off + ((size_t)r * wcap + base) * 8, x + r * n + lo[w], (uint32_t)len[w] * 8u,
+                                 &full[s]);
+                }
+                base += len[w];
+            }
         }
     };
 
@@ -300,10 +335,33 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         const int rows = min(GS_THREADS, row1 - r_begin);
         mbar_wait(&full[s], parity);
 
-        const int k0 = reinterpret_cast<const int *>(st + L.hdr_off)[0];
+        const int *hdr = reinterpret_cast<const int *>(st + L.hdr_off);
+        const int k0 = hdr[0];
         const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
         const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
         const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
+        const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off);
+        const bool use_win = WIN && hdr[1] > 0;
+        int wlo[GS_WIN_MAX], wlen[GS_WIN_MAX];
+#pragma unroll
+        for (int w = 0; w < GS_WIN_MAX; ++w) {
+            wlo[w] = hdr[2 + w];
+            wlen[w] = hdr[2 + GS_WIN_MAX + w];
+        }
+        // value of unknown c of right-hand side r: from the staged windows, else from global memory
+        auto xval = [&](int c, int r) -> double {
+            if (use_win) {
+                int base = 0, slot = 0;
+#pragma unroll
+                for (int w = 0; w < GS_WIN_MAX; ++w) {
+                    const unsigned d = (unsigned)(c - wlo[w]);
+                    if (d < (unsigned)wlen[w]) slot = base + (int)d;
+                    base += wlen[w];
+                }
+                return xw_s[(size_t)r * wcap + slot];
+            }
+            return __ldg(x + r * n + c);
+        };
         const int i = r_begin + tid;
         const bool valid = tid < rows;
         double diff[NRHS];
@@ -326,7 +384,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                 for (int j = 0; j < GS_UNROLL; ++j) { // all gathers of the row in flight before the first use
                     const bool off = cc[j] != i;
 #pragma unroll
-                    for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? __ldg(x + r * n + cc[j]) : 0.0;
+                    for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? xval(cc[j], r) : 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) {
@@ -348,14 +406,14 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                         d = v;
                     } else {
 #pragma unroll
-                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, __ldg(x + r * n + c)));
+                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xval(c, r)));
                     }
                 }
             }
             if (d != 0.0) {
+                const int po = (r_begin & 1) + tid;
 #pragma unroll
                 for (int r = 0; r < NRHS; ++r) {
-                    const int po = (int)((r * n + r_begin) & 1) + tid;
                     const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
                     const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
                     if (CHECK) diff[r] = fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
@@ -369,6 +427,84 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
             const int tn = t + STAGES * gridDim.x;
             if (tn < ntiles) issue(tn, s);
         }
+    }
+}
+
+// Per-tile gather windows (kernel 4).  One CTA per tile: the 64-column granules the tile's off-diagonal
+// columns touch are collected in a small hash set, sorted, and runs of consecutive granules become windows.
+// desc = {nwin, lo[4], len[4]}; nwin = 0 marks a tile that keeps global gathers.  stats[0] = max total
+// window length, stats[1] = tiles without windows.
+__global__ void __launch_bounds__(GS_THREADS) plan_tile_windows(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                                int row0, int row1, int *__restrict__ desc,
+                                                                int *__restrict__ stats) {
+    constexpr int TABLE = 512, MAXG = 40;
+    __shared__ int table[TABLE];
+    __shared__ int overflow;
+    const int t = blockIdx.x;
+    for (int q = threadIdx.x; q < TABLE; q += GS_THREADS) table[q] = -1;
+    if (threadIdx.x == 0) overflow = 0;
+    __syncthreads();
+    const int i = row0 + t * GS_THREADS + threadIdx.x;
+    if (i < row1) {
+        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+            const int c = ci[k];
+            if (c == i) continue;
+            const int g = c / GS_WIN_GRANULE;
+            unsigned h = ((unsigned)g * 2654435761u) % TABLE;
+            for (int probe = 0; probe < TABLE; ++probe) {
+                int old = atomicCAS(&table[h], -1, g);
+                if (old == -1 || old == g) break;
+                h = (h + 1) % TABLE;
+                if (probe == TABLE - 1) overflow = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int *d = desc + (size_t)t * GS_WIN_DESC;
+        for (int q = 0; q < GS_WIN_DESC; ++q) d[q] = 0;
+        int g[MAXG], cnt = 0;
+        bool ok = !overflow;
+        for (int q = 0; q < TABLE && ok; ++q)
+            if (table[q] >= 0) {
+                if (cnt == MAXG) {
+                    ok = false;
+                    break;
+                }
+                int v = table[q], p = cnt++;
+                while (p > 0 && g[p - 1] > v) {
+                    g[p] = g[p - 1];
+                    --p;
+                }
+                g[p] = v;
+            }
+        int nwin = 0, total = 0;
+        if (ok && cnt > 0) {
+            int lo = g[0], prev = g[0];
+            for (int q = 1; q <= cnt && ok; ++q) {
+                if (q < cnt && g[q] == prev + 1) {
+                    prev = g[q];
+                    continue;
+                }
+                if (nwin == GS_WIN_MAX) {
+                    ok = false;
+                    break;
+                }
+                d[1 + nwin] = lo * GS_WIN_GRANULE;
+                d[1 + GS_WIN_MAX + nwin] = (prev - lo + 1) * GS_WIN_GRANULE;
+                total += (prev - lo + 1) * GS_WIN_GRANULE;
+                ++nwin;
+                if (q < cnt) lo = prev = g[q];
+            }
+        }
+        if (!ok || total > GS_WIN_CAP_MAX) {
+            for (int q = 0; q < GS_WIN_DESC; ++q) d[q] = 0;
+            nwin = 0;
+            total = 0;
+            if (cnt > 0 || !ok) atomicAdd(&stats[1], 1);
+        }
+        d[0] = nwin;
+        atomicMax(&stats[0], total);
     }
 }
 
@@ -466,8 +602,8 @@ int GsbPlan::total_blocks() const {
     return s;
 }
 
-int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colors, int kernel_request,
-                   cudaStream_t st) {
+int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_start, int n_colors,
+                   int kernel_request, cudaStream_t st) {
     p->n_colors = n_colors;
     p->requested = kernel_request;
     for (int c = 0; c <= n_colors; ++c) p->color_start[c] = color_start[c];
@@ -504,10 +640,45 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *color_start, int n_colo
                 p->smem_bytes = 16 + p->cap * 12;
                 // the ring kernel needs full 256-row tiles and STAGES stages within the 227 KB limit
                 if (tile_rows == GS_THREADS && kernel_request != 2 &&
-                    64 + 2 * ring_layout(p->cap, GSB_MAX_RHS, true).stage_bytes <= 200 * 1024)
+                    64 + 2 * ring_layout(p->cap, GSB_MAX_RHS, true, 0).stage_bytes <= 200 * 1024)
                     p->kernel = 3;
                 break;
             }
+        }
+        // kernel 4: gather windows, if (nearly) every tile's gathers fit a few contiguous spans of x
+        p->wcap = 0;
+        if (p->kernel == 3 && kernel_request != 3) {
+            int total = 0;
+            for (int c = 0; c < n_colors; ++c) {
+                p->win_off[c] = total;
+                total += p->blocks[c];
+            }
+            DevBuf<int> stats;
+            GSB_TRY(stats.alloc(2));
+            GSB_CUDA(cudaMemsetAsync(stats.p, 0, 2 * sizeof(int), st));
+            GSB_TRY(p->tile_win.alloc((int64_t)total * GS_WIN_DESC));
+            for (int c = 0; c < n_colors; ++c) {
+                if (!p->blocks[c]) continue;
+                plan_tile_windows<<<p->blocks[c], GS_THREADS, 0, st>>>(rp, ci, color_start[c], color_start[c + 1],
+                                                                      p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC,
+                                                                      stats.p);
+                GSB_KERNEL_CHECK();
+            }
+            int hs[2] = {0, 0};
+            GSB_CUDA(cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+            GSB_CUDA(cudaStreamSynchronize(st));
+            const bool mostly = hs[1] * 8 <= total; // at most 1/8 of the tiles fall back to global gathers
+            if (hs[0] > 0 && mostly &&
+                64 + 2 * ring_layout(p->cap, GSB_MAX_RHS, true, hs[0]).stage_bytes <= 220 * 1024) {
+                p->kernel = 4;
+                p->wcap = hs[0];
+            } else {
+                p->tile_win.release();
+            }
+        }
+        if (p->kernel != 4 && kernel_request == 4) {
+            gsb_set_error("window kernel unavailable: the gathers of this matrix do not form contiguous windows");
+            return GSB_ERR_ARG;
         }
         if (p->kernel != 3 && kernel_request == 3) {
             gsb_set_error("ring kernel unavailable for this matrix (rows too long); use kernel 0/1/2");
@@ -533,7 +704,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     const int nb = p->blocks[c];
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
-    if (p->kernel == 3) {
+    if (p->kernel == 3 || p->kernel == 4) {
         // tuning knobs (defaults measured on B200, see profiles/README.md); overridable for experiments
         static int env_stages = -1, env_ctas = -1;
         if (env_stages < 0) {
@@ -542,39 +713,48 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
             e = getenv("GSB_RING_CTAS");
             env_ctas = e ? atoi(e) : 0;
         }
-        const int stage_bytes = ring_layout(p->cap, NRHS, check).stage_bytes;
+        const bool win = p->kernel == 4;
+        const int wcap = win ? p->wcap : 0;
+        const int stage_bytes = ring_layout(p->cap, NRHS, check, wcap).stage_bytes;
         int stages = env_stages ? env_stages : GS_RING_STAGES_DEFAULT;
         if (stages < 2) stages = 2;
         if (stages > GS_RING_STAGES_MAX) stages = GS_RING_STAGES_MAX;
         while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
         const int smem = 64 + stages * stage_bytes;
         const int *tk = p->tile_k.p + p->tile_off[c];
-#define GSB_RING_LAUNCH(ST)                                                                                      \
-    {                                                                                                            \
-        auto kern = check ? (void (*)(const int *, const int *, const double *, const double *, double *, int64_t, \
-                                      int, int, int, const int *, int, const GsCtl *, double *))                 \
-                                gs_phase_ring<NRHS, true, ST>                                                   \
-                          : gs_phase_ring<NRHS, false, ST>;                                                     \
-        static int have[2] = {0, 0};                                                                             \
-        if (smem > 48 * 1024 && have[check ? 1 : 0] < smem) {                                                    \
-            GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-            have[check ? 1 : 0] = smem;                                                                          \
-        }                                                                                                        \
-        static int occ[2] = {0, 0}, occ_smem[2] = {0, 0};                                                        \
-        if (!occ[check ? 1 : 0] || occ_smem[check ? 1 : 0] != smem) { /* resident CTAs per SM: a persistent grid */ \
-            int o = 0;                                                                                           \
-            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));    \
-            occ[check ? 1 : 0] = o < 1 ? 1 : o;                                                                  \
-            occ_smem[check ? 1 : 0] = smem;                                                                      \
-        }                                                                                                        \
-        int per_sm = occ[check ? 1 : 0];                                                                         \
-        if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;                                                    \
-        int grid = gsb_sm_count() * per_sm;                                                                      \
-        if (grid > nb) grid = nb;                                                                                \
-        kern<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, p->cap, ctl, partials);    \
-    }
-        if (stages == 2) GSB_RING_LAUNCH(2) else if (stages == 3) GSB_RING_LAUNCH(3) else GSB_RING_LAUNCH(4)
-#undef GSB_RING_LAUNCH
+        const int *tw = win ? p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC : nullptr;
+        typedef void (*ring_fn)(const int *, const int *, const double *, const double *, double *, int64_t, int, int,
+                                int, const int *, const int *, int, int, const GsCtl *, double *);
+#define GSB_RING_PICK(ST, WN) (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN>)
+        ring_fn kern = nullptr;
+        if (win)
+            kern = stages == 2 ? GSB_RING_PICK(2, true) : stages == 3 ? GSB_RING_PICK(3, true) : GSB_RING_PICK(4, true);
+        else
+            kern = stages == 2 ? GSB_RING_PICK(2, false) : stages == 3 ? GSB_RING_PICK(3, false) : GSB_RING_PICK(4, false);
+#undef GSB_RING_PICK
+        // per (variant) cache of the opt-in shared-memory size and the resident CTAs per SM
+        struct Cfg { const void *fn; int smem, occ; };
+        static Cfg cfgs[64];
+        static int ncfg = 0;
+        Cfg *cf = nullptr;
+        for (int q = 0; q < ncfg; ++q)
+            if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem) cf = &cfgs[q];
+        if (!cf) {
+            if (smem > 48 * 1024)
+                GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int o = 0;
+            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
+            if (ncfg == 64) ncfg = 0;
+            cf = &cfgs[ncfg++];
+            cf->fn = (const void *)kern;
+            cf->smem = smem;
+            cf->occ = o < 1 ? 1 : o;
+        }
+        int per_sm = cf->occ;
+        if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
+        int grid = gsb_sm_count() * per_sm;
+        if (grid > nb) grid = nb;
+        kern<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap, ctl, partials);
     } else if (p->kernel == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;

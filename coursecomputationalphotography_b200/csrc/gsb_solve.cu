@@ -21,20 +21,21 @@
 // ---------------------------------------------------------------------------------------------
 // vector permutation helpers
 // ---------------------------------------------------------------------------------------------
+// natural order (stride n) -> colour-major workspace (stride ld)
 __global__ void __launch_bounds__(256) gather_perm(const double *__restrict__ src, const int *__restrict__ perm,
-                                                   int64_t n, int nrhs, double *__restrict__ dst) {
+                                                   int64_t n, int64_t ld, int nrhs, double *__restrict__ dst) {
     int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= n) return;
     int o = perm[p];
-    for (int r = 0; r < nrhs; ++r) dst[r * n + p] = src[r * n + o];
+    for (int r = 0; r < nrhs; ++r) dst[r * ld + p] = src[r * n + o];
 }
 
 __global__ void __launch_bounds__(256) scatter_perm(const double *__restrict__ src, const int *__restrict__ perm,
-                                                    int64_t n, int nrhs, double *__restrict__ dst) {
+                                                    int64_t n, int64_t ld, int nrhs, double *__restrict__ dst) {
     int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= n) return;
     int o = perm[p];
-    for (int r = 0; r < nrhs; ++r) dst[r * n + o] = src[r * n + p];
+    for (int r = 0; r < nrhs; ++r) dst[r * n + o] = src[r * ld + p];
 }
 
 __global__ void __launch_bounds__(256) fill_f64(double *__restrict__ p, int64_t n, double v) {
@@ -57,7 +58,7 @@ extern "C" void gsb_gs_default_options(gsb_gs_options *o) {
 
 static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, cudaStream_t st, int64_t *launches) {
     GsCtl *ctl = (GsCtl *)m->ctl.p;
-    const int64_t n = m->n_rows;
+    const int64_t n = gsb_padded_ld(m->n_rows);
     int poff = 0;
     for (int c = 0; c < m->n_colors; ++c) {
         const int nb = m->plan->blocks[c];
@@ -84,13 +85,14 @@ static int ensure_workspace(gsb_matrix *m, int nrhs, int kernel_request, cudaStr
     if (!m->plan) m->plan = new (std::nothrow) GsbPlan();
     if (!m->plan) return GSB_ERR_ALLOC;
     if (!m->plan->valid || m->plan->requested != kernel_request) {
-        GSB_TRY(gsb_plan_build(m->plan, m->rp.p, m->color_start, m->n_colors, kernel_request, st));
+        GSB_TRY(gsb_plan_build(m->plan, m->rp.p, m->ci.p, m->color_start, m->n_colors, kernel_request, st));
         GSB_TRY(m->partials.alloc((int64_t)(m->plan->total_blocks() + 1) * MAX_RHS));
         drop_graph(m);
     }
     if (m->ws_nrhs < nrhs) {
-        GSB_TRY(m->xw.alloc(n * nrhs + 8)); // +8: aligned bulk copies may over-read
-        GSB_TRY(m->bw.alloc(n * nrhs + 8));
+        const int64_t ld = gsb_padded_ld(n); // even stride: every plane starts 16-byte aligned
+        GSB_TRY(m->xw.alloc(ld * nrhs + 128)); // +128: aligned bulk copies / 64-column windows may over-read
+        GSB_TRY(m->bw.alloc(ld * nrhs + 128));
         m->ws_nrhs = nrhs;
         drop_graph(m);
     }
@@ -130,12 +132,13 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     const int64_t n = m->n_rows;
     GSB_TRY(ensure_workspace(m, nrhs, opts.kernel, st));
     const int nbv = (int)((n + 255) / 256);
-    gather_perm<<<nbv, 256, 0, st>>>(b_dev, m->perm.p, n, nrhs, m->bw.p);
+    const int64_t ld = gsb_padded_ld(n);
+    gather_perm<<<nbv, 256, 0, st>>>(b_dev, m->perm.p, n, ld, nrhs, m->bw.p);
     GSB_KERNEL_CHECK();
     if (x0_dev)
-        gather_perm<<<nbv, 256, 0, st>>>(x0_dev, m->perm.p, n, nrhs, m->xw.p);
+        gather_perm<<<nbv, 256, 0, st>>>(x0_dev, m->perm.p, n, ld, nrhs, m->xw.p);
     else
-        fill_f64<<<gsb_blocks_for(n * nrhs, 256 * 4, gsb_sm_count() * 16), 256, 0, st>>>(m->xw.p, n * nrhs,
+        fill_f64<<<gsb_blocks_for(ld * nrhs, 256 * 4, gsb_sm_count() * 16), 256, 0, st>>>(m->xw.p, ld * nrhs,
                                                                                       1.0); // v2 :352
     GSB_KERNEL_CHECK();
     int64_t launches = 2;
@@ -236,7 +239,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     cudaEventDestroy(ev1);
     if (status != GSB_OK) return status;
 
-    scatter_perm<<<nbv, 256, 0, st>>>(m->xw.p, m->perm.p, n, nrhs, x_dev);
+    scatter_perm<<<nbv, 256, 0, st>>>(m->xw.p, m->perm.p, n, ld, nrhs, x_dev);
     GSB_KERNEL_CHECK();
     ++launches;
     if (stats) {

@@ -287,7 +287,8 @@ def test_full_size_properties_4096(gsb):
 
 @pytest.mark.parametrize("nrhs", [1, 3])
 def test_all_kernels_agree_bitwise(gsb, nrhs):
-    """direct (1), staged (2) and ring (3) kernels implement the same arithmetic in the same order."""
+    """direct (1), staged (2), ring (3) and window-staged ring (4) kernels implement the same arithmetic in
+    the same order."""
     from coursecomputationalphotography_b200 import workloads as wl
     W, H = 300, 217  # odd sizes: tiles and bulk-copy spans start at unaligned offsets
     sp = gsb.SparseMatrix(np.float64)
@@ -295,7 +296,7 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
     bb = b[:nrhs] if nrhs > 1 else b[0]
     res = {}
-    for k in (1, 2, 3):
+    for k in (1, 2, 3, 4):
         for ce in (1, 3):
             x = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=12, options=gsb.SparseMatrix.options(kernel=k, check_every=ce))
             assert sp.last_stats.kernel_used == k and sp.last_stats.sweeps == 12
@@ -308,5 +309,11 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     r, c, v, b2, _ = wl.diag_dominant_system(7001, 6, seed=13)
     sg = gsb.SparseMatrix(np.float64)
     sg.initializeFromVector(r, c, v)
-    outs = [sg.gaussSeidel(b2, epsilon=0.0, max_iteration=6, options=gsb.SparseMatrix.options(kernel=k)) for k in (1, 2, 3)]
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    outs = [sg.gaussSeidel(b2, epsilon=0.0, max_iteration=6, options=gsb.SparseMatrix.options(kernel=k)) for k in (1, 2, 3, 0)]
+    assert sg.last_stats.kernel_used == 3  # random columns do not form windows: auto keeps global gathers
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
+    with pytest.raises(gsb.GsbError):
+        sg.gaussSeidel(b2, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=4))
+    # auto on the grid picks the window kernel
+    sp.gaussSeidel(bb, epsilon=0.0, max_iteration=1)
+    assert sp.last_stats.kernel_used == 4
