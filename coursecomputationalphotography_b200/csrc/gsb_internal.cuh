@@ -177,6 +177,7 @@ struct GsbPlan {
     DevBuf<int> tile_k; // per colour: CSR offset at every tile boundary (blocks[c] + 1 entries)
     // kernel 4: per tile up to 4 windows of x columns (64-column granules) that cover every gather of the tile
     DevBuf<int> tile_win; // 12 ints per tile: {nwin, lo[4], len[4], pad[3]}; same indexing as partial slots
+    DevBuf<int> ci_slot;  // kernel 4's index array: shared-memory slots for window tiles (-1 = diagonal)
     int win_off[66];      // tile index of the colour's first tile
     int wcap = 0;         // doubles per right-hand side reserved per stage for the windows
     int total_blocks() const;

@@ -341,28 +341,15 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
         const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
         const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off);
+        // kernel 4: in a window tile the staged index array holds shared-memory slots (-1 marks the diagonal),
+        // precomputed by plan_tile_slots; otherwise it holds column numbers and gathers go to global memory
         const bool use_win = WIN && hdr[1] > 0;
-        int wlo[GS_WIN_MAX], wlen[GS_WIN_MAX];
-#pragma unroll
-        for (int w = 0; w < GS_WIN_MAX; ++w) {
-            wlo[w] = hdr[2 + w];
-            wlen[w] = hdr[2 + GS_WIN_MAX + w];
-        }
-        // value of unknown c of right-hand side r: from the staged windows, else from global memory
         auto xval = [&](int c, int r) -> double {
-            if (use_win) {
-                int base = 0, slot = 0;
-#pragma unroll
-                for (int w = 0; w < GS_WIN_MAX; ++w) {
-                    const unsigned d = (unsigned)(c - wlo[w]);
-                    if (d < (unsigned)wlen[w]) slot = base + (int)d;
-                    base += wlen[w];
-                }
-                return xw_s[(size_t)r * wcap + slot];
-            }
+            if (use_win) return xw_s[(size_t)r * wcap + c];
             return __ldg(x + r * n + c);
         };
         const int i = r_begin + tid;
+        const int diag_mark = use_win ? -1 : i;
         const bool valid = tid < rows;
         double diff[NRHS];
 #pragma unroll
@@ -379,10 +366,10 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                 int cc[GS_UNROLL];
                 double xg[GS_UNROLL][NRHS];
 #pragma unroll
-                for (int j = 0; j < GS_UNROLL; ++j) cc[j] = j < len ? crow[j] : i;
+                for (int j = 0; j < GS_UNROLL; ++j) cc[j] = j < len ? crow[j] : diag_mark;
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) { // all gathers of the row in flight before the first use
-                    const bool off = cc[j] != i;
+                    const bool off = cc[j] != diag_mark;
 #pragma unroll
                     for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? xval(cc[j], r) : 0.0;
                 }
@@ -390,7 +377,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                 for (int j = 0; j < GS_UNROLL; ++j) {
                     if (j < len) {
                         const double v = vrow[j];
-                        if (cc[j] == i) {
+                        if (cc[j] == diag_mark) {
                             d = v;
                         } else {
 #pragma unroll
@@ -402,7 +389,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                 for (int j = 0; j < len; ++j) {
                     const int c = crow[j];
                     const double v = vrow[j];
-                    if (c == i) {
+                    if (c == diag_mark) {
                         d = v;
                     } else {
 #pragma unroll
@@ -505,6 +492,41 @@ __global__ void __launch_bounds__(GS_THREADS) plan_tile_windows(const int *__res
         }
         d[0] = nwin;
         atomicMax(&stats[0], total);
+    }
+}
+
+// Index array of kernel 4: for a window tile, the shared-memory slot of every off-diagonal entry (-1 for the
+// diagonal); for a fallback tile, the column number unchanged.
+__global__ void __launch_bounds__(GS_THREADS) plan_tile_slots(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                              int row0, int row1, const int *__restrict__ desc,
+                                                              int *__restrict__ ci_slot) {
+    const int t = blockIdx.x;
+    const int *d = desc + (size_t)t * GS_WIN_DESC;
+    const int nwin = d[0];
+    int lo[GS_WIN_MAX], len[GS_WIN_MAX];
+#pragma unroll
+    for (int w = 0; w < GS_WIN_MAX; ++w) {
+        lo[w] = d[1 + w];
+        len[w] = d[1 + GS_WIN_MAX + w];
+    }
+    const int i = row0 + t * GS_THREADS + threadIdx.x;
+    if (i >= row1) return;
+    for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        const int c = ci[k];
+        int out = c;
+        if (nwin > 0) {
+            out = -1;
+            if (c != i) {
+                int base = 0;
+#pragma unroll
+                for (int w = 0; w < GS_WIN_MAX; ++w) {
+                    const unsigned dd = (unsigned)(c - lo[w]);
+                    if (dd < (unsigned)len[w]) out = base + (int)dd;
+                    base += len[w];
+                }
+            }
+        }
+        ci_slot[k] = out;
     }
 }
 
@@ -672,6 +694,18 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
                 64 + 2 * ring_layout(p->cap, GSB_MAX_RHS, true, hs[0]).stage_bytes <= 220 * 1024) {
                 p->kernel = 4;
                 p->wcap = hs[0];
+                int nnz_h = 0;
+                GSB_CUDA(cudaMemcpyAsync(&nnz_h, rp + color_start[n_colors], sizeof(int), cudaMemcpyDeviceToHost, st));
+                GSB_CUDA(cudaStreamSynchronize(st));
+                GSB_TRY(p->ci_slot.alloc((int64_t)nnz_h + 8));
+                for (int c = 0; c < n_colors; ++c) {
+                    if (!p->blocks[c]) continue;
+                    plan_tile_slots<<<p->blocks[c], GS_THREADS, 0, st>>>(
+                        rp, ci, color_start[c], color_start[c + 1], p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC,
+                        p->ci_slot.p);
+                    GSB_KERNEL_CHECK();
+                }
+                GSB_CUDA(cudaStreamSynchronize(st));
             } else {
                 p->tile_win.release();
             }
@@ -754,7 +788,8 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
-        kern<<<grid, GS_THREADS, smem, st>>>(rp, ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap, ctl, partials);
+        kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
+                                             ctl, partials);
     } else if (p->kernel == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;

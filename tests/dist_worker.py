@@ -106,9 +106,9 @@ def gpu_mode(rank, world, local):
     dev = torch.device("cuda", local)
     pkg._lib.check(pkg.load().gsb_set_device(local), "gsb_set_device")
     uid = strips.broadcast_unique_id(dist, rank, dev)
+    s = strips.StripSolver(uid, rank, world, local)  # one communicator; the strip matrix is rebuilt per case
     for (W, H, ch, sweeps, ce) in ((64, 48, 3, 9, 1), (301, 203, 1, 5, 2), (1024, 1024, 3, 6, 1)):
         y0, y1 = wl.strip_bounds(H, world)[rank]
-        s = strips.StripSolver(uid, rank, world, local)
         s.poisson_strip(W, H, y0, y1)
         b = strips.strip_rhs(W, H, ch, y0, y1)
         bd = torch.from_numpy(b).to(dev)
@@ -117,10 +117,15 @@ def gpu_mode(rank, world, local):
         st = s.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, sweeps, opts)
         assert st.sweeps == sweeps
         res = s.residual_dev(bd[0].data_ptr(), xd[0].data_ptr())
-        parts = [torch.empty(ch, W * (b1 - a1), dtype=torch.float64, device=dev) for a1, b1 in wl.strip_bounds(H, world)]
-        dist.all_gather(parts, xd)
+        # strips may differ by one image row: gather through equal-sized padded buffers
+        bounds = wl.strip_bounds(H, world)
+        nmax = max(W * (b1 - a1) for a1, b1 in bounds)
+        pad = torch.zeros(ch, nmax, dtype=torch.float64, device=dev)
+        pad[:, :xd.shape[1]] = xd
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
         if rank == 0:
-            x_all = torch.cat(parts, dim=1).cpu().numpy()
+            x_all = torch.cat([p[:, :W * (b1 - a1)] for p, (a1, b1) in zip(parts, bounds)], dim=1).cpu().numpy()
             img = wl.synth_image(W, H, ch, seed=7)
             gx, gy = wl.seamless_gradients(img)
             bf = pkg.poisson_rhs(W, H, gx, gy, img[:, 0, 0].astype(np.float64)).reshape(ch, W * H)
@@ -132,8 +137,8 @@ def gpu_mode(rank, world, local):
             r1 = sp.residual(bf[0], xs[0])
             assert abs(r1 - res) <= 1e-9 * max(1.0, r1), (r1, res)
             print("gpu strips ok: %dx%dx%d world %d sweeps %d residual %.6e" % (W, H, ch, world, sweeps, res))
-        s.close()
         dist.barrier()
+    s.close()
 
 
 def main():
