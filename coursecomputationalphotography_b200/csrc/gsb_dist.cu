@@ -491,6 +491,7 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
         return GSB_ERR_SHAPE;
     }
     d->ws_nrhs = 0;
+    d->plan.valid = false; // the launch plan belongs to the previous matrix
     d->built = true;
     return GSB_OK;
 }

@@ -257,12 +257,32 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
     unsigned char *stage0 = smem_raw + 64;
     const int tid = threadIdx.x;
 
-    auto issue = [&](int t, int s) { // thread 0 only
+    // tile descriptor: fetched by thread 0 one iteration before it is needed, so that its L2 latency hides
+    // behind the compute of the current tile
+    struct TileDesc {
+        int k0, k1;
+        int4 w0, w1, w2; // {nwin, lo0, lo1, lo2}, {lo3, len0, len1, len2}, {len3, -, -, -}
+    };
+    auto load_desc = [&](int t) -> TileDesc {
+        TileDesc d;
+        d.k0 = tile_k[t];
+        d.k1 = tile_k[t + 1];
+        if (WIN) {
+            const int4 *wd = reinterpret_cast<const int4 *>(tile_win + (size_t)t * GS_WIN_DESC);
+            d.w0 = wd[0];
+            d.w1 = wd[1];
+            d.w2 = wd[2];
+        } else {
+            d.w0 = d.w1 = d.w2 = make_int4(0, 0, 0, 0);
+        }
+        return d;
+    };
+    auto issue = [&](const TileDesc &td, int t, int s) { // thread 0 only
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
         int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
-        const int k0 = tile_k[t], k1 = tile_k[t + 1];
+        const int k0 = td.k0, k1 = td.k1;
         const int kv0 = k0 & ~1, kc0 = k0 & ~3;
         const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
         const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
@@ -273,14 +293,11 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         uint32_t total = bytes_v + bytes_c + bytes_r + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
         int nwin = 0, lo[GS_WIN_MAX], len[GS_WIN_MAX];
         if (WIN) {
-            const int *wd = tile_win + (size_t)t * GS_WIN_DESC;
-            nwin = wd[0];
+            nwin = td.w0.x;
+            lo[0] = td.w0.y; lo[1] = td.w0.z; lo[2] = td.w0.w; lo[3] = td.w1.x;
+            len[0] = td.w1.y; len[1] = td.w1.z; len[2] = td.w1.w; len[3] = td.w2.x;
 #pragma unroll
-            for (int w = 0; w < GS_WIN_MAX; ++w) {
-                lo[w] = wd[1 + w];
-                len[w] = wd[1 + GS_WIN_MAX + w];
-                total += (uint32_t)NRHS * (uint32_t)len[w] * 8u;
-            }
+            for (int w = 0; w < GS_WIN_MAX; ++w) total += (uint32_t)NRHS * (uint32_t)len[w] * 8u;
         }
         hdr[0] = k0;
         hdr[1] = nwin;
@@ -322,7 +339,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int t = blockIdx.x + s * gridDim.x;
-            if (t < ntiles) issue(t, s);
+            if (t < ntiles) issue(load_desc(t), t, s);
         }
     }
 
@@ -331,6 +348,9 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         const int s = k % STAGES;
         const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+        const int tn = t + STAGES * gridDim.x; // the tile that will reuse this stage
+        TileDesc next_desc;
+        if (tid == 0 && tn < ntiles) next_desc = load_desc(tn);
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
         mbar_wait(&full[s], parity);
@@ -410,10 +430,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         }
         if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
         __syncthreads(); // every thread is done with stage s (and with the reduction scratch)
-        if (tid == 0) {
-            const int tn = t + STAGES * gridDim.x;
-            if (tn < ntiles) issue(tn, s);
-        }
+        if (tid == 0 && tn < ntiles) issue(next_desc, tn, s);
     }
 }
 
