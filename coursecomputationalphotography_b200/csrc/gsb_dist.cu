@@ -13,9 +13,11 @@
 #include "gsb_internal.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include <new>
+#include <vector>
 
 // ---------------------------------------------------------------------------------------------
 // NCCL binding
@@ -106,6 +108,20 @@ struct gsb_dist {
     void *ctl_host = nullptr;
     int ws_nrhs = 0;
     GsbPlan plan;
+    // fused halo exchange over peer-mapped memory (NVLink): see GsbHaloArgs
+    bool peer_ready = false;   // peer pointers valid for the current xw allocation
+    bool peer_failed = false;  // IPC unavailable: stay on the NCCL send/recv path
+    bool halo_meta = false;    // tile order / info / push maps built for the current plan
+    DevBuf<int> flags;         // [peer][colour] raised by the neighbours, then [4..5] halo-tile counters per colour
+    double *peer_x[2] = {nullptr, nullptr};
+    int *peer_flags[2] = {nullptr, nullptr};
+    long long peer_ld[2] = {0, 0};
+    int peer_gs[2][2] = {{0, 0}, {0, 0}};
+    DevBuf<int> tile_order[2], push_map[2];
+    DevBuf<unsigned char> tile_info[2];
+    int n_halo_tiles[2] = {0, 0};
+    long long epoch = 0;       // flags only ever grow: epoch of the last sweep issued so far
+    int used_peer = 0;
     int peer_rank(int p) const { return p == 0 ? rank - 1 : rank + 1; }
     bool has_peer(int p) const { return p == 0 ? rank > 0 : rank < world - 1; }
 };
@@ -149,6 +165,10 @@ extern "C" int gsb_dist_finalize(gsb_dist *d) {
     if (!d) return GSB_OK;
     cudaSetDevice(d->device);
     cudaStreamSynchronize(gsb_cur_stream());
+    for (int p = 0; p < 2; ++p) {
+        if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
+        if (d->peer_flags[p]) cudaIpcCloseMemHandle(d->peer_flags[p]);
+    }
     if (d->comm) g_nccl.CommDestroy(d->comm);
     if (d->ctl_host) cudaFreeHost(d->ctl_host);
     delete d;
@@ -492,6 +512,7 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     }
     d->ws_nrhs = 0;
     d->plan.valid = false; // the launch plan belongs to the previous matrix
+    d->halo_meta = false;
     d->built = true;
     return GSB_OK;
 }
@@ -546,6 +567,170 @@ extern "C" int gsb_dist_matrix_rows(gsb_dist *d, const double *values, const int
         GSB_CUDA(cudaMemcpyAsync(d->nat_va.p, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     }
     return dist_build(d, row0, n_local, n_global, grid_width);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused halo exchange: peer mappings and per-tile metadata
+// ---------------------------------------------------------------------------------------------
+struct PeerHello { // what a rank tells a neighbour so that it can write this rank's ghost slots
+    cudaIpcMemHandle_t hx, hf;
+    long long ld;
+    int gs[2];
+    int ok;
+    int pad;
+};
+
+// (re)maps the neighbours' x workspaces and flag words; collective over neighbours (same order everywhere)
+static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
+    if (d->world == 1 || d->peer_failed) return GSB_OK;
+    if (!d->flags.p) {
+        GSB_TRY(d->flags.alloc(8));
+        GSB_CUDA(cudaMemsetAsync(d->flags.p, 0, 8 * sizeof(int), st));
+    }
+    for (int p = 0; p < 2; ++p) {
+        if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
+        d->peer_x[p] = nullptr;
+    }
+    PeerHello mine[2], theirs[2];
+    memset(mine, 0, sizeof(mine));
+    memset(theirs, 0, sizeof(theirs));
+    int ok = 1;
+    cudaIpcMemHandle_t hx, hf;
+    if (cudaIpcGetMemHandle(&hx, d->xw.p) != cudaSuccess || cudaIpcGetMemHandle(&hf, d->flags.p) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    for (int p = 0; p < 2; ++p) {
+        mine[p].hx = hx;
+        mine[p].hf = hf;
+        mine[p].ld = d->ld;
+        mine[p].gs[0] = d->ghost_start[p][0];
+        mine[p].gs[1] = d->ghost_start[p][1];
+        mine[p].ok = ok;
+    }
+    DevBuf<unsigned char> dm, dt;
+    GSB_TRY(dm.alloc(2 * sizeof(PeerHello)));
+    GSB_TRY(dt.alloc(2 * sizeof(PeerHello)));
+    GSB_CUDA(cudaMemcpyAsync(dm.p, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    GSB_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < 2; ++p)
+        if (d->has_peer(p)) {
+            GSB_NCCL(g_nccl.Send(dm.p + p * sizeof(PeerHello), sizeof(PeerHello), ncclInt8, d->peer_rank(p), d->comm, st));
+            GSB_NCCL(g_nccl.Recv(dt.p + p * sizeof(PeerHello), sizeof(PeerHello), ncclInt8, d->peer_rank(p), d->comm, st));
+        }
+    GSB_NCCL(g_nccl.GroupEnd());
+    GSB_CUDA(cudaMemcpyAsync(theirs, dt.p, sizeof(theirs), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < 2 && ok; ++p) {
+        if (!d->has_peer(p)) continue;
+        if (!theirs[p].ok) {
+            ok = 0;
+            break;
+        }
+        void *px = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&px, theirs[p].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        d->peer_x[p] = (double *)px;
+        if (!d->peer_flags[p]) {
+            if (cudaIpcOpenMemHandle(&pf, theirs[p].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            d->peer_flags[p] = (int *)pf;
+        }
+        d->peer_ld[p] = theirs[p].ld;
+        // this rank is the neighbour's other-side peer: it writes the ghost range the neighbour keeps for it
+        d->peer_gs[p][0] = theirs[p].gs[0];
+        d->peer_gs[p][1] = theirs[p].gs[1];
+    }
+    // all ranks must agree on the transport: one failure anywhere keeps everybody on NCCL send/recv
+    DevBuf<int> agree;
+    GSB_TRY(agree.alloc(1));
+    GSB_CUDA(cudaMemcpyAsync(agree.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
+    GSB_CUDA(cudaMemcpyAsync(&ok, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (!ok) {
+        d->peer_failed = true;
+        d->peer_ready = false;
+        return GSB_OK;
+    }
+    d->peer_ready = true;
+    return GSB_OK;
+}
+
+__global__ void __launch_bounds__(256) d_tile_needs_ghost(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                          int row0, int row1, int n_local,
+                                                          unsigned char *__restrict__ info) {
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    const int i = row0 + blockIdx.x * 256 + threadIdx.x;
+    if (i < row1) {
+        bool g = false;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) g = g || ci[k] >= n_local;
+        if (g) any = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && any) info[blockIdx.x] |= 1;
+}
+
+__global__ void __launch_bounds__(256) d_mark_push(const int *__restrict__ send_idx, int cnt, int row0,
+                                                   int *__restrict__ push_map, unsigned char *__restrict__ info) {
+    int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= cnt) return;
+    int row = send_idx[j];
+    push_map[row] = j;
+    info[(row - row0) / 256] = info[(row - row0) / 256] | 2; // benign race: every writer sets bit 1 of a byte that
+                                                             // d_tile_needs_ghost finished writing earlier
+}
+
+// tile order (halo tiles first), info and push maps for the current plan; host builds the small order array
+static int dist_halo_meta(gsb_dist *d, cudaStream_t st) {
+    if (d->halo_meta) return GSB_OK;
+    if (d->plan.kernel != 3 && d->plan.kernel != 4) return GSB_OK;
+    for (int p = 0; p < 2; ++p) {
+        GSB_TRY(d->push_map[p].alloc(d->n_local));
+        GSB_CUDA(cudaMemsetAsync(d->push_map[p].p, 0xff, sizeof(int) * (size_t)d->n_local, st));
+    }
+    for (int c = 0; c < 2; ++c) {
+        const int nt = d->plan.blocks[c];
+        GSB_TRY(d->tile_info[c].alloc(nt));
+        GSB_TRY(d->tile_order[c].alloc(nt));
+        d->n_halo_tiles[c] = 0;
+        if (nt == 0) continue;
+        GSB_CUDA(cudaMemsetAsync(d->tile_info[c].p, 0, (size_t)nt, st));
+        d_tile_needs_ghost<<<nt, 256, 0, st>>>(d->rp.p, d->ci.p, d->color_start[c], d->color_start[c + 1], d->n_local,
+                                              d->tile_info[c].p);
+        GSB_KERNEL_CHECK();
+        GSB_CUDA(cudaStreamSynchronize(st));
+        for (int p = 0; p < 2; ++p)
+            if (d->has_peer(p) && d->send_cnt[p][c]) {
+                d_mark_push<<<(d->send_cnt[p][c] + 255) / 256, 256, 0, st>>>(d->send_idx[p][c].p, d->send_cnt[p][c],
+                                                                           d->color_start[c], d->push_map[p].p,
+                                                                           d->tile_info[c].p);
+                GSB_KERNEL_CHECK();
+                GSB_CUDA(cudaStreamSynchronize(st)); // the two neighbours' marks touch the same bytes: serialise
+            }
+        std::vector<unsigned char> hi((size_t)nt);
+        GSB_CUDA(cudaMemcpyAsync(hi.data(), d->tile_info[c].p, (size_t)nt, cudaMemcpyDeviceToHost, st));
+        GSB_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> order;
+        order.reserve((size_t)nt);
+        for (int t = 0; t < nt; ++t)
+            if (hi[t]) order.push_back(t);
+        d->n_halo_tiles[c] = (int)order.size();
+        for (int t = 0; t < nt; ++t)
+            if (!hi[t]) order.push_back(t);
+        GSB_CUDA(cudaMemcpyAsync(d->tile_order[c].p, order.data(), sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, st));
+        GSB_CUDA(cudaStreamSynchronize(st));
+    }
+    d->halo_meta = true;
+    return GSB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -605,7 +790,21 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         GSB_TRY(d->xw.alloc(ld * nrhs + 128));
         GSB_TRY(d->bw.alloc(ld * nrhs + 128));
         d->ws_nrhs = nrhs;
+        d->peer_ready = false; // x moved: the neighbours' mappings of it are stale
     }
+    // transport of the halo: fused peer stores inside the ring kernels (default), or packed ncclSend/ncclRecv
+    bool use_peer = d->world > 1 && !d->peer_failed && (d->plan.kernel == 3 || d->plan.kernel == 4);
+    {
+        const char *e = getenv("GSB_DIST_TRANSPORT");
+        if (e && strcmp(e, "nccl") == 0) use_peer = false;
+    }
+    if (use_peer) {
+        if (!d->peer_ready) GSB_TRY(dist_peer_setup(d, st));
+        GSB_TRY(dist_halo_meta(d, st));
+        if (d->peer_failed || !d->peer_ready || !d->halo_meta || d->n_halo_tiles[0] == 0 || d->n_halo_tiles[1] == 0)
+            use_peer = false;
+    }
+    d->used_peer = use_peer ? 1 : 0;
     if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));
     if (!d->ctl_host) GSB_CUDA(cudaHostAlloc(&d->ctl_host, sizeof(GsCtl), cudaHostAllocDefault));
     GsCtl *ctl = (GsCtl *)d->ctl.p;
@@ -628,12 +827,11 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     GSB_CUDA(cudaMemcpyAsync(ctl, hp, sizeof(GsCtl), cudaMemcpyHostToDevice, st));
 
     int batch = opts.batch_sweeps;
-    if (batch <= 0) {
-        double bytes = 12.0 * (double)d->nnz_local + (4.0 + 24.0 * nrhs) * (double)n_local;
-        double est_ms = bytes / 3.0e9 + 0.05;
-        batch = (int)(4.0 / est_ms);
-        if (batch < 4) batch = 4;
-        if (batch > 128) batch = 128;
+    if (batch <= 0) batch = 32; // identical on every rank (the flag epochs below count issued sweeps)
+    const long long epoch_base = d->epoch;
+    if (use_peer) {
+        // every rank has refilled its ghosts (stream order) before any neighbour starts pushing into them
+        GSB_NCCL(g_nccl.AllReduce(ctl, ctl, 1, ncclInt32, ncclMax, d->comm, st));
     }
     cudaEvent_t ev0, ev1;
     GSB_CUDA(cudaEventCreate(&ev0));
@@ -651,12 +849,34 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             for (int c = 0; c < 2 && status == GSB_OK; ++c) {
                 const int r0 = d->color_start[c], r1 = d->color_start[c + 1];
                 if (r1 > r0) {
+                    GsbHaloArgs ha;
+                    memset(&ha, 0, sizeof(ha));
+                    if (use_peer) {
+                        const long long sidx = (long long)issued + s; // sweeps of this call issued before this one
+                        ha.enabled = 1;
+                        ha.n_halo_tiles = d->n_halo_tiles[c];
+                        ha.order = d->tile_order[c].p;
+                        ha.info = d->tile_info[c].p;
+                        for (int p = 0; p < 2; ++p) {
+                            ha.has_peer[p] = d->has_peer(p) ? 1 : 0;
+                            ha.push_map[p] = d->push_map[p].p;
+                            ha.peer_x[p] = d->peer_x[p];
+                            ha.peer_ld[p] = d->peer_ld[p];
+                            ha.peer_gs[p] = d->peer_gs[p][c];
+                            // this rank is peer (1-p) in the neighbour's numbering
+                            ha.peer_flag[p] = d->peer_flags[p] ? d->peer_flags[p] + ((1 - p) * 2 + c) : nullptr;
+                            ha.wait_flag[p] = d->flags.p + (p * 2 + (1 - c));
+                        }
+                        ha.wait_epoch = c == 0 ? (sidx == 0 ? 0 : (int)(epoch_base + sidx)) : (int)(epoch_base + sidx + 1);
+                        ha.signal_epoch = (int)(epoch_base + sidx + 1);
+                        ha.counter = d->flags.p + 4 + c;
+                    }
                     status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->bw.p, d->xw.p, ld, nrhs, check,
-                                             ctl, d->partials.p + (size_t)poff * nrhs, st);
+                                             ctl, d->partials.p + (size_t)poff * nrhs, st, use_peer ? &ha : nullptr);
                     poff += d->plan.blocks[c];
                     ++launches;
                 }
-                if (status == GSB_OK) status = dist_exchange(d, c, nrhs, st, &launches);
+                if (status == GSB_OK && !use_peer) status = dist_exchange(d, c, nrhs, st, &launches);
             }
             if (status != GSB_OK) break;
             if (check) {
@@ -676,6 +896,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             }
         }
         issued += todo;
+        d->epoch = epoch_base + issued;
         if (status != GSB_OK) break;
         cudaError_t ce = cudaMemcpyAsync(hp, ctl, sizeof(GsCtl), cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
@@ -702,7 +923,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         stats->sweeps = h.sweeps;
         stats->n_colors = 2;
         stats->ordering_used = GSB_ORDER_REDBLACK;
-        stats->kernel_used = d->plan.kernel;
+        stats->kernel_used = d->plan.kernel + (d->used_peer ? 10 : 0); // +10: fused peer-memory halo exchange
         stats->kernel_launches = launches;
         for (int r = 0; r < nrhs; ++r) stats->last_eps[r] = h.eps_last[r];
         stats->solve_ms = solve_ms;

@@ -185,10 +185,30 @@ struct GsbPlan {
 int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_start, int n_colors,
                    int kernel_request, cudaStream_t st);
 static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
+// Fused halo exchange of the strip solver (gsb_dist.cu): the phase kernel itself writes the boundary values a
+// neighbour GPU reads straight into that neighbour's ghost slots (peer-mapped memory over NVLink) and
+// raises a flag there; tiles that read ghosts are processed first and wait on the flag the neighbour
+// raised in its previous phase.  Passed by value to the ring kernels; enabled == 0 on a single GPU.
+struct GsbHaloArgs {
+    int enabled;
+    int n_halo_tiles;          // tiles (first in `order`) that read ghosts and/or own rows a neighbour reads
+    const int *order;          // processing order of this colour's tiles: halo tiles first
+    const unsigned char *info; // per tile: bit0 reads ghosts, bit1 has rows to push
+    const int *push_map[2];    // per neighbour: row (permuted local index) -> slot in the neighbour's ghost range, or -1
+    double *peer_x[2];         // neighbour's x workspace (peer mapping)
+    long long peer_ld[2];
+    int peer_gs[2];            // start of the neighbour's ghost range that holds this colour's values from this rank
+    int *peer_flag[2];         // neighbour's flag to raise once every halo tile of this phase is done
+    const int *wait_flag[2];   // own flags the neighbours raise: the other colour's values have arrived
+    int wait_epoch, signal_epoch;
+    int *counter;              // halo tiles finished in this phase
+    int has_peer[2];
+};
+
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles
 int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
                     double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
-                    cudaStream_t st);
+                    cudaStream_t st, const GsbHaloArgs *halo = nullptr);
 // end of sweep.  mode 0: fold partials, bump the counter, decide (single GPU)
 //                mode 1: fold partials into ctl->eps_last only (strip solver, before the all-reduce)
 //                mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)

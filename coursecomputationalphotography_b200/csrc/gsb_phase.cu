@@ -245,11 +245,11 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check,
 }
 
 template <int NRHS, bool CHECK, int STAGES, bool WIN>
-__global__ void __launch_bounds__(GS_THREADS, 4)
+__global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
                   const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
-                  const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
+                  const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (ctl->done) return; // written only by gs_end_sweep, i.e. constant for the lifetime of this kernel
     const RingLayout L = ring_layout(cap, NRHS, CHECK, WIN ? wcap : 0);
@@ -277,7 +277,21 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         }
         return d;
     };
+    // strip solver: halo tiles come first in the processing order
+    auto tile_of = [&](int logical) -> int { return halo.enabled ? halo.order[logical] : logical; };
     auto issue = [&](const TileDesc &td, int t, int s) { // thread 0 only
+        if (halo.enabled && halo.wait_epoch > 0 && (halo.info[t] & 1)) {
+            // this tile reads ghost unknowns: the neighbours' values of the other colour must have landed
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr)
+                if (halo.has_peer[pr]) {
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(halo.wait_flag[pr]) : "memory");
+                    } while (v < halo.wait_epoch);
+                }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
         int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
         const int r_begin = row0 + t * GS_THREADS;
@@ -338,19 +352,28 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            const int t = blockIdx.x + s * gridDim.x;
-            if (t < ntiles) issue(load_desc(t), t, s);
+            const int tl = blockIdx.x + s * gridDim.x;
+            if (tl < ntiles) {
+                const int t = tile_of(tl);
+                issue(load_desc(t), t, s);
+            }
         }
     }
 
     int k = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
+        const int t = tile_of(tl);
         const int s = k % STAGES;
         const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
-        const int tn = t + STAGES * gridDim.x; // the tile that will reuse this stage
+        const int tln = tl + STAGES * gridDim.x; // the (logical) tile that will reuse this stage
+        int tn = 0;
         TileDesc next_desc;
-        if (tid == 0 && tn < ntiles) next_desc = load_desc(tn);
+        if (tid == 0 && tln < ntiles) {
+            tn = tile_of(tln);
+            next_desc = load_desc(tn);
+        }
+        const int tinfo = halo.enabled ? halo.info[t] : 0;
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
         mbar_wait(&full[s], parity);
@@ -425,12 +448,35 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
                     const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
                     if (CHECK) diff[r] = fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
                     x[r * n + i] = xn;
+                    if (tinfo & 2) { // a neighbour GPU reads this row: store it into its ghost slot as well
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr)
+                            if (halo.has_peer[pr]) {
+                                const int slot = halo.push_map[pr][i];
+                                if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
+                            }
+                    }
                 }
             }
         }
+        if (tinfo & 2) __threadfence_system(); // peer stores visible before this tile is counted as done
         if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
         __syncthreads(); // every thread is done with stage s (and with the reduction scratch)
-        if (tid == 0 && tn < ntiles) issue(next_desc, tn, s);
+        if (tid == 0 && tinfo) {
+            // last halo tile of the phase: every ghost read and every push of this phase is complete ->
+            // raise the neighbours' flags (release at system scope orders the pushes before the flag)
+            const int done_tiles = atomicAdd(halo.counter, 1) + 1;
+            if (done_tiles == halo.n_halo_tiles) {
+                *halo.counter = 0;
+                __threadfence_system();
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr)
+                    if (halo.has_peer[pr])
+                        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(halo.peer_flag[pr]), "r"(halo.signal_epoch)
+                                     : "memory");
+            }
+        }
+        if (tid == 0 && tln < ntiles) issue(next_desc, tn, s);
     }
 }
 
@@ -751,7 +797,15 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
 
 template <int NRHS>
 static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
-                         double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials, cudaStream_t st) {
+                         double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials, cudaStream_t st,
+                         const GsbHaloArgs *halo_in) {
+    GsbHaloArgs halo;
+    memset(&halo, 0, sizeof(halo));
+    if (halo_in) halo = *halo_in;
+    if (halo.enabled && p->kernel != 3 && p->kernel != 4) {
+        gsb_set_error("fused halo exchange needs the ring kernels (3/4)");
+        return GSB_ERR_ARG;
+    }
     const int nb = p->blocks[c];
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
@@ -775,7 +829,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         const int *tk = p->tile_k.p + p->tile_off[c];
         const int *tw = win ? p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC : nullptr;
         typedef void (*ring_fn)(const int *, const int *, const double *, const double *, double *, int64_t, int, int,
-                                int, const int *, const int *, int, int, const GsCtl *, double *);
+                                int, const int *, const int *, int, int, const GsCtl *, double *, const GsbHaloArgs);
 #define GSB_RING_PICK(ST, WN) (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN>)
         ring_fn kern = nullptr;
         if (win)
@@ -806,7 +860,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
         kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
-                                             ctl, partials);
+                                             ctl, partials, halo);
     } else if (p->kernel == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;
@@ -838,12 +892,12 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
 
 int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
                     double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
-                    cudaStream_t st) {
+                    cudaStream_t st, const GsbHaloArgs *halo) {
     switch (nrhs) {
-        case 1: return plan_launch_t<1>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
-        case 2: return plan_launch_t<2>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
-        case 3: return plan_launch_t<3>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
-        case 4: return plan_launch_t<4>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st);
+        case 1: return plan_launch_t<1>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
+        case 2: return plan_launch_t<2>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
+        case 3: return plan_launch_t<3>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
+        case 4: return plan_launch_t<4>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
     }
     gsb_set_error("nrhs must be 1..%d", GSB_MAX_RHS);
     return GSB_ERR_ARG;

@@ -114,8 +114,19 @@ def gpu_mode(rank, world, local):
         bd = torch.from_numpy(b).to(dev)
         xd = torch.empty_like(bd)
         opts = pkg.SparseMatrix.options(check_every=ce)
+        # both halo transports must give the same bits: packed ncclSend/ncclRecv, then the fused peer-memory path
+        os.environ["GSB_DIST_TRANSPORT"] = "nccl"
         st = s.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, sweeps, opts)
-        assert st.sweeps == sweeps
+        assert st.sweeps == sweeps and st.kernel_used < 10
+        x_nccl = xd.clone()
+        os.environ["GSB_DIST_TRANSPORT"] = "peer"
+        for rep in range(3):  # repeated solves reuse flags/epochs
+            xd.zero_()
+            st = s.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, sweeps, opts)
+            assert st.sweeps == sweeps
+            if world > 1:
+                assert st.kernel_used >= 10, "fused peer halo was not used (kernel_used=%d)" % st.kernel_used
+            assert torch.equal(xd, x_nccl), "peer-memory halo differs from the NCCL halo (rep %d)" % rep
         res = s.residual_dev(bd[0].data_ptr(), xd[0].data_ptr())
         # strips may differ by one image row: gather through equal-sized padded buffers
         bounds = wl.strip_bounds(H, world)
