@@ -923,7 +923,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         stats->sweeps = h.sweeps;
         stats->n_colors = 2;
         stats->ordering_used = GSB_ORDER_REDBLACK;
-        stats->kernel_used = d->plan.kernel + (d->used_peer ? 10 : 0); // +10: fused peer-memory halo exchange
+        stats->kernel_used = gsb_plan_effective_kernel(&d->plan, nrhs) + (d->used_peer ? 10 : 0); // +10: fused peer-memory halo exchange
         stats->kernel_launches = launches;
         for (int r = 0; r < nrhs; ++r) stats->last_eps[r] = h.eps_last[r];
         stats->solve_ms = solve_ms;

@@ -184,6 +184,7 @@ struct GsbPlan {
 };
 int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_start, int n_colors,
                    int kernel_request, cudaStream_t st);
+int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs);
 static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
 // Fused halo exchange of the strip solver (gsb_dist.cu): the phase kernel itself writes the boundary values a
 // neighbour GPU reads straight into that neighbour's ghost slots (peer-mapped memory over NVLink) and

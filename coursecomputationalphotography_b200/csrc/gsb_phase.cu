@@ -480,6 +480,251 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// kernel 5: window ring with the right-hand sides processed one after another inside a tile
+//
+// With k fused right-hand sides kernel 4 needs k planes of b, x_old and x windows per stage; at k = 3 a
+// stage is ~49 KB and only two CTAs x two stages fit an SM, too few tiles in flight.  Here the CSR slice
+// of a tile (values, slots, row offsets) sits in ring A and is read once per tile, while the per-RHS data
+// (one plane of b, x_old and the x windows) streams through the deeper ring B.  A tile is processed as k
+// single-RHS passes over the same shared-memory CSR: the register footprint and the per-stage size are
+// those of the single-RHS kernel, and HBM still sees the matrix once per sweep.
+// ---------------------------------------------------------------------------------------------
+#define GS_RSER_SA 2
+
+struct RserLayout {
+    int va_off, ci_off, rp_off, hdr_off, a_bytes; // ring A
+    int b_off, xo_off, xw_off, b_bytes;           // ring B
+};
+
+__host__ __device__ inline RserLayout rser_layout(int cap, bool check, int wcap) {
+    RserLayout L;
+    L.va_off = 0;
+    L.ci_off = cap * 8;
+    L.rp_off = L.ci_off + cap * 4;
+    L.hdr_off = L.rp_off + (GS_THREADS + 8) * 4;
+    L.a_bytes = L.hdr_off + 64;
+    L.b_off = 0;
+    L.xo_off = (GS_THREADS + 2) * 8;
+    L.xw_off = L.xo_off + (check ? (GS_THREADS + 2) * 8 : 0);
+    L.b_bytes = L.xw_off + wcap * 8;
+    return L;
+}
+
+template <int NRHS, bool CHECK, int SB>
+__global__ void __launch_bounds__(GS_THREADS, 3)
+    gs_phase_rser(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                  const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
+                  const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
+                  const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (ctl->done) return;
+    constexpr int SA = GS_RSER_SA;
+    const RserLayout L = rser_layout(cap, CHECK, wcap);
+    uint64_t *fullA = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *fullB = fullA + SA;
+    unsigned char *ringA = smem_raw + 64;
+    unsigned char *ringB = ringA + (size_t)SA * L.a_bytes;
+    const int tid = threadIdx.x;
+    auto tile_of = [&](int logical) -> int { return halo.enabled ? halo.order[logical] : logical; };
+    // number of tiles this CTA owns, and the tile of its j-th turn
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    auto issueA = [&](int j) { // thread 0: CSR slice of this CTA's j-th tile
+        const int t = tile_of(blockIdx.x + j * gridDim.x);
+        const int s = j % SA;
+        unsigned char *st = ringA + (size_t)s * L.a_bytes;
+        int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
+        const int r_begin = row0 + t * GS_THREADS;
+        const int rows = min(GS_THREADS, row1 - r_begin);
+        const int k0 = tile_k[t], k1 = tile_k[t + 1];
+        const int kv0 = k0 & ~1, kc0 = k0 & ~3;
+        const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+        const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+        const int ra = r_begin & ~3;
+        const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
+        hdr[0] = k0;
+        hdr[1] = tile_win[(size_t)t * GS_WIN_DESC];
+        mbar_expect_tx(&fullA[s], bytes_v + bytes_c + bytes_r);
+        if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &fullA[s]);
+        if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &fullA[s]);
+        bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &fullA[s]);
+    };
+    struct WinDesc {
+        int4 w0, w1, w2;
+    };
+    auto load_win = [&](int q) -> WinDesc { // windows of the tile of pair q
+        const int t = tile_of(blockIdx.x + (q / NRHS) * gridDim.x);
+        const int4 *wd = reinterpret_cast<const int4 *>(tile_win + (size_t)t * GS_WIN_DESC);
+        WinDesc d;
+        d.w0 = wd[0];
+        d.w1 = wd[1];
+        d.w2 = wd[2];
+        return d;
+    };
+    auto issueB = [&](const WinDesc &wd, int q) { // thread 0: plane r = q % NRHS of the tile of pair q
+        const int t = tile_of(blockIdx.x + (q / NRHS) * gridDim.x);
+        const int r = q % NRHS;
+        const int s = q % SB;
+        if (halo.enabled && halo.wait_epoch > 0 && (halo.info[t] & 1)) {
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr)
+                if (halo.has_peer[pr]) {
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(halo.wait_flag[pr]) : "memory");
+                    } while (v < halo.wait_epoch);
+                }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        unsigned char *st = ringB + (size_t)s * L.b_bytes;
+        const int r_begin = row0 + t * GS_THREADS;
+        const int rows = min(GS_THREADS, row1 - r_begin);
+        const int ea = r_begin & ~1;
+        const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
+        const int lo[GS_WIN_MAX] = {wd.w0.y, wd.w0.z, wd.w0.w, wd.w1.x};
+        const int len[GS_WIN_MAX] = {wd.w1.y, wd.w1.z, wd.w1.w, wd.w2.x};
+        uint32_t total = bytes_p * (CHECK ? 2u : 1u);
+#pragma unroll
+        for (int w = 0; w < GS_WIN_MAX; ++w) total += (uint32_t)len[w] * 8u;
+        mbar_expect_tx(&fullB[s], total);
+        bulk_g2s(st + L.b_off, b + r * n + ea, bytes_p, &fullB[s]);
+        if (CHECK) bulk_g2s(st + L.xo_off, x + r * n + ea, bytes_p, &fullB[s]);
+        int base = 0;
+#pragma unroll
+        for (int w = 0; w < GS_WIN_MAX; ++w) {
+            if (len[w] > 0) bulk_g2s(st + L.xw_off + (size_t)base * 8, x + r * n + lo[w], (uint32_t)len[w] * 8u, &fullB[s]);
+            base += len[w];
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SA; ++s) mbar_init(&fullA[s], 1);
+#pragma unroll
+        for (int s = 0; s < SB; ++s) mbar_init(&fullB[s], 1);
+    }
+    __syncthreads();
+    const int my_pairs = my_tiles * NRHS;
+    if (tid == 0) {
+        for (int j = 0; j < SA && j < my_tiles; ++j) issueA(j);
+        for (int q = 0; q < SB && q < my_pairs; ++q) issueB(load_win(q), q);
+    }
+
+    int q = 0;
+    for (int j = 0; j < my_tiles; ++j) {
+        const int t = tile_of(blockIdx.x + j * gridDim.x);
+        const int sa = j % SA;
+        unsigned char *stA = ringA + (size_t)sa * L.a_bytes;
+        const int r_begin = row0 + t * GS_THREADS;
+        const int rows = min(GS_THREADS, row1 - r_begin);
+        const int tinfo = halo.enabled ? halo.info[t] : 0;
+        mbar_wait(&fullA[sa], (uint32_t)(j / SA) & 1u);
+        const int *hdr = reinterpret_cast<const int *>(stA + L.hdr_off);
+        const int k0 = hdr[0];
+        const bool use_win = hdr[1] > 0;
+        const double *va_s = reinterpret_cast<const double *>(stA + L.va_off) - (k0 & ~1);
+        const int *ci_s = reinterpret_cast<const int *>(stA + L.ci_off) - (k0 & ~3);
+        const int *rp_s = reinterpret_cast<const int *>(stA + L.rp_off) + (r_begin & 3);
+        const int i = r_begin + tid;
+        const int diag_mark = use_win ? -1 : i;
+        const bool valid = tid < rows;
+        int rs = 0, len = 0;
+        int cc[GS_UNROLL];
+        double vv[GS_UNROLL];
+        if (valid) {
+            rs = rp_s[tid];
+            len = rp_s[tid + 1] - rs;
+        }
+        const bool small = len <= GS_UNROLL;
+#pragma unroll
+        for (int u = 0; u < GS_UNROLL; ++u) { // the row's slots and values stay in registers across the k passes
+            const bool on = valid && small && u < len;
+            cc[u] = on ? ci_s[rs + u] : diag_mark;
+            vv[u] = on ? va_s[rs + u] : 0.0;
+        }
+        double diff[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
+
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r, ++q) {
+            const int sb = q % SB;
+            unsigned char *stB = ringB + (size_t)sb * L.b_bytes;
+            const int qn = q + SB;
+            WinDesc next_win;
+            if (tid == 0 && qn < my_pairs) next_win = load_win(qn);
+            mbar_wait(&fullB[sb], (uint32_t)(q / SB) & 1u);
+            const double *xw_s = reinterpret_cast<const double *>(stB + L.xw_off);
+            const double *xg = x + r * n;
+            if (valid) {
+                double sig = 0.0, d = 0.0;
+                if (small) {
+                    double xv[GS_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < GS_UNROLL; ++u) {
+                        const bool off = cc[u] != diag_mark;
+                        xv[u] = off ? (use_win ? xw_s[cc[u]] : __ldg(xg + cc[u])) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < GS_UNROLL; ++u) {
+                        if (u < len) {
+                            if (cc[u] == diag_mark)
+                                d = vv[u];
+                            else
+                                sig = __dadd_rn(sig, __dmul_rn(vv[u], xv[u]));
+                        }
+                    }
+                } else {
+                    for (int u = 0; u < len; ++u) {
+                        const int c = ci_s[rs + u];
+                        const double v = va_s[rs + u];
+                        if (c == diag_mark)
+                            d = v;
+                        else
+                            sig = __dadd_rn(sig, __dmul_rn(v, use_win ? xw_s[c] : __ldg(xg + c)));
+                    }
+                }
+                if (d != 0.0) {
+                    const int po = (r_begin & 1) + tid;
+                    const double bb = reinterpret_cast<const double *>(stB + L.b_off)[po];
+                    const double xn = __ddiv_rn(__dsub_rn(bb, sig), d);
+                    if (CHECK) diff[r] = fabs(xn - reinterpret_cast<const double *>(stB + L.xo_off)[po]);
+                    x[r * n + i] = xn;
+                    if (tinfo & 2) {
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr)
+                            if (halo.has_peer[pr]) {
+                                const int slot = halo.push_map[pr][i];
+                                if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
+                            }
+                    }
+                }
+            }
+            if (tinfo & 2) __threadfence_system();
+            if (r == NRHS - 1 && CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
+            __syncthreads(); // stage sb (and after the last pass stage sa and the reduction scratch) is free
+            if (tid == 0 && qn < my_pairs) issueB(next_win, qn);
+        }
+        if (tid == 0) {
+            if (tinfo) {
+                const int done_tiles = atomicAdd(halo.counter, 1) + 1;
+                if (done_tiles == halo.n_halo_tiles) {
+                    *halo.counter = 0;
+                    __threadfence_system();
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr)
+                        if (halo.has_peer[pr])
+                            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(halo.peer_flag[pr]),
+                                         "r"(halo.signal_epoch)
+                                         : "memory");
+                }
+            }
+            if (j + SA < my_tiles) issueA(j + SA);
+        }
+    }
+}
+
 // Per-tile gather windows (kernel 4).  One CTA per tile: the 64-column granules the tile's off-diagonal
 // columns touch are collected in a small hash set, sorted, and runs of consecutive granules become windows.
 // desc = {nwin, lo[4], len[4]}; nwin = 0 marks a tile that keeps global gathers.  stats[0] = max total
@@ -681,6 +926,13 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
     }
 }
 
+// kernel that actually runs for `nrhs` right-hand sides: with windows available, several right-hand sides go
+// through the RHS-serial ring (5) unless the caller pinned kernel 4
+int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
+    if (p->kernel == 4 && nrhs >= 2 && p->requested != 4) return 5;
+    return p->kernel;
+}
+
 int GsbPlan::total_blocks() const {
     int s = 0;
     for (int c = 0; c < n_colors; ++c) s += blocks[c];
@@ -732,7 +984,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
         }
         // kernel 4: gather windows, if (nearly) every tile's gathers fit a few contiguous spans of x
         p->wcap = 0;
-        if (p->kernel == 3 && kernel_request != 3) {
+        if (p->kernel == 3 && kernel_request != 3) { // requests 0, 4 and 5 all want the windows
             int total = 0;
             for (int c = 0; c < n_colors; ++c) {
                 p->win_off[c] = total;
@@ -773,7 +1025,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
                 p->tile_win.release();
             }
         }
-        if (p->kernel != 4 && kernel_request == 4) {
+        if (p->kernel != 4 && (kernel_request == 4 || kernel_request == 5)) {
             gsb_set_error("window kernel unavailable: the gathers of this matrix do not form contiguous windows");
             return GSB_ERR_ARG;
         }
@@ -802,14 +1054,53 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     GsbHaloArgs halo;
     memset(&halo, 0, sizeof(halo));
     if (halo_in) halo = *halo_in;
-    if (halo.enabled && p->kernel != 3 && p->kernel != 4) {
+    if (halo.enabled && p->kernel != 3 && p->kernel != 4 && p->kernel != 5) {
         gsb_set_error("fused halo exchange needs the ring kernels (3/4)");
         return GSB_ERR_ARG;
     }
     const int nb = p->blocks[c];
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
-    if (p->kernel == 3 || p->kernel == 4) {
+    if (gsb_plan_effective_kernel(p, NRHS) == 5) {
+        // RHS-serial window ring (NRHS >= 2); ring B depth from the shared memory left after ring A
+        static int env_sb = -1;
+        if (env_sb < 0) {
+            const char *e = getenv("GSB_RSER_SB");
+            env_sb = e ? atoi(e) : 0;
+        }
+        const RserLayout RL = rser_layout(p->cap, check, p->wcap);
+        int sb = env_sb ? env_sb : 3;
+        if (sb < 2) sb = 2;
+        if (sb > 4) sb = 4;
+        const int smem = 64 + GS_RSER_SA * RL.a_bytes + sb * RL.b_bytes;
+        typedef void (*rser_fn)(const int *, const int *, const double *, const double *, double *, int64_t, int, int,
+                                int, const int *, const int *, int, int, const GsCtl *, double *, const GsbHaloArgs);
+#define GSB_RSER_PICK(SBV) (check ? (rser_fn)gs_phase_rser<NRHS, true, SBV> : (rser_fn)gs_phase_rser<NRHS, false, SBV>)
+        rser_fn kern = sb == 2 ? GSB_RSER_PICK(2) : sb == 3 ? GSB_RSER_PICK(3) : GSB_RSER_PICK(4);
+#undef GSB_RSER_PICK
+        struct Cfg { const void *fn; int smem, occ; };
+        static Cfg cfgs[32];
+        static int ncfg = 0;
+        Cfg *cf = nullptr;
+        for (int q = 0; q < ncfg; ++q)
+            if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem) cf = &cfgs[q];
+        if (!cf) {
+            if (smem > 48 * 1024)
+                GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int o = 0;
+            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
+            if (ncfg == 32) ncfg = 0;
+            cf = &cfgs[ncfg++];
+            cf->fn = (const void *)kern;
+            cf->smem = smem;
+            cf->occ = o < 1 ? 1 : o;
+        }
+        int grid = gsb_sm_count() * cf->occ;
+        if (grid > nb) grid = nb;
+        kern<<<grid, GS_THREADS, smem, st>>>(rp, p->ci_slot.p, va, b, x, ld, row0, row1, nb, p->tile_k.p + p->tile_off[c],
+                                             p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC, p->cap, p->wcap, ctl,
+                                             partials, halo);
+    } else if (p->kernel == 3 || p->kernel == 4) {
         // tuning knobs (defaults measured on B200, see profiles/README.md); overridable for experiments
         static int env_stages = -1, env_ctas = -1;
         if (env_stages < 0) {

@@ -177,7 +177,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         if (todo > batch) todo = batch;
         if (todo <= 0) todo = 1; // cannot happen (done would be set) -- guards an endless loop
         if (use_graph) {
-            int key[6] = {nrhs, batch, 1, m->plan->kernel, m->n_colors, 1};
+            int key[6] = {nrhs, batch, 1, gsb_plan_effective_kernel(m->plan, nrhs), m->n_colors, 1};
             if (!m->graph_exec || memcmp(key, m->graph_key, sizeof(key)) != 0) {
                 if (m->graph_exec) {
                     cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
@@ -247,7 +247,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         stats->sweeps = h.sweeps;
         stats->n_colors = m->n_colors;
         stats->ordering_used = m->ordering_used;
-        stats->kernel_used = m->plan->kernel;
+        stats->kernel_used = gsb_plan_effective_kernel(m->plan, nrhs);
         stats->kernel_launches = launches;
         for (int r = 0; r < MAX_RHS; ++r) stats->last_eps[r] = r < nrhs ? h.eps_last[r] : 0.0;
         stats->solve_ms = solve_ms;
