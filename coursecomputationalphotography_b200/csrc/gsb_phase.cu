@@ -926,11 +926,15 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
     }
 }
 
-// kernel that actually runs for `nrhs` right-hand sides: with windows available, several right-hand sides go
-// through the RHS-serial ring (5) unless the caller pinned kernel 4
+// Kernel that actually runs for `nrhs` right-hand sides.  plan->kernel == 4 means "gather windows available".
+// Measured on B200 (profiles/README.md): one right-hand side is fastest with the windows (4); with several
+// fused right-hand sides a window stage no longer leaves room for enough resident CTAs, and the ring with
+// global gathers (3) wins.  Kernels 4 and 5 stay selectable explicitly.
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
-    if (p->kernel == 4 && nrhs >= 2 && p->requested != 4) return 5;
-    return p->kernel;
+    if (p->kernel != 4) return p->kernel;
+    if (p->requested == 4) return 4;
+    if (p->requested == 5) return nrhs >= 2 ? 5 : 4;
+    return nrhs >= 2 ? 3 : 4;
 }
 
 int GsbPlan::total_blocks() const {
@@ -1061,7 +1065,8 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     const int nb = p->blocks[c];
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
-    if (gsb_plan_effective_kernel(p, NRHS) == 5) {
+    const int eff = gsb_plan_effective_kernel(p, NRHS);
+    if (eff == 5) {
         // RHS-serial window ring (NRHS >= 2); ring B depth from the shared memory left after ring A
         static int env_sb = -1;
         if (env_sb < 0) {
@@ -1100,7 +1105,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         kern<<<grid, GS_THREADS, smem, st>>>(rp, p->ci_slot.p, va, b, x, ld, row0, row1, nb, p->tile_k.p + p->tile_off[c],
                                              p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC, p->cap, p->wcap, ctl,
                                              partials, halo);
-    } else if (p->kernel == 3 || p->kernel == 4) {
+    } else if (eff == 3 || eff == 4) {
         // tuning knobs (defaults measured on B200, see profiles/README.md); overridable for experiments
         static int env_stages = -1, env_ctas = -1;
         if (env_stages < 0) {
@@ -1109,7 +1114,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
             e = getenv("GSB_RING_CTAS");
             env_ctas = e ? atoi(e) : 0;
         }
-        const bool win = p->kernel == 4;
+        const bool win = eff == 4;
         const int wcap = win ? p->wcap : 0;
         const int stage_bytes = ring_layout(p->cap, NRHS, check, wcap).stage_bytes;
         int stages = env_stages ? env_stages : GS_RING_STAGES_DEFAULT;
@@ -1152,7 +1157,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (grid > nb) grid = nb;
         kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
                                              ctl, partials, halo);
-    } else if (p->kernel == 2) {
+    } else if (eff == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;
         if (p->smem_bytes > 48 * 1024) {
