@@ -784,7 +784,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     const int64_t ld = d->ld;
     if (!d->plan.valid || d->plan.requested != opts.kernel) {
         GSB_TRY(gsb_plan_build(&d->plan, d->rp.p, d->ci.p, d->color_start, 2, opts.kernel, st));
-        GSB_TRY(d->partials.alloc((int64_t)(d->plan.total_blocks() + 1) * GSB_MAX_RHS));
+        GSB_TRY(d->partials.alloc((int64_t)(d->plan.total_blocks() + 1 + 64) * GSB_MAX_RHS));
     }
     if (d->ws_nrhs < nrhs) {
         GSB_TRY(d->xw.alloc(ld * nrhs + 128));

@@ -245,7 +245,7 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check,
 }
 
 template <int NRHS, bool CHECK, int STAGES, bool WIN>
-__global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
+__global__ void __launch_bounds__(GS_THREADS * NRHS, (NRHS == 1 ? 4 : 2))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
                   const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
@@ -360,6 +360,11 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
         }
     }
 
+    // consumers: one thread per (row, right-hand side); warps [8r, 8r+8) own plane r of the tile
+    const int r = tid / GS_THREADS;   // right-hand side of this thread (warp-uniform)
+    const int lt = tid % GS_THREADS;  // row inside the tile
+    const int lane = tid & 31, wid = tid >> 5;
+    __shared__ double red_ws[NRHS * (GS_THREADS / 32)];
     int k = 0;
     for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
         const int t = tile_of(tl);
@@ -383,85 +388,80 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
         const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
         const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
         const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
-        const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off);
         // kernel 4: in a window tile the staged index array holds shared-memory slots (-1 marks the diagonal),
         // precomputed by plan_tile_slots; otherwise it holds column numbers and gathers go to global memory
         const bool use_win = WIN && hdr[1] > 0;
-        auto xval = [&](int c, int r) -> double {
-            if (use_win) return xw_s[(size_t)r * wcap + c];
-            return __ldg(x + r * n + c);
-        };
-        const int i = r_begin + tid;
+        const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off) + (size_t)r * wcap;
+        const double *xg = x + r * n;
+        const int i = r_begin + lt;
         const int diag_mark = use_win ? -1 : i;
-        const bool valid = tid < rows;
-        double diff[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
+        const bool valid = lt < rows;
+        double diff = 0.0;
         if (valid) {
-            const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
+            const int rs = rp_s[lt], len = rp_s[lt + 1] - rs;
             const double *vrow = va_s + rs;
             const int *crow = ci_s + rs;
-            double sig[NRHS];
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
-            double d = 0.0;
+            double sig = 0.0, d = 0.0;
             if (len <= GS_UNROLL) {
                 int cc[GS_UNROLL];
-                double xg[GS_UNROLL][NRHS];
+                double xv[GS_UNROLL];
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) cc[j] = j < len ? crow[j] : diag_mark;
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) { // all gathers of the row in flight before the first use
                     const bool off = cc[j] != diag_mark;
-#pragma unroll
-                    for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? xval(cc[j], r) : 0.0;
+                    xv[j] = off ? (use_win ? xw_s[cc[j]] : __ldg(xg + cc[j])) : 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) {
                     if (j < len) {
                         const double v = vrow[j];
-                        if (cc[j] == diag_mark) {
+                        if (cc[j] == diag_mark)
                             d = v;
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xg[j][r]));
-                        }
+                        else
+                            sig = __dadd_rn(sig, __dmul_rn(v, xv[j]));
                     }
                 }
             } else {
                 for (int j = 0; j < len; ++j) {
                     const int c = crow[j];
                     const double v = vrow[j];
-                    if (c == diag_mark) {
+                    if (c == diag_mark)
                         d = v;
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xval(c, r)));
-                    }
+                    else
+                        sig = __dadd_rn(sig, __dmul_rn(v, use_win ? xw_s[c] : __ldg(xg + c)));
                 }
             }
-            if (d != 0.0) {
-                const int po = (r_begin & 1) + tid;
+            if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+                const int po = (r_begin & 1) + lt;
+                const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
+                const double xn = __ddiv_rn(__dsub_rn(bb, sig), d);
+                if (CHECK) diff = fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
+                x[r * n + i] = xn;
+                if (tinfo & 2) { // a neighbour GPU reads this row: store it into its ghost slot as well
 #pragma unroll
-                for (int r = 0; r < NRHS; ++r) {
-                    const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
-                    const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
-                    if (CHECK) diff[r] = fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
-                    x[r * n + i] = xn;
-                    if (tinfo & 2) { // a neighbour GPU reads this row: store it into its ghost slot as well
-#pragma unroll
-                        for (int pr = 0; pr < 2; ++pr)
-                            if (halo.has_peer[pr]) {
-                                const int slot = halo.push_map[pr][i];
-                                if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
-                            }
-                    }
+                    for (int pr = 0; pr < 2; ++pr)
+                        if (halo.has_peer[pr]) {
+                            const int slot = halo.push_map[pr][i];
+                            if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
+                        }
                 }
             }
         }
         if (tinfo & 2) __threadfence_system(); // peer stores visible before this tile is counted as done
-        if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
-        __syncthreads(); // every thread is done with stage s (and with the reduction scratch)
+        if (CHECK) { // fixed-order fold: shuffle tree inside a warp, then the 8 warps of a plane in order
+            double v = diff;
+#pragma unroll
+            for (int dlt = 16; dlt > 0; dlt >>= 1) v += __shfl_down_sync(0xffffffffu, v, dlt);
+            if (lane == 0) red_ws[wid] = v;
+        }
+        __syncthreads(); // every thread is done with stage s
+        if (CHECK && tid < NRHS) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < GS_THREADS / 32; ++w) sum += red_ws[tid * (GS_THREADS / 32) + w];
+            partials[(size_t)t * NRHS + tid] = sum;
+        }
         if (tid == 0 && tinfo) {
             // last halo tile of the phase: every ghost read and every push of this phase is complete ->
             // raise the neighbours' flags (release at system scope orders the pushes before the flag)
@@ -477,251 +477,6 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
             }
         }
         if (tid == 0 && tln < ntiles) issue(next_desc, tn, s);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernel 5: window ring with the right-hand sides processed one after another inside a tile
-//
-// With k fused right-hand sides kernel 4 needs k planes of b, x_old and x windows per stage; at k = 3 a
-// stage is ~49 KB and only two CTAs x two stages fit an SM, too few tiles in flight.  Here the CSR slice
-// of a tile (values, slots, row offsets) sits in ring A and is read once per tile, while the per-RHS data
-// (one plane of b, x_old and the x windows) streams through the deeper ring B.  A tile is processed as k
-// single-RHS passes over the same shared-memory CSR: the register footprint and the per-stage size are
-// those of the single-RHS kernel, and HBM still sees the matrix once per sweep.
-// ---------------------------------------------------------------------------------------------
-#define GS_RSER_SA 2
-
-struct RserLayout {
-    int va_off, ci_off, rp_off, hdr_off, a_bytes; // ring A
-    int b_off, xo_off, xw_off, b_bytes;           // ring B
-};
-
-__host__ __device__ inline RserLayout rser_layout(int cap, bool check, int wcap) {
-    RserLayout L;
-    L.va_off = 0;
-    L.ci_off = cap * 8;
-    L.rp_off = L.ci_off + cap * 4;
-    L.hdr_off = L.rp_off + (GS_THREADS + 8) * 4;
-    L.a_bytes = L.hdr_off + 64;
-    L.b_off = 0;
-    L.xo_off = (GS_THREADS + 2) * 8;
-    L.xw_off = L.xo_off + (check ? (GS_THREADS + 2) * 8 : 0);
-    L.b_bytes = L.xw_off + wcap * 8;
-    return L;
-}
-
-template <int NRHS, bool CHECK, int SB>
-__global__ void __launch_bounds__(GS_THREADS, 3)
-    gs_phase_rser(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                  const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
-                  const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
-                  const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (ctl->done) return;
-    constexpr int SA = GS_RSER_SA;
-    const RserLayout L = rser_layout(cap, CHECK, wcap);
-    uint64_t *fullA = reinterpret_cast<uint64_t *>(smem_raw);
-    uint64_t *fullB = fullA + SA;
-    unsigned char *ringA = smem_raw + 64;
-    unsigned char *ringB = ringA + (size_t)SA * L.a_bytes;
-    const int tid = threadIdx.x;
-    auto tile_of = [&](int logical) -> int { return halo.enabled ? halo.order[logical] : logical; };
-    // number of tiles this CTA owns, and the tile of its j-th turn
-    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
-    auto issueA = [&](int j) { // thread 0: CSR slice of this CTA's j-th tile
-        const int t = tile_of(blockIdx.x + j * gridDim.x);
-        const int s = j % SA;
-        unsigned char *st = ringA + (size_t)s * L.a_bytes;
-        int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
-        const int r_begin = row0 + t * GS_THREADS;
-        const int rows = min(GS_THREADS, row1 - r_begin);
-        const int k0 = tile_k[t], k1 = tile_k[t + 1];
-        const int kv0 = k0 & ~1, kc0 = k0 & ~3;
-        const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
-        const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
-        const int ra = r_begin & ~3;
-        const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
-        hdr[0] = k0;
-        hdr[1] = tile_win[(size_t)t * GS_WIN_DESC];
-        mbar_expect_tx(&fullA[s], bytes_v + bytes_c + bytes_r);
-        if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &fullA[s]);
-        if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &fullA[s]);
-        bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &fullA[s]);
-    };
-    struct WinDesc {
-        int4 w0, w1, w2;
-    };
-    auto load_win = [&](int q) -> WinDesc { // windows of the tile of pair q
-        const int t = tile_of(blockIdx.x + (q / NRHS) * gridDim.x);
-        const int4 *wd = reinterpret_cast<const int4 *>(tile_win + (size_t)t * GS_WIN_DESC);
-        WinDesc d;
-        d.w0 = wd[0];
-        d.w1 = wd[1];
-        d.w2 = wd[2];
-        return d;
-    };
-    auto issueB = [&](const WinDesc &wd, int q) { // thread 0: plane r = q % NRHS of the tile of pair q
-        const int t = tile_of(blockIdx.x + (q / NRHS) * gridDim.x);
-        const int r = q % NRHS;
-        const int s = q % SB;
-        if (halo.enabled && halo.wait_epoch > 0 && (halo.info[t] & 1)) {
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr)
-                if (halo.has_peer[pr]) {
-                    int v;
-                    do {
-                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(halo.wait_flag[pr]) : "memory");
-                    } while (v < halo.wait_epoch);
-                }
-            asm volatile("fence.proxy.async;" ::: "memory");
-        }
-        unsigned char *st = ringB + (size_t)s * L.b_bytes;
-        const int r_begin = row0 + t * GS_THREADS;
-        const int rows = min(GS_THREADS, row1 - r_begin);
-        const int ea = r_begin & ~1;
-        const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
-        const int lo[GS_WIN_MAX] = {wd.w0.y, wd.w0.z, wd.w0.w, wd.w1.x};
-        const int len[GS_WIN_MAX] = {wd.w1.y, wd.w1.z, wd.w1.w, wd.w2.x};
-        uint32_t total = bytes_p * (CHECK ? 2u : 1u);
-#pragma unroll
-        for (int w = 0; w < GS_WIN_MAX; ++w) total += (uint32_t)len[w] * 8u;
-        mbar_expect_tx(&fullB[s], total);
-        bulk_g2s(st + L.b_off, b + r * n + ea, bytes_p, &fullB[s]);
-        if (CHECK) bulk_g2s(st + L.xo_off, x + r * n + ea, bytes_p, &fullB[s]);
-        int base = 0;
-#pragma unroll
-        for (int w = 0; w < GS_WIN_MAX; ++w) {
-            if (len[w] > 0) bulk_g2s(st + L.xw_off + (size_t)base * 8, x + r * n + lo[w], (uint32_t)len[w] * 8u, &fullB[s]);
-            base += len[w];
-        }
-    };
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < SA; ++s) mbar_init(&fullA[s], 1);
-#pragma unroll
-        for (int s = 0; s < SB; ++s) mbar_init(&fullB[s], 1);
-    }
-    __syncthreads();
-    const int my_pairs = my_tiles * NRHS;
-    if (tid == 0) {
-        for (int j = 0; j < SA && j < my_tiles; ++j) issueA(j);
-        for (int q = 0; q < SB && q < my_pairs; ++q) issueB(load_win(q), q);
-    }
-
-    int q = 0;
-    for (int j = 0; j < my_tiles; ++j) {
-        const int t = tile_of(blockIdx.x + j * gridDim.x);
-        const int sa = j % SA;
-        unsigned char *stA = ringA + (size_t)sa * L.a_bytes;
-        const int r_begin = row0 + t * GS_THREADS;
-        const int rows = min(GS_THREADS, row1 - r_begin);
-        const int tinfo = halo.enabled ? halo.info[t] : 0;
-        mbar_wait(&fullA[sa], (uint32_t)(j / SA) & 1u);
-        const int *hdr = reinterpret_cast<const int *>(stA + L.hdr_off);
-        const int k0 = hdr[0];
-        const bool use_win = hdr[1] > 0;
-        const double *va_s = reinterpret_cast<const double *>(stA + L.va_off) - (k0 & ~1);
-        const int *ci_s = reinterpret_cast<const int *>(stA + L.ci_off) - (k0 & ~3);
-        const int *rp_s = reinterpret_cast<const int *>(stA + L.rp_off) + (r_begin & 3);
-        const int i = r_begin + tid;
-        const int diag_mark = use_win ? -1 : i;
-        const bool valid = tid < rows;
-        int rs = 0, len = 0;
-        int cc[GS_UNROLL];
-        double vv[GS_UNROLL];
-        if (valid) {
-            rs = rp_s[tid];
-            len = rp_s[tid + 1] - rs;
-        }
-        const bool small = len <= GS_UNROLL;
-#pragma unroll
-        for (int u = 0; u < GS_UNROLL; ++u) { // the row's slots and values stay in registers across the k passes
-            const bool on = valid && small && u < len;
-            cc[u] = on ? ci_s[rs + u] : diag_mark;
-            vv[u] = on ? va_s[rs + u] : 0.0;
-        }
-        double diff[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
-
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r, ++q) {
-            const int sb = q % SB;
-            unsigned char *stB = ringB + (size_t)sb * L.b_bytes;
-            const int qn = q + SB;
-            WinDesc next_win;
-            if (tid == 0 && qn < my_pairs) next_win = load_win(qn);
-            mbar_wait(&fullB[sb], (uint32_t)(q / SB) & 1u);
-            const double *xw_s = reinterpret_cast<const double *>(stB + L.xw_off);
-            const double *xg = x + r * n;
-            if (valid) {
-                double sig = 0.0, d = 0.0;
-                if (small) {
-                    double xv[GS_UNROLL];
-#pragma unroll
-                    for (int u = 0; u < GS_UNROLL; ++u) {
-                        const bool off = cc[u] != diag_mark;
-                        xv[u] = off ? (use_win ? xw_s[cc[u]] : __ldg(xg + cc[u])) : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < GS_UNROLL; ++u) {
-                        if (u < len) {
-                            if (cc[u] == diag_mark)
-                                d = vv[u];
-                            else
-                                sig = __dadd_rn(sig, __dmul_rn(vv[u], xv[u]));
-                        }
-                    }
-                } else {
-                    for (int u = 0; u < len; ++u) {
-                        const int c = ci_s[rs + u];
-                        const double v = va_s[rs + u];
-                        if (c == diag_mark)
-                            d = v;
-                        else
-                            sig = __dadd_rn(sig, __dmul_rn(v, use_win ? xw_s[c] : __ldg(xg + c)));
-                    }
-                }
-                if (d != 0.0) {
-                    const int po = (r_begin & 1) + tid;
-                    const double bb = reinterpret_cast<const double *>(stB + L.b_off)[po];
-                    const double xn = __ddiv_rn(__dsub_rn(bb, sig), d);
-                    if (CHECK) diff[r] = fabs(xn - reinterpret_cast<const double *>(stB + L.xo_off)[po]);
-                    x[r * n + i] = xn;
-                    if (tinfo & 2) {
-#pragma unroll
-                        for (int pr = 0; pr < 2; ++pr)
-                            if (halo.has_peer[pr]) {
-                                const int slot = halo.push_map[pr][i];
-                                if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
-                            }
-                    }
-                }
-            }
-            if (tinfo & 2) __threadfence_system();
-            if (r == NRHS - 1 && CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(diff, partials + (size_t)t * NRHS);
-            __syncthreads(); // stage sb (and after the last pass stage sa and the reduction scratch) is free
-            if (tid == 0 && qn < my_pairs) issueB(next_win, qn);
-        }
-        if (tid == 0) {
-            if (tinfo) {
-                const int done_tiles = atomicAdd(halo.counter, 1) + 1;
-                if (done_tiles == halo.n_halo_tiles) {
-                    *halo.counter = 0;
-                    __threadfence_system();
-#pragma unroll
-                    for (int pr = 0; pr < 2; ++pr)
-                        if (halo.has_peer[pr])
-                            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(halo.peer_flag[pr]),
-                                         "r"(halo.signal_epoch)
-                                         : "memory");
-                }
-            }
-            if (j + SA < my_tiles) issueA(j + SA);
-        }
     }
 }
 
@@ -897,8 +652,40 @@ __global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *_
     }
 }
 
+// first level of the fold for many partials: GS_FOLD_BLOCKS blocks, each folds one contiguous chunk in a
+// fixed order -> out[b * NRHS + r]; gs_end_sweep then folds those.  The grouping depends only on n_partials.
+#define GS_FOLD_BLOCKS 64
+template <int NRHS>
+__global__ void __launch_bounds__(256) gs_fold_partials(const double *__restrict__ partials, int n_partials,
+                                                        double *__restrict__ out) {
+    const int chunk = (n_partials + GS_FOLD_BLOCKS - 1) / GS_FOLD_BLOCKS;
+    const int lo = blockIdx.x * chunk, hi = min(n_partials, lo + chunk);
+    double s[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += 256) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] += partials[(size_t)i * NRHS + r];
+    }
+    gsb_block_reduce_store<NRHS, 256>(s, out + (size_t)blockIdx.x * NRHS);
+}
+
+// partials must have room for GS_FOLD_BLOCKS * nrhs more doubles after the n_partials * nrhs used ones
 int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
                          cudaStream_t st) {
+    if (checked && mode != 2 && n_partials > 4 * GS_FOLD_BLOCKS) {
+        double *scratch = const_cast<double *>(partials) + (size_t)n_partials * nrhs;
+        switch (nrhs) {
+            case 1: gs_fold_partials<1><<<GS_FOLD_BLOCKS, 256, 0, st>>>(partials, n_partials, scratch); break;
+            case 2: gs_fold_partials<2><<<GS_FOLD_BLOCKS, 256, 0, st>>>(partials, n_partials, scratch); break;
+            case 3: gs_fold_partials<3><<<GS_FOLD_BLOCKS, 256, 0, st>>>(partials, n_partials, scratch); break;
+            case 4: gs_fold_partials<4><<<GS_FOLD_BLOCKS, 256, 0, st>>>(partials, n_partials, scratch); break;
+            default: return GSB_ERR_ARG;
+        }
+        GSB_KERNEL_CHECK();
+        partials = scratch;
+        n_partials = GS_FOLD_BLOCKS;
+    }
     switch (nrhs) {
         case 1: gs_end_sweep<1><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
         case 2: gs_end_sweep<2><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
@@ -926,15 +713,12 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
     }
 }
 
-// Kernel that actually runs for `nrhs` right-hand sides.  plan->kernel == 4 means "gather windows available".
-// Measured on B200 (profiles/README.md): one right-hand side is fastest with the windows (4); with several
-// fused right-hand sides a window stage no longer leaves room for enough resident CTAs, and the ring with
-// global gathers (3) wins.  Kernels 4 and 5 stay selectable explicitly.
+// Kernel that actually runs for `nrhs` right-hand sides.  plan->kernel == 4 means "gather windows available";
+// a caller that asked for kernel 3 gets the same ring with global gathers.
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
-    if (p->kernel != 4) return p->kernel;
-    if (p->requested == 4) return 4;
-    if (p->requested == 5) return nrhs >= 2 ? 5 : 4;
-    return nrhs >= 2 ? 3 : 4;
+    (void)nrhs;
+    if (p->kernel == 4 && p->requested == 3) return 3;
+    return p->kernel;
 }
 
 int GsbPlan::total_blocks() const {
@@ -988,7 +772,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
         }
         // kernel 4: gather windows, if (nearly) every tile's gathers fit a few contiguous spans of x
         p->wcap = 0;
-        if (p->kernel == 3 && kernel_request != 3) { // requests 0, 4 and 5 all want the windows
+        if (p->kernel == 3) { // windows are probed even when kernel 3 was requested (cheap; keeps one plan per matrix)
             int total = 0;
             for (int c = 0; c < n_colors; ++c) {
                 p->win_off[c] = total;
@@ -1029,7 +813,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
                 p->tile_win.release();
             }
         }
-        if (p->kernel != 4 && (kernel_request == 4 || kernel_request == 5)) {
+        if (p->kernel != 4 && kernel_request == 4) {
             gsb_set_error("window kernel unavailable: the gathers of this matrix do not form contiguous windows");
             return GSB_ERR_ARG;
         }
@@ -1058,7 +842,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     GsbHaloArgs halo;
     memset(&halo, 0, sizeof(halo));
     if (halo_in) halo = *halo_in;
-    if (halo.enabled && p->kernel != 3 && p->kernel != 4 && p->kernel != 5) {
+    if (halo.enabled && p->kernel != 3 && p->kernel != 4) {
         gsb_set_error("fused halo exchange needs the ring kernels (3/4)");
         return GSB_ERR_ARG;
     }
@@ -1066,46 +850,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
     if (nb <= 0) return GSB_OK;
     const int row0 = p->color_start[c], row1 = p->color_start[c + 1];
     const int eff = gsb_plan_effective_kernel(p, NRHS);
-    if (eff == 5) {
-        // RHS-serial window ring (NRHS >= 2); ring B depth from the shared memory left after ring A
-        static int env_sb = -1;
-        if (env_sb < 0) {
-            const char *e = getenv("GSB_RSER_SB");
-            env_sb = e ? atoi(e) : 0;
-        }
-        const RserLayout RL = rser_layout(p->cap, check, p->wcap);
-        int sb = env_sb ? env_sb : 3;
-        if (sb < 2) sb = 2;
-        if (sb > 4) sb = 4;
-        const int smem = 64 + GS_RSER_SA * RL.a_bytes + sb * RL.b_bytes;
-        typedef void (*rser_fn)(const int *, const int *, const double *, const double *, double *, int64_t, int, int,
-                                int, const int *, const int *, int, int, const GsCtl *, double *, const GsbHaloArgs);
-#define GSB_RSER_PICK(SBV) (check ? (rser_fn)gs_phase_rser<NRHS, true, SBV> : (rser_fn)gs_phase_rser<NRHS, false, SBV>)
-        rser_fn kern = sb == 2 ? GSB_RSER_PICK(2) : sb == 3 ? GSB_RSER_PICK(3) : GSB_RSER_PICK(4);
-#undef GSB_RSER_PICK
-        struct Cfg { const void *fn; int smem, occ; };
-        static Cfg cfgs[32];
-        static int ncfg = 0;
-        Cfg *cf = nullptr;
-        for (int q = 0; q < ncfg; ++q)
-            if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem) cf = &cfgs[q];
-        if (!cf) {
-            if (smem > 48 * 1024)
-                GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            int o = 0;
-            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
-            if (ncfg == 32) ncfg = 0;
-            cf = &cfgs[ncfg++];
-            cf->fn = (const void *)kern;
-            cf->smem = smem;
-            cf->occ = o < 1 ? 1 : o;
-        }
-        int grid = gsb_sm_count() * cf->occ;
-        if (grid > nb) grid = nb;
-        kern<<<grid, GS_THREADS, smem, st>>>(rp, p->ci_slot.p, va, b, x, ld, row0, row1, nb, p->tile_k.p + p->tile_off[c],
-                                             p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC, p->cap, p->wcap, ctl,
-                                             partials, halo);
-    } else if (eff == 3 || eff == 4) {
+    if (eff == 3 || eff == 4) {
         // tuning knobs (defaults measured on B200, see profiles/README.md); overridable for experiments
         static int env_stages = -1, env_ctas = -1;
         if (env_stages < 0) {
@@ -1144,7 +889,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
             if (smem > 48 * 1024)
                 GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             int o = 0;
-            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
+            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS * NRHS, smem));
             if (ncfg == 64) ncfg = 0;
             cf = &cfgs[ncfg++];
             cf->fn = (const void *)kern;
@@ -1155,7 +900,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
-        kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
+        kern<<<grid, GS_THREADS * NRHS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
                                              ctl, partials, halo);
     } else if (eff == 2) {
         auto kt = gs_phase_staged<NRHS, true>;

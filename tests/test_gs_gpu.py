@@ -296,11 +296,10 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
     bb = b[:nrhs] if nrhs > 1 else b[0]
     res = {}
-    for k in (1, 2, 3, 4, 5):
+    for k in (1, 2, 3, 4):
         for ce in (1, 3):
             x = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=12, options=gsb.SparseMatrix.options(kernel=k, check_every=ce))
-            # kernel 5 (right-hand sides one after another inside a tile) only exists for nrhs >= 2
-            assert sp.last_stats.kernel_used == (4 if (k == 5 and nrhs == 1) else k) and sp.last_stats.sweeps == 12
+            assert sp.last_stats.kernel_used == k and sp.last_stats.sweeps == 12
             res[(k, ce)] = (x, sp.last_stats.last_eps[0])
     x0, e0 = res[(1, 1)]
     for key, (x, e) in res.items():
@@ -317,4 +316,4 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
         sg.gaussSeidel(b2, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=4))
     # auto on the grid picks the window kernel
     sp.gaussSeidel(bb, epsilon=0.0, max_iteration=1)
-    assert sp.last_stats.kernel_used == (4 if nrhs == 1 else 3)  # measured policy, see gsb_plan_effective_kernel
+    assert sp.last_stats.kernel_used == 4
