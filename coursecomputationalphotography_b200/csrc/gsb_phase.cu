@@ -245,7 +245,7 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check,
 }
 
 template <int NRHS, bool CHECK, int STAGES, bool WIN>
-__global__ void __launch_bounds__(GS_THREADS * NRHS, (NRHS == 1 ? 4 : 2))
+__global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
                   const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
@@ -360,11 +360,11 @@ __global__ void __launch_bounds__(GS_THREADS * NRHS, (NRHS == 1 ? 4 : 2))
         }
     }
 
-    // consumers: one thread per (row, right-hand side); warps [8r, 8r+8) own plane r of the tile
-    const int r = tid / GS_THREADS;   // right-hand side of this thread (warp-uniform)
-    const int lt = tid % GS_THREADS;  // row inside the tile
-    const int lane = tid & 31, wid = tid >> 5;
-    __shared__ double red_ws[NRHS * (GS_THREADS / 32)];
+    // stop-rule partial: accumulated per thread over the CTA's tiles (static schedule -> fixed order) and folded
+    // once at the end into partial slot blockIdx.x; the phase's other slots are zeroed
+    double acc[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
     int k = 0;
     for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
         const int t = tile_of(tl);
@@ -388,80 +388,81 @@ __global__ void __launch_bounds__(GS_THREADS * NRHS, (NRHS == 1 ? 4 : 2))
         const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
         const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
         const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
+        const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off);
         // kernel 4: in a window tile the staged index array holds shared-memory slots (-1 marks the diagonal),
         // precomputed by plan_tile_slots; otherwise it holds column numbers and gathers go to global memory
         const bool use_win = WIN && hdr[1] > 0;
-        const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off) + (size_t)r * wcap;
-        const double *xg = x + r * n;
-        const int i = r_begin + lt;
+        auto xval = [&](int c, int r) -> double {
+            if (use_win) return xw_s[(size_t)r * wcap + c];
+            return __ldg(x + r * n + c);
+        };
+        const int i = r_begin + tid;
         const int diag_mark = use_win ? -1 : i;
-        const bool valid = lt < rows;
-        double diff = 0.0;
+        const bool valid = tid < rows;
         if (valid) {
-            const int rs = rp_s[lt], len = rp_s[lt + 1] - rs;
+            const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
             const double *vrow = va_s + rs;
             const int *crow = ci_s + rs;
-            double sig = 0.0, d = 0.0;
+            double sig[NRHS];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+            double d = 0.0;
             if (len <= GS_UNROLL) {
                 int cc[GS_UNROLL];
-                double xv[GS_UNROLL];
+                double xg[GS_UNROLL][NRHS];
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) cc[j] = j < len ? crow[j] : diag_mark;
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) { // all gathers of the row in flight before the first use
                     const bool off = cc[j] != diag_mark;
-                    xv[j] = off ? (use_win ? xw_s[cc[j]] : __ldg(xg + cc[j])) : 0.0;
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? xval(cc[j], r) : 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < GS_UNROLL; ++j) {
                     if (j < len) {
                         const double v = vrow[j];
-                        if (cc[j] == diag_mark)
+                        if (cc[j] == diag_mark) {
                             d = v;
-                        else
-                            sig = __dadd_rn(sig, __dmul_rn(v, xv[j]));
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xg[j][r]));
+                        }
                     }
                 }
             } else {
                 for (int j = 0; j < len; ++j) {
                     const int c = crow[j];
                     const double v = vrow[j];
-                    if (c == diag_mark)
+                    if (c == diag_mark) {
                         d = v;
-                    else
-                        sig = __dadd_rn(sig, __dmul_rn(v, use_win ? xw_s[c] : __ldg(xg + c)));
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xval(c, r)));
+                    }
                 }
             }
-            if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
-                const int po = (r_begin & 1) + lt;
-                const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
-                const double xn = __ddiv_rn(__dsub_rn(bb, sig), d);
-                if (CHECK) diff = fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
-                x[r * n + i] = xn;
-                if (tinfo & 2) { // a neighbour GPU reads this row: store it into its ghost slot as well
+            if (d != 0.0) {
+                const int po = (r_begin & 1) + tid;
 #pragma unroll
-                    for (int pr = 0; pr < 2; ++pr)
-                        if (halo.has_peer[pr]) {
-                            const int slot = halo.push_map[pr][i];
-                            if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
-                        }
+                for (int r = 0; r < NRHS; ++r) {
+                    const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
+                    const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
+                    if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
+                    x[r * n + i] = xn;
+                    if (tinfo & 2) { // a neighbour GPU reads this row: store it into its ghost slot as well
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr)
+                            if (halo.has_peer[pr]) {
+                                const int slot = halo.push_map[pr][i];
+                                if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
+                            }
+                    }
                 }
             }
         }
         if (tinfo & 2) __threadfence_system(); // peer stores visible before this tile is counted as done
-        if (CHECK) { // fixed-order fold: shuffle tree inside a warp, then the 8 warps of a plane in order
-            double v = diff;
-#pragma unroll
-            for (int dlt = 16; dlt > 0; dlt >>= 1) v += __shfl_down_sync(0xffffffffu, v, dlt);
-            if (lane == 0) red_ws[wid] = v;
-        }
         __syncthreads(); // every thread is done with stage s
-        if (CHECK && tid < NRHS) {
-            double sum = 0.0;
-#pragma unroll
-            for (int w = 0; w < GS_THREADS / 32; ++w) sum += red_ws[tid * (GS_THREADS / 32) + w];
-            partials[(size_t)t * NRHS + tid] = sum;
-        }
         if (tid == 0 && tinfo) {
             // last halo tile of the phase: every ghost read and every push of this phase is complete ->
             // raise the neighbours' flags (release at system scope orders the pushes before the flag)
@@ -477,6 +478,11 @@ __global__ void __launch_bounds__(GS_THREADS * NRHS, (NRHS == 1 ? 4 : 2))
             }
         }
         if (tid == 0 && tln < ntiles) issue(next_desc, tn, s);
+    }
+    if (CHECK) {
+        gsb_block_reduce_store<NRHS, GS_THREADS>(acc, partials + (size_t)blockIdx.x * NRHS);
+        for (int t2 = blockIdx.x + gridDim.x; t2 < ntiles; t2 += gridDim.x)
+            if (tid < NRHS) partials[(size_t)t2 * NRHS + tid] = 0.0;
     }
 }
 
@@ -713,12 +719,15 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
     }
 }
 
-// Kernel that actually runs for `nrhs` right-hand sides.  plan->kernel == 4 means "gather windows available";
-// a caller that asked for kernel 3 gets the same ring with global gathers.
+// Kernel that actually runs for `nrhs` right-hand sides.  plan->kernel == 4 means "gather windows available".
+// Measured on B200 (profiles/README.md): one right-hand side is fastest with the windows (4); with several
+// fused right-hand sides a window stage (49 KB at k = 3) leaves room for two CTAs per SM only, and the ring
+// with global gathers (3), which fits three, wins.  Kernel 4 stays selectable explicitly.
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
-    (void)nrhs;
-    if (p->kernel == 4 && p->requested == 3) return 3;
-    return p->kernel;
+    if (p->kernel != 4) return p->kernel;
+    if (p->requested == 4) return 4;
+    if (p->requested == 3) return 3;
+    return nrhs >= 2 ? 3 : 4;
 }
 
 int GsbPlan::total_blocks() const {
@@ -772,7 +781,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
         }
         // kernel 4: gather windows, if (nearly) every tile's gathers fit a few contiguous spans of x
         p->wcap = 0;
-        if (p->kernel == 3) { // windows are probed even when kernel 3 was requested (cheap; keeps one plan per matrix)
+        if (p->kernel == 3) { // windows are probed even when kernel 3 was requested: one plan per matrix
             int total = 0;
             for (int c = 0; c < n_colors; ++c) {
                 p->win_off[c] = total;
@@ -817,7 +826,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
             gsb_set_error("window kernel unavailable: the gathers of this matrix do not form contiguous windows");
             return GSB_ERR_ARG;
         }
-        if (p->kernel != 3 && kernel_request == 3) {
+        if (p->kernel != 3 && p->kernel != 4 && kernel_request == 3) {
             gsb_set_error("ring kernel unavailable for this matrix (rows too long); use kernel 0/1/2");
             return GSB_ERR_ARG;
         }
@@ -889,7 +898,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
             if (smem > 48 * 1024)
                 GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             int o = 0;
-            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS * NRHS, smem));
+            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
             if (ncfg == 64) ncfg = 0;
             cf = &cfgs[ncfg++];
             cf->fn = (const void *)kern;
@@ -900,7 +909,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
-        kern<<<grid, GS_THREADS * NRHS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
+        kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
                                              ctl, partials, halo);
     } else if (eff == 2) {
         auto kt = gs_phase_staged<NRHS, true>;

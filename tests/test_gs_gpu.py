@@ -304,7 +304,15 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     x0, e0 = res[(1, 1)]
     for key, (x, e) in res.items():
         assert np.array_equal(x, x0), key
-        assert e == e0, key  # fixed-order partial sums: the stop norm is identical too
+        # the stop norm is summed in a fixed but kernel-specific order: equal to rounding
+        assert abs(e - e0) <= 1e-12 * abs(e0), key
+    # ... and run-to-run identical for one kernel
+    for k in (3, 4):
+        o = gsb.SparseMatrix.options(kernel=k)
+        sp.gaussSeidel(bb, epsilon=0.0, max_iteration=5, options=o)
+        e1 = sp.last_stats.last_eps[0]
+        sp.gaussSeidel(bb, epsilon=0.0, max_iteration=5, options=o)
+        assert sp.last_stats.last_eps[0] == e1
     # a general (multicolour) matrix through the staged/ring kernels
     r, c, v, b2, _ = wl.diag_dominant_system(7001, 6, seed=13)
     sg = gsb.SparseMatrix(np.float64)
@@ -316,4 +324,4 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
         sg.gaussSeidel(b2, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=4))
     # auto on the grid picks the window kernel
     sp.gaussSeidel(bb, epsilon=0.0, max_iteration=1)
-    assert sp.last_stats.kernel_used == 4
+    assert sp.last_stats.kernel_used == (4 if nrhs == 1 else 3)  # measured policy, see gsb_plan_effective_kernel
