@@ -91,8 +91,8 @@ struct gsb_dist {
     int64_t ld = 0; // n_local + n_ghost: leading dimension of xw / bw
     int64_t nnz_local = 0;
     int color_start[3] = {0, 0, 0};
-    DevBuf<int> perm, iperm, rp, ci;
-    DevBuf<double> va;
+    DevBuf<int> perm, iperm, rp, ci; // rp/ci/va: off-diagonal entries only
+    DevBuf<double> va, dg;          // dg: diagonal per (permuted) local row
     // halo: peer 0 = rank-1 (rows above), peer 1 = rank+1 (rows below); second index = colour
     int need_cnt[2][2] = {{0, 0}, {0, 0}};
     int ghost_start[2][2] = {{0, 0}, {0, 0}};
@@ -244,12 +244,16 @@ __global__ void __launch_bounds__(256) d_ghost_place(const int *__restrict__ sca
     }
 }
 
+// off-diagonal row lengths in permuted order
 __global__ void __launch_bounds__(256) d_perm_len(const int *__restrict__ perm, const int *__restrict__ rp_nat,
-                                                  int n_local, int *__restrict__ len) {
+                                                  const int *__restrict__ cg_nat, int64_t row0, int n_local,
+                                                  int *__restrict__ len) {
     int p = blockIdx.x * 256 + threadIdx.x;
     if (p < n_local) {
         int o = perm[p];
-        len[p] = rp_nat[o + 1] - rp_nat[o];
+        int off = 0;
+        for (int k = rp_nat[o]; k < rp_nat[o + 1]; ++k) off += cg_nat[k] != row0 + o;
+        len[p] = off;
     }
     if (p == n_local) len[p] = 0;
 }
@@ -261,18 +265,25 @@ __global__ void __launch_bounds__(128) d_fill_rows(const int *__restrict__ perm,
                                                    int64_t row1, int halo_lo, int W, const int *__restrict__ map_lo,
                                                    const int *__restrict__ map_hi, const int *__restrict__ rp,
                                                    int *__restrict__ ci, double *__restrict__ va,
-                                                   int *__restrict__ bad) {
+                                                   double *__restrict__ dg, int *__restrict__ bad) {
     int p = blockIdx.x * 128 + threadIdx.x;
     if (p >= n_local) return;
     const int o = perm[p];
-    const int src = rp_nat[o], len = rp_nat[o + 1] - src, dst = rp[p];
+    const int src = rp_nat[o], len_all = rp_nat[o + 1] - src, dst = rp[p];
+    const int len = rp[p + 1] - dst;
     const int my_par = parity_of(row0 + o, W);
-    for (int k = 0; k < len; ++k) { // insertion sort on key (colour, global id); ci temporarily holds global ids
+    double d = 0.0;
+    int w = 0;
+    for (int k = 0; k < len_all; ++k) { // insertion sort on key (colour, global id); ci temporarily holds global ids
         int g = cg_nat[src + k];
         double v = va_nat[src + k];
+        if (g == row0 + o) { // the diagonal goes to its own array
+            d = v;
+            continue;
+        }
         int gp = parity_of(g, W);
-        if (g != row0 + o && gp == my_par) atomicOr(bad, 1); // parity colouring improper for this matrix
-        int q = dst + k;
+        if (gp == my_par) atomicOr(bad, 1); // parity colouring improper for this matrix
+        int q = dst + w;
         while (q > dst) {
             int h = ci[q - 1];
             int hp = parity_of(h, W);
@@ -283,7 +294,9 @@ __global__ void __launch_bounds__(128) d_fill_rows(const int *__restrict__ perm,
         }
         ci[q] = g;
         va[q] = v;
+        ++w;
     }
+    dg[p] = d;
     for (int k = 0; k < len; ++k) {
         int64_t g = ci[dst + k];
         int l;
@@ -442,15 +455,16 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
 
     // 5. colour-major local CSR
     GSB_TRY(d->rp.alloc((int64_t)n_local + 1 + 8));
-    d_perm_len<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(d->perm.p, d->nat_rp.p, n_local, d->rp.p);
+    d_perm_len<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(d->perm.p, d->nat_rp.p, d->nat_cg.p, row0, n_local, d->rp.p);
     GSB_KERNEL_CHECK();
     GSB_TRY(gsb_exclusive_scan_i32(d->rp.p, d->rp.p, (int64_t)n_local + 1, nullptr, st));
     GSB_TRY(d->ci.alloc((int64_t)nnz + 8));
     GSB_TRY(d->va.alloc((int64_t)nnz + 8));
+    GSB_TRY(d->dg.alloc((int64_t)n_local + 8));
     GSB_CUDA(cudaMemsetAsync(mm.p + 2, 0, sizeof(int), st));
     d_fill_rows<<<(n_local + 127) / 128, 128, 0, st>>>(d->perm.p, d->iperm.p, d->nat_rp.p, d->nat_cg.p, d->nat_va.p,
                                                       n_local, row0, row1, halo_lo, W, map_lo.p, map_hi.p, d->rp.p,
-                                                      d->ci.p, d->va.p, mm.p + 2);
+                                                      d->ci.p, d->va.p, d->dg.p, mm.p + 2);
     GSB_KERNEL_CHECK();
     int h_bad = 0;
     GSB_CUDA(cudaMemcpyAsync(&h_bad, mm.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -871,7 +885,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         ha.signal_epoch = (int)(epoch_base + sidx + 1);
                         ha.counter = d->flags.p + 4 + c;
                     }
-                    status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->bw.p, d->xw.p, ld, nrhs, check,
+                    status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p, d->xw.p, ld, nrhs, check,
                                              ctl, d->partials.p + (size_t)poff * nrhs, st, use_peer ? &ha : nullptr);
                     poff += d->plan.blocks[c];
                     ++launches;
@@ -933,11 +947,12 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
 
 // ||b - A x||_2 over all strips: x's ghost values are fetched from the neighbours first
 __global__ void __launch_bounds__(256) d_resid(const int *__restrict__ rp, const int *__restrict__ ci,
-                                               const double *__restrict__ va, const double *__restrict__ b,
-                                               const double *__restrict__ x, int n_local, double *__restrict__ acc) {
+                                               const double *__restrict__ va, const double *__restrict__ dg,
+                                               const double *__restrict__ b, const double *__restrict__ x, int n_local,
+                                               double *__restrict__ acc) {
     double s2 = 0.0;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n_local; i += gridDim.x * 256) {
-        double s = 0.0;
+        double s = dg[i] * x[i];
         for (int k = rp[i]; k < rp[i + 1]; ++k) s += va[k] * x[ci[k]];
         double r = b[i] - s;
         s2 += r * r;
@@ -968,7 +983,7 @@ extern "C" int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const 
     DevBuf<double> acc;
     GSB_TRY(acc.alloc(1));
     GSB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), st));
-    d_resid<<<gsb_blocks_for(n_local, 256, gsb_sm_count() * 8), 256, 0, st>>>(d->rp.p, d->ci.p, d->va.p, d->bw.p,
+    d_resid<<<gsb_blocks_for(n_local, 256, gsb_sm_count() * 8), 256, 0, st>>>(d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p,
                                                                              d->xw.p, n_local, acc.p);
     GSB_KERNEL_CHECK();
     if (d->world > 1) GSB_NCCL(g_nccl.AllReduce(acc.p, acc.p, 1, ncclFloat64, ncclSum, d->comm, st));

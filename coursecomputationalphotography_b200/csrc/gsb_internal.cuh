@@ -120,8 +120,10 @@ struct gsb_matrix {
     DevBuf<int> iperm;     // iperm[old] = new
     DevBuf<int> colors;    // colour[old]
     DevBuf<int> rp;        // n_rows+1
-    DevBuf<int> ci;        // nnz (permuted column ids, ascending per row)
-    DevBuf<double> va;     // nnz
+    DevBuf<int> ci;        // off-diagonal entries only (permuted column ids, ascending per row)
+    DevBuf<double> va;     // their values
+    DevBuf<double> dg;     // dg[new row] = diagonal value, 0 when the row stores none (row skipped, v2 :360-363)
+    int64_t nnz_off = 0;   // entries in ci/va
     // staged-kernel tiling (gsb_solve.cu)
     DevBuf<int4> tiles;    // per tile: {row0, nrows, nnz0_aligned, nnz_count_aligned}
     int tile_rows = 0;
@@ -207,8 +209,9 @@ struct GsbHaloArgs {
 };
 
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles
-int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
-                    double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
+// rp/ci/va: off-diagonal CSR in colour-major order; dg: the diagonal (0 = row skipped)
+int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
+                    const double *b, double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
                     cudaStream_t st, const GsbHaloArgs *halo = nullptr);
 // end of sweep.  mode 0: fold partials, bump the counter, decide (single GPU)
 //                mode 1: fold partials into ctl->eps_last only (strip solver, before the all-reduce)

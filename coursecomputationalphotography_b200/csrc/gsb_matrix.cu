@@ -24,6 +24,7 @@ void gsb_matrix::drop_analysis() {
     rp.release();
     ci.release();
     va.release();
+    dg.release();
     tiles.release();
     xw.release();
     bw.release();
@@ -228,10 +229,18 @@ __global__ void __launch_bounds__(256) color_place(const int *__restrict__ color
     }
 }
 
-__global__ void __launch_bounds__(256) perm_row_len(const int *__restrict__ perm, const int *__restrict__ row_nnz,
+// off-diagonal length of every row in permuted order (the diagonal goes to its own array)
+__global__ void __launch_bounds__(256) perm_row_len(const int *__restrict__ perm, const int *__restrict__ row_begin,
+                                                    const int *__restrict__ row_nnz, const int *__restrict__ cols,
                                                     int n_rows, int *__restrict__ len) {
     int p = blockIdx.x * 256 + threadIdx.x;
-    if (p < n_rows) len[p] = row_nnz[perm[p]];
+    if (p < n_rows) {
+        const int old = perm[p];
+        const int src = row_begin[old], cnt = row_nnz[old];
+        int off = 0;
+        for (int k = 0; k < cnt; ++k) off += cols[src + k] != old;
+        len[p] = off;
+    }
     if (p == n_rows) len[p] = 0;
 }
 
@@ -240,16 +249,24 @@ __global__ void __launch_bounds__(128) perm_fill_rows(const int *__restrict__ pe
                                                       const int *__restrict__ row_nnz,
                                                       const int *__restrict__ cols, const double *__restrict__ vals,
                                                       int n_rows, const int *__restrict__ rp, int *__restrict__ ci,
-                                                      double *__restrict__ va) {
+                                                      double *__restrict__ va, double *__restrict__ dg) {
     int p = blockIdx.x * 128 + threadIdx.x;
     if (p >= n_rows) return;
     int old = perm[p];
     int src = row_begin[old], len = row_nnz[old], dst = rp[p];
-    // insertion sort by permuted column while copying (rows are short and nearly sorted)
+    // insertion sort by permuted column while copying (rows are short and nearly sorted); the diagonal entry
+    // (what at(i,i) finds, v2 :360) is split off into dg
+    double d = 0.0;
+    int w = 0;
     for (int k = 0; k < len; ++k) {
-        int c = iperm[cols[src + k]];
+        int co = cols[src + k];
         double v = vals[src + k];
-        int q = dst + k;
+        if (co == old) {
+            d = v;
+            continue;
+        }
+        int c = iperm[co];
+        int q = dst + w;
         while (q > dst && ci[q - 1] > c) {
             ci[q] = ci[q - 1];
             va[q] = va[q - 1];
@@ -257,7 +274,9 @@ __global__ void __launch_bounds__(128) perm_fill_rows(const int *__restrict__ pe
         }
         ci[q] = c;
         va[q] = v;
+        ++w;
     }
+    dg[p] = d;
 }
 
 static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
@@ -287,13 +306,18 @@ static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
         return GSB_ERR_COLORING;
     }
     GSB_TRY(m->rp.alloc((int64_t)n + 1 + 8)); // +8: aligned bulk copies may over-read
-    perm_row_len<<<(n + 1 + 255) / 256, 256, 0, st>>>(m->perm.p, m->row_nnz.p, n, m->rp.p);
+    perm_row_len<<<(n + 1 + 255) / 256, 256, 0, st>>>(m->perm.p, m->row_begin.p, m->row_nnz.p, m->cols.p, n, m->rp.p);
     GSB_KERNEL_CHECK();
     GSB_TRY(gsb_exclusive_scan_i32(m->rp.p, m->rp.p, (int64_t)n + 1, nullptr, st));
-    GSB_TRY(m->ci.alloc(m->nnz + 8)); // +8: the staged kernel's 16-byte aligned bulk copies may over-read
-    GSB_TRY(m->va.alloc(m->nnz + 8));
+    int nnz_off = 0;
+    GSB_CUDA(cudaMemcpyAsync(&nnz_off, m->rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    m->nnz_off = nnz_off;
+    GSB_TRY(m->ci.alloc(m->nnz_off + 8)); // +8: the staged kernels' 16-byte aligned bulk copies may over-read
+    GSB_TRY(m->va.alloc(m->nnz_off + 8));
+    GSB_TRY(m->dg.alloc((int64_t)n + 8));
     perm_fill_rows<<<(n + 127) / 128, 128, 0, st>>>(m->perm.p, m->iperm.p, m->row_begin.p, m->row_nnz.p, m->cols.p,
-                                                   m->vals(), n, m->rp.p, m->ci.p, m->va.p);
+                                                   m->vals(), n, m->rp.p, m->ci.p, m->va.p, m->dg.p);
     GSB_KERNEL_CHECK();
     GSB_CUDA(cudaStreamSynchronize(st));
     return GSB_OK;

@@ -16,13 +16,53 @@
 //                    global memory; for short rows all gathers of a row are issued before the first is
 //                    consumed.  HBM sees long contiguous bursts instead of 32-byte sectors.
 // The stop rule's L1 update norm is accumulated per block into `partials` (fixed order, no atomics).
+//
+// Solver format: the colour-major CSR holds the OFF-DIAGONAL entries only (rp/ci/va) and the diagonal lives in
+// its own array dg[row] (0 when the row has no diagonal -> the row is skipped).  The row body then has no
+// per-entry "is this the diagonal" test, and a 5-point row has at most 4 entries.
 #include "gsb_internal.cuh"
 
 #include <stdlib.h>
 
 #define GS_THREADS 256
 #define GS_TILE_CAP_MAX 6144 // CSR entries per tile that still leave >= 3 CTAs per SM (72 KB each)
-#define GS_UNROLL 6          // rows up to this length take the gather-prefetch path (5-point rows have <= 5)
+#define GS_UNROLL 4          // rows with up to this many off-diagonal entries take the gather-prefetch path (5-point rows)
+
+// sigma_r = sum_j v_j * x_r[c_j] over the row's off-diagonal entries, storage order, product and sum rounded
+// separately.  XV(c, r) yields x_r[c] (global memory or a shared-memory window).  For short rows all gathers are
+// issued before the first is consumed; padded positions load index 0 (always valid) and are not accumulated.
+template <int NRHS, typename XV>
+__device__ __forceinline__ void gs_row_sigma(const int *__restrict__ crow, const double *__restrict__ vrow, int len,
+                                             XV xv, double (&sig)[NRHS]) {
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+    if (len <= GS_UNROLL) {
+        int cc[GS_UNROLL];
+        double vv[GS_UNROLL], xg[GS_UNROLL][NRHS];
+#pragma unroll
+        for (int j = 0; j < GS_UNROLL; ++j) {
+            cc[j] = j < len ? crow[j] : 0;
+            vv[j] = j < len ? vrow[j] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < GS_UNROLL; ++j)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) xg[j][r] = xv(cc[j], r);
+#pragma unroll
+        for (int j = 0; j < GS_UNROLL; ++j)
+            if (j < len) {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(vv[j], xg[j][r]));
+            }
+    } else {
+        for (int j = 0; j < len; ++j) {
+            const int c = crow[j];
+            const double v = vrow[j];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xv(c, r)));
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernel 1: row per thread, direct global loads
@@ -30,8 +70,8 @@
 template <int NRHS, bool CHECK>
 __global__ void __launch_bounds__(GS_THREADS)
     gs_phase_direct(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                    const double *__restrict__ b, double *x, int64_t n, int row0, int row1,
-                    const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
+                    const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0,
+                    int row1, const GsCtl *__restrict__ ctl, double *__restrict__ partials) {
     if (*(volatile const int *)&ctl->done) return;
     const int i = row0 + blockIdx.x * GS_THREADS + threadIdx.x;
     double diff[NRHS];
@@ -39,20 +79,9 @@ __global__ void __launch_bounds__(GS_THREADS)
     for (int r = 0; r < NRHS; ++r) diff[r] = 0.0;
     if (i < row1) {
         const int k0 = rp[i], k1 = rp[i + 1];
+        const double d = dg[i];
         double sig[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
-        double d = 0.0;
-        for (int k = k0; k < k1; ++k) {
-            const int c = ci[k];
-            const double v = va[k];
-            if (c == i) {
-                d = v;
-            } else {
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, x[r * n + c]));
-            }
-        }
+        gs_row_sigma<NRHS>(ci + k0, va + k0, k1 - k0, [&](int c, int r) { return x[r * n + c]; }, sig);
         if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
 #pragma unroll
             for (int r = 0; r < NRHS; ++r) {
@@ -105,8 +134,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 template <int NRHS, bool CHECK>
 __global__ void __launch_bounds__(GS_THREADS, 4)
     gs_phase_staged(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                    const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int tile_rows,
-                    const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
+                    const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0,
+                    int row1, int tile_rows, const int *__restrict__ tile_k, int cap, const GsCtl *__restrict__ ctl,
                     double *__restrict__ partials) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -132,12 +161,13 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
     const int i = r_begin + threadIdx.x;
     const bool valid = threadIdx.x < tile_rows && i < r_end;
     int rs = 0, re = 0;
-    double bb[NRHS], xo[NRHS], diff[NRHS];
+    double d = 0.0, bb[NRHS], xo[NRHS], diff[NRHS];
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) bb[r] = xo[r] = diff[r] = 0.0;
     if (valid) {
         rs = rp[i];
         re = rp[i + 1];
+        d = dg[i];
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
             bb[r] = b[r * n + i];
@@ -147,51 +177,8 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
     mbar_wait(mbar, 0);
 
     if (valid) {
-        const int len = re - rs;
-        const double *vrow = va_s + (rs - kv0);
-        const int *crow = ci_s + (rs - kc0);
         double sig[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
-        double d = 0.0;
-        if (len <= GS_UNROLL) {
-            int cc[GS_UNROLL];
-            double vv[GS_UNROLL], xg[GS_UNROLL][NRHS];
-#pragma unroll
-            for (int j = 0; j < GS_UNROLL; ++j) {
-                const bool on = j < len;
-                cc[j] = on ? crow[j] : i;
-                vv[j] = on ? vrow[j] : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < GS_UNROLL; ++j) { // every gather of the row is in flight before the first use
-                const bool off = j < len && cc[j] != i;
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? x[r * n + cc[j]] : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < GS_UNROLL; ++j) {
-                if (j < len) {
-                    if (cc[j] == i) {
-                        d = vv[j];
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(vv[j], xg[j][r]));
-                    }
-                }
-            }
-        } else {
-            for (int j = 0; j < len; ++j) {
-                const int c = crow[j];
-                const double v = vrow[j];
-                if (c == i) {
-                    d = v;
-                } else {
-#pragma unroll
-                    for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, x[r * n + c]));
-                }
-            }
-        }
+        gs_row_sigma<NRHS>(ci_s + (rs - kc0), va_s + (rs - kv0), re - rs, [&](int c, int r) { return x[r * n + c]; }, sig);
         if (d != 0.0) {
 #pragma unroll
             for (int r = 0; r < NRHS; ++r) {
@@ -227,14 +214,15 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 #define GS_WIN_DESC 12         // ints per tile descriptor
 
 struct RingLayout {
-    int va_off, b_off, xo_off, xw_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
+    int va_off, dg_off, b_off, xo_off, xw_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
 };
 
 __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check, int wcap) {
     RingLayout L;
     L.plane = GS_THREADS + 2;
     L.va_off = 0;
-    L.b_off = L.va_off + cap * 8;
+    L.dg_off = L.va_off + cap * 8;
+    L.b_off = L.dg_off + L.plane * 8;
     L.xo_off = L.b_off + nrhs * L.plane * 8;
     L.xw_off = L.xo_off + (check ? nrhs * L.plane * 8 : 0);
     L.ci_off = L.xw_off + nrhs * wcap * 8;
@@ -247,7 +235,8 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check,
 template <int NRHS, bool CHECK, int STAGES, bool WIN>
 __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                  const double *__restrict__ b, double *x, int64_t n, int row0, int row1, int ntiles,
+                  const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0,
+                  int row1, int ntiles,
                   const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
                   const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -304,7 +293,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
         const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
         const int ea = r_begin & ~1; // n (the leading dimension) is even: the same alignment for every plane
         const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
-        uint32_t total = bytes_v + bytes_c + bytes_r + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
+        uint32_t total = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
         int nwin = 0, lo[GS_WIN_MAX], len[GS_WIN_MAX];
         if (WIN) {
             nwin = td.w0.x;
@@ -324,6 +313,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
         if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
         if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
         bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
+        bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
             bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
@@ -389,61 +379,20 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
         const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
         const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
         const double *xw_s = reinterpret_cast<const double *>(st + L.xw_off);
-        // kernel 4: in a window tile the staged index array holds shared-memory slots (-1 marks the diagonal),
-        // precomputed by plan_tile_slots; otherwise it holds column numbers and gathers go to global memory
+        // kernel 4: in a window tile the staged index array holds shared-memory slots precomputed by
+        // plan_tile_slots; otherwise it holds column numbers and the gathers go to global memory
         const bool use_win = WIN && hdr[1] > 0;
-        auto xval = [&](int c, int r) -> double {
-            if (use_win) return xw_s[(size_t)r * wcap + c];
-            return __ldg(x + r * n + c);
-        };
         const int i = r_begin + tid;
-        const int diag_mark = use_win ? -1 : i;
-        const bool valid = tid < rows;
-        if (valid) {
+        if (tid < rows) {
             const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
-            const double *vrow = va_s + rs;
-            const int *crow = ci_s + rs;
+            const int po = (r_begin & 1) + tid;
+            const double d = reinterpret_cast<const double *>(st + L.dg_off)[po];
             double sig[NRHS];
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
-            double d = 0.0;
-            if (len <= GS_UNROLL) {
-                int cc[GS_UNROLL];
-                double xg[GS_UNROLL][NRHS];
-#pragma unroll
-                for (int j = 0; j < GS_UNROLL; ++j) cc[j] = j < len ? crow[j] : diag_mark;
-#pragma unroll
-                for (int j = 0; j < GS_UNROLL; ++j) { // all gathers of the row in flight before the first use
-                    const bool off = cc[j] != diag_mark;
-#pragma unroll
-                    for (int r = 0; r < NRHS; ++r) xg[j][r] = off ? xval(cc[j], r) : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < GS_UNROLL; ++j) {
-                    if (j < len) {
-                        const double v = vrow[j];
-                        if (cc[j] == diag_mark) {
-                            d = v;
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xg[j][r]));
-                        }
-                    }
-                }
-            } else {
-                for (int j = 0; j < len; ++j) {
-                    const int c = crow[j];
-                    const double v = vrow[j];
-                    if (c == diag_mark) {
-                        d = v;
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xval(c, r)));
-                    }
-                }
-            }
-            if (d != 0.0) {
-                const int po = (r_begin & 1) + tid;
+            if (use_win)
+                gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int c, int r) { return xw_s[(size_t)r * wcap + c]; }, sig);
+            else
+                gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int c, int r) { return __ldg(x + r * n + c); }, sig);
+            if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
 #pragma unroll
                 for (int r = 0; r < NRHS; ++r) {
                     const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
@@ -504,7 +453,6 @@ __global__ void __launch_bounds__(GS_THREADS) plan_tile_windows(const int *__res
     if (i < row1) {
         for (int k = rp[i]; k < rp[i + 1]; ++k) {
             const int c = ci[k];
-            if (c == i) continue;
             const int g = c / GS_WIN_GRANULE;
             unsigned h = ((unsigned)g * 2654435761u) % TABLE;
             for (int probe = 0; probe < TABLE; ++probe) {
@@ -564,8 +512,8 @@ __global__ void __launch_bounds__(GS_THREADS) plan_tile_windows(const int *__res
     }
 }
 
-// Index array of kernel 4: for a window tile, the shared-memory slot of every off-diagonal entry (-1 for the
-// diagonal); for a fallback tile, the column number unchanged.
+// Index array of kernel 4: for a window tile, the shared-memory slot of every (off-diagonal) entry; for a
+// fallback tile, the column number unchanged.
 __global__ void __launch_bounds__(GS_THREADS) plan_tile_slots(const int *__restrict__ rp, const int *__restrict__ ci,
                                                               int row0, int row1, const int *__restrict__ desc,
                                                               int *__restrict__ ci_slot) {
@@ -584,15 +532,12 @@ __global__ void __launch_bounds__(GS_THREADS) plan_tile_slots(const int *__restr
         const int c = ci[k];
         int out = c;
         if (nwin > 0) {
-            out = -1;
-            if (c != i) {
-                int base = 0;
+            int base = 0;
 #pragma unroll
-                for (int w = 0; w < GS_WIN_MAX; ++w) {
-                    const unsigned dd = (unsigned)(c - lo[w]);
-                    if (dd < (unsigned)len[w]) out = base + (int)dd;
-                    base += len[w];
-                }
+            for (int w = 0; w < GS_WIN_MAX; ++w) {
+                const unsigned dd = (unsigned)(c - lo[w]);
+                if (dd < (unsigned)len[w]) out = base + (int)dd;
+                base += len[w];
             }
         }
         ci_slot[k] = out;
@@ -845,9 +790,9 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
 }
 
 template <int NRHS>
-static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
-                         double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials, cudaStream_t st,
-                         const GsbHaloArgs *halo_in) {
+static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
+                         const double *b, double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials,
+                         cudaStream_t st, const GsbHaloArgs *halo_in) {
     GsbHaloArgs halo;
     memset(&halo, 0, sizeof(halo));
     if (halo_in) halo = *halo_in;
@@ -878,8 +823,9 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         const int smem = 64 + stages * stage_bytes;
         const int *tk = p->tile_k.p + p->tile_off[c];
         const int *tw = win ? p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC : nullptr;
-        typedef void (*ring_fn)(const int *, const int *, const double *, const double *, double *, int64_t, int, int,
-                                int, const int *, const int *, int, int, const GsCtl *, double *, const GsbHaloArgs);
+        typedef void (*ring_fn)(const int *, const int *, const double *, const double *, const double *, double *,
+                                int64_t, int, int, int, const int *, const int *, int, int, const GsCtl *, double *,
+                                const GsbHaloArgs);
 #define GSB_RING_PICK(ST, WN) (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN>)
         ring_fn kern = nullptr;
         if (win)
@@ -909,7 +855,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
-        kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
+        kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, dg, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
                                              ctl, partials, halo);
     } else if (eff == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
@@ -925,29 +871,29 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         }
         const int *tk = p->tile_k.p + p->tile_off[c];
         if (check)
-            kt<<<nb, GS_THREADS, p->smem_bytes, st>>>(rp, ci, va, b, x, ld, row0, row1, p->tile_rows, tk, p->cap, ctl,
+            kt<<<nb, GS_THREADS, p->smem_bytes, st>>>(rp, ci, va, dg, b, x, ld, row0, row1, p->tile_rows, tk, p->cap, ctl,
                                                        partials);
         else
-            kf<<<nb, GS_THREADS, p->smem_bytes, st>>>(rp, ci, va, b, x, ld, row0, row1, p->tile_rows, tk, p->cap, ctl,
+            kf<<<nb, GS_THREADS, p->smem_bytes, st>>>(rp, ci, va, dg, b, x, ld, row0, row1, p->tile_rows, tk, p->cap, ctl,
                                                        partials);
     } else {
         if (check)
-            gs_phase_direct<NRHS, true><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
+            gs_phase_direct<NRHS, true><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, dg, b, x, ld, row0, row1, ctl, partials);
         else
-            gs_phase_direct<NRHS, false><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, b, x, ld, row0, row1, ctl, partials);
+            gs_phase_direct<NRHS, false><<<nb, GS_THREADS, 0, st>>>(rp, ci, va, dg, b, x, ld, row0, row1, ctl, partials);
     }
     GSB_KERNEL_CHECK();
     return GSB_OK;
 }
 
-int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *b,
-                    double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
+int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
+                    const double *b, double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
                     cudaStream_t st, const GsbHaloArgs *halo) {
     switch (nrhs) {
-        case 1: return plan_launch_t<1>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
-        case 2: return plan_launch_t<2>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
-        case 3: return plan_launch_t<3>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
-        case 4: return plan_launch_t<4>(p, c, rp, ci, va, b, x, ld, check, ctl, partials, st, halo);
+        case 1: return plan_launch_t<1>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
+        case 2: return plan_launch_t<2>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
+        case 3: return plan_launch_t<3>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
+        case 4: return plan_launch_t<4>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
     }
     gsb_set_error("nrhs must be 1..%d", GSB_MAX_RHS);
     return GSB_ERR_ARG;

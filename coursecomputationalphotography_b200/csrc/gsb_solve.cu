@@ -63,7 +63,7 @@ static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, cudaStream_t st, i
     for (int c = 0; c < m->n_colors; ++c) {
         const int nb = m->plan->blocks[c];
         if (nb == 0) continue;
-        GSB_TRY(gsb_plan_launch(m->plan, c, m->rp.p, m->ci.p, m->va.p, m->bw.p, m->xw.p, n, nrhs, check, ctl,
+        GSB_TRY(gsb_plan_launch(m->plan, c, m->rp.p, m->ci.p, m->va.p, m->dg.p, m->bw.p, m->xw.p, n, nrhs, check, ctl,
                                 m->partials.p + (size_t)poff * nrhs, st));
         poff += nb;
         ++*launches;
