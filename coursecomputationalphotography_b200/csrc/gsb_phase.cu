@@ -232,8 +232,10 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check,
     return L;
 }
 
-template <int NRHS, bool CHECK, int STAGES, bool WIN>
-__global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
+// resident CTAs per SM the register allocation must allow: 4 wherever shared memory lets 4 stages-pairs fit
+// (k = 3 with windows is limited to 2-3 by its 49 KB stages)
+template <int NRHS, bool CHECK, int STAGES, bool WIN, bool HALO>
+__global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0,
                   int row1, int ntiles,
@@ -267,9 +269,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
         return d;
     };
     // strip solver: halo tiles come first in the processing order
-    auto tile_of = [&](int logical) -> int { return halo.enabled ? halo.order[logical] : logical; };
+    auto tile_of = [&](int logical) -> int { return HALO ? halo.order[logical] : logical; };
     auto issue = [&](const TileDesc &td, int t, int s) { // thread 0 only
-        if (halo.enabled && halo.wait_epoch > 0 && (halo.info[t] & 1)) {
+        if (HALO && halo.wait_epoch > 0 && (halo.info[t] & 1)) {
             // this tile reads ghost unknowns: the neighbours' values of the other colour must have landed
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr)
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
             tn = tile_of(tln);
             next_desc = load_desc(tn);
         }
-        const int tinfo = halo.enabled ? halo.info[t] : 0;
+        const int tinfo = HALO ? halo.info[t] : 0;
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
         mbar_wait(&full[s], parity);
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
                     const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
                     if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
                     x[r * n + i] = xn;
-                    if (tinfo & 2) { // a neighbour GPU reads this row: store it into its ghost slot as well
+                    if (HALO && (tinfo & 2)) { // a neighbour GPU reads this row: store it into its ghost slot as well
 #pragma unroll
                         for (int pr = 0; pr < 2; ++pr)
                             if (halo.has_peer[pr]) {
@@ -410,9 +412,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 ? 3 : 4))
                 }
             }
         }
-        if (tinfo & 2) __threadfence_system(); // peer stores visible before this tile is counted as done
+        if (HALO && (tinfo & 2)) __threadfence_system(); // peer stores visible before this tile is counted as done
         __syncthreads(); // every thread is done with stage s
-        if (tid == 0 && tinfo) {
+        if (HALO && tid == 0 && tinfo) {
             // last halo tile of the phase: every ghost read and every push of this phase is complete ->
             // raise the neighbours' flags (release at system scope orders the pushes before the flag)
             const int done_tiles = atomicAdd(halo.counter, 1) + 1;
@@ -826,12 +828,16 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         typedef void (*ring_fn)(const int *, const int *, const double *, const double *, const double *, double *,
                                 int64_t, int, int, int, const int *, const int *, int, int, const GsCtl *, double *,
                                 const GsbHaloArgs);
-#define GSB_RING_PICK(ST, WN) (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN>)
+#define GSB_RING_PICK(ST, WN, HL) \
+    (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN, HL> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN, HL>)
+#define GSB_RING_PICK_ST(WN, HL) \
+    (stages == 2 ? GSB_RING_PICK(2, WN, HL) : stages == 3 ? GSB_RING_PICK(3, WN, HL) : GSB_RING_PICK(4, WN, HL))
         ring_fn kern = nullptr;
-        if (win)
-            kern = stages == 2 ? GSB_RING_PICK(2, true) : stages == 3 ? GSB_RING_PICK(3, true) : GSB_RING_PICK(4, true);
+        if (halo.enabled)
+            kern = win ? GSB_RING_PICK_ST(true, true) : GSB_RING_PICK_ST(false, true);
         else
-            kern = stages == 2 ? GSB_RING_PICK(2, false) : stages == 3 ? GSB_RING_PICK(3, false) : GSB_RING_PICK(4, false);
+            kern = win ? GSB_RING_PICK_ST(true, false) : GSB_RING_PICK_ST(false, false);
+#undef GSB_RING_PICK_ST
 #undef GSB_RING_PICK
         // per (variant) cache of the opt-in shared-memory size and the resident CTAs per SM
         struct Cfg { const void *fn; int smem, occ; };
