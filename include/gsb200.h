@@ -44,8 +44,7 @@ typedef enum gsb_status {
 } gsb_status;
 
 enum { GSB_F64 = 0, GSB_I32 = 1 };                       /* vtype */
-enum { GSB_ORDER_AUTO = 0, GSB_ORDER_REDBLACK = 1, GSB_ORDER_MULTICOLOR = 2, GSB_ORDER_USER = 3,
-       GSB_ORDER_NATURAL_PARITY = 4 /* colour = row index & 1 (strip-local parity, see dist) */ };
+enum { GSB_ORDER_AUTO = 0, GSB_ORDER_REDBLACK = 1, GSB_ORDER_MULTICOLOR = 2, GSB_ORDER_USER = 3 };
 
 typedef struct gsb_matrix gsb_matrix; /* opaque: device-resident slack CSR + solver format */
 typedef struct gsb_dist gsb_dist;     /* opaque: one rank of a row-strip multi-GPU solve    */
@@ -128,7 +127,8 @@ typedef struct gsb_gs_options {
     int check_every;     /* evaluate the stop rule every k-th sweep; 1 = every sweep (reference)     */
     int batch_sweeps;    /* sweeps enqueued between host reads of the stop flag; 0 = library default */
     int use_graph;       /* 1 = replay a captured CUDA graph per batch; 0 = plain launches; -1 auto  */
-    int kernel;          /* 0 = auto; 1 = row-per-thread direct; 2 = staged (bulk-copy CSR tiles)     */
+    int kernel;          /* 0 = auto; 1 = row-per-thread direct; 2 = staged tiles (bulk copies);
+                            3 = persistent ring; 4 = ring + shared-memory gather windows            */
     int compute_residual;/* 1 = also return ||b - A x||_2 per right-hand side in stats                */
     int reserved[2];
 } gsb_gs_options;
@@ -137,7 +137,7 @@ typedef struct gsb_gs_stats {
     int sweeps;          /* cnt at exit (v2 :377)                                                     */
     int n_colors;
     int ordering_used;
-    int kernel_used;
+    int kernel_used;     /* 1..4 as above; +10 when the strip solver fused the halo exchange into it   */
     int64_t kernel_launches; /* launches of this library's kernels enqueued by the call              */
     double last_eps[4];  /* L1 norm of the last evaluated sweep update, per right-hand side (v2 :376) */
     double residual_l2[4];
