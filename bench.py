@@ -320,7 +320,7 @@ def run_ours(args):
     line = {
         "metric": "gauss_seidel_throughput", "value": value, "unit": "Gnnz/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, ch),
                    "n": n, "nnz": int(nnz), "sweeps_per_step": args.sweeps, "ordering": "red-black",
                    "n_colors": info["n_colors"], "check_every": args.check_every,

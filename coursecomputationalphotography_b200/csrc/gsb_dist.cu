@@ -31,6 +31,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -61,6 +62,7 @@ static int nccl_load() {
     LOAD(Send, "ncclSend")
     LOAD(Recv, "ncclRecv")
     LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather")
     LOAD(GroupStart, "ncclGroupStart")
     LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(GetErrorString, "ncclGetErrorString")
@@ -122,6 +124,12 @@ struct gsb_dist {
     int n_halo_tiles[2] = {0, 0};
     long long epoch = 0;       // flags only ever grow: epoch of the last sweep issued so far
     int used_peer = 0;
+    // fused stop-rule all-reduce (GsbEpsExchange): this rank's box and every rank's box peer-mapped
+    DevBuf<double> eps_box;
+    double *peer_box[GSB_DIST_MAX_WORLD] = {nullptr};
+    bool box_ready = false, box_failed = false;
+    long long xcount = 0;      // stop-rule exchanges issued so far (identical on every rank)
+    int used_fused_eps = 0;
     int peer_rank(int p) const { return p == 0 ? rank - 1 : rank + 1; }
     bool has_peer(int p) const { return p == 0 ? rank > 0 : rank < world - 1; }
 };
@@ -169,6 +177,8 @@ extern "C" int gsb_dist_finalize(gsb_dist *d) {
         if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
         if (d->peer_flags[p]) cudaIpcCloseMemHandle(d->peer_flags[p]);
     }
+    for (int q = 0; q < d->world && q < GSB_DIST_MAX_WORLD; ++q)
+        if (q != d->rank && d->peer_box[q]) cudaIpcCloseMemHandle(d->peer_box[q]);
     if (d->comm) g_nccl.CommDestroy(d->comm);
     if (d->ctl_host) cudaFreeHost(d->ctl_host);
     delete d;
@@ -441,6 +451,9 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
             int q = w * 2 + c, len = flen[q], cnt = 0;
             if (len > 0) GSB_TRY(scan_count(f[q], len, st, &cnt));
             d->need_cnt[w][c] = cnt;
+            // every ghost segment starts on its own 128-byte line: a line of x then holds either owned values or
+            // the values one neighbour pushes in one colour phase, never both (the gathers may cache lines in L1)
+            base = (base + 15) & ~15;
             d->ghost_start[w][c] = base;
             GSB_TRY(need_ids[w][c].alloc(cnt));
             if (cnt > 0) {
@@ -593,6 +606,66 @@ struct PeerHello { // what a rank tells a neighbour so that it can write this ra
     int ok;
     int pad;
 };
+
+// allocates this rank's stop-rule box and maps every other rank's (all-gather of the IPC handles); collective.
+// Any failure anywhere keeps every rank on the ncclAllReduce path.
+static int dist_box_setup(gsb_dist *d, cudaStream_t st) {
+    if (d->box_ready || d->box_failed) return GSB_OK;
+    if (d->world > GSB_DIST_MAX_WORLD) {
+        d->box_failed = true;
+        return GSB_OK;
+    }
+    const int64_t box_doubles = (int64_t)2 * d->world * GSB_MAX_RHS + d->world + 8; // flags: 2 * world ints
+    int ok = 1;
+    if (d->eps_box.alloc(box_doubles) != GSB_OK) ok = 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        GSB_CUDA(cudaMemsetAsync(d->eps_box.p, 0, sizeof(double) * (size_t)box_doubles, st));
+        if (cudaIpcGetMemHandle(&mine, d->eps_box.p) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        }
+    }
+    struct Hello { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+    Hello hm;
+    memset(&hm, 0, sizeof(hm));
+    hm.h = mine;
+    hm.ok = ok;
+    std::vector<Hello> all((size_t)d->world);
+    DevBuf<unsigned char> dm, da;
+    GSB_TRY(dm.alloc(sizeof(Hello)));
+    GSB_TRY(da.alloc((int64_t)sizeof(Hello) * d->world));
+    GSB_CUDA(cudaMemcpyAsync(dm.p, &hm, sizeof(Hello), cudaMemcpyHostToDevice, st));
+    GSB_NCCL(g_nccl.AllGather(dm.p, da.p, sizeof(Hello), ncclInt8, d->comm, st));
+    GSB_CUDA(cudaMemcpyAsync(all.data(), da.p, sizeof(Hello) * (size_t)d->world, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    for (int q = 0; q < d->world; ++q) ok = ok && all[(size_t)q].ok;
+    for (int q = 0; q < d->world && ok; ++q) {
+        if (q == d->rank) {
+            d->peer_box[q] = d->eps_box.p;
+            continue;
+        }
+        void *pb = nullptr;
+        if (cudaIpcOpenMemHandle(&pb, all[(size_t)q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        d->peer_box[q] = (double *)pb;
+    }
+    DevBuf<int> agree;
+    GSB_TRY(agree.alloc(1));
+    GSB_CUDA(cudaMemcpyAsync(agree.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
+    GSB_CUDA(cudaMemcpyAsync(&ok, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (ok)
+        d->box_ready = true;
+    else
+        d->box_failed = true;
+    return GSB_OK;
+}
 
 // (re)maps the neighbours' x workspaces and flag words; collective over neighbours (same order everywhere)
 static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
@@ -819,6 +892,17 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             use_peer = false;
     }
     d->used_peer = use_peer ? 1 : 0;
+    // stop-rule all-reduce: fused into the end-of-sweep kernel over peer memory, or fold + ncclAllReduce + decide
+    bool fused_eps = use_peer;
+    {
+        const char *e = getenv("GSB_DIST_EPS");
+        if (e && strcmp(e, "nccl") == 0) fused_eps = false;
+    }
+    if (fused_eps) {
+        GSB_TRY(dist_box_setup(d, st));
+        fused_eps = d->box_ready;
+    }
+    d->used_fused_eps = fused_eps ? 1 : 0;
     if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));
     if (!d->ctl_host) GSB_CUDA(cudaHostAlloc(&d->ctl_host, sizeof(GsCtl), cudaHostAllocDefault));
     GsCtl *ctl = (GsCtl *)d->ctl.p;
@@ -887,13 +971,22 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                     }
                     status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p, d->xw.p, ld, nrhs, check,
                                              ctl, d->partials.p + (size_t)poff * nrhs, st, use_peer ? &ha : nullptr);
-                    poff += d->plan.blocks[c];
+                    poff += gsb_plan_partial_slots(&d->plan, c, nrhs);
                     ++launches;
                 }
                 if (status == GSB_OK && !use_peer) status = dist_exchange(d, c, nrhs, st, &launches);
             }
             if (status != GSB_OK) break;
-            if (check) {
+            if (check && fused_eps) {
+                GsbEpsExchange ex;
+                memset(&ex, 0, sizeof(ex));
+                ex.world = d->world;
+                ex.rank = d->rank;
+                ex.epoch = (int)(++d->xcount);
+                for (int q = 0; q < d->world; ++q) ex.box[q] = d->peer_box[q];
+                status = gsb_launch_end_sweep_peer(ctl, d->partials.p, poff, nrhs, &ex, st);
+                ++launches;
+            } else if (check) {
                 status = gsb_launch_end_sweep(ctl, d->partials.p, poff, nrhs, 1, 1, st);
                 if (status == GSB_OK && d->world > 1) {
                     ncclResult_t r = g_nccl.AllReduce(ctl->eps_last, ctl->eps_last, nrhs, ncclFloat64, ncclSum, d->comm, st);
@@ -920,6 +1013,10 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             break;
         }
         h = *hp;
+        if (h.error) {
+            gsb_set_error("dist: the peer stop-rule exchange timed out on rank %d (a rank is missing)", d->rank);
+            status = GSB_ERR_NCCL;
+        }
     }
     cudaEventRecord(ev1, st);
     cudaEventSynchronize(ev1);
@@ -937,7 +1034,8 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         stats->sweeps = h.sweeps;
         stats->n_colors = 2;
         stats->ordering_used = GSB_ORDER_REDBLACK;
-        stats->kernel_used = gsb_plan_effective_kernel(&d->plan, nrhs) + (d->used_peer ? 10 : 0); // +10: fused peer-memory halo exchange
+        // +10: fused peer-memory halo exchange; +20 more: the stop-rule all-reduce fused into the end-of-sweep kernel
+        stats->kernel_used = gsb_plan_effective_kernel(&d->plan, nrhs) + (d->used_peer ? 10 : 0) + (d->used_fused_eps ? 20 : 0);
         stats->kernel_launches = launches;
         for (int r = 0; r < nrhs; ++r) stats->last_eps[r] = h.eps_last[r];
         stats->solve_ms = solve_ms;

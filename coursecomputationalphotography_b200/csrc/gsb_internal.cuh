@@ -162,6 +162,8 @@ struct GsCtl {
     int check_every;
     double epsilon;
     double eps_last[GSB_MAX_RHS];
+    int error; // 1: the peer stop-rule exchange timed out (a rank is missing); the solve stops
+    int pad_;
 };
 
 // how the colour phases of one colour-major CSR are launched (gsb_phase.cu)
@@ -187,6 +189,10 @@ struct GsbPlan {
 int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_start, int n_colors,
                    int kernel_request, cudaStream_t st);
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs);
+int gsb_plan_partial_slots(const GsbPlan *p, int c, int nrhs); // stop-rule partial slots of colour phase c
+// programmatic dependent launch of the ring kernels / gs_end_sweep (GSB_PDL=0 disables; suppressed during graph capture)
+bool gsb_pdl_enabled();
+void gsb_pdl_suppress(int on);
 static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
 // Fused halo exchange of the strip solver (gsb_dist.cu): the phase kernel itself writes the boundary values a
 // neighbour GPU reads straight into that neighbour's ghost slots (peer-mapped memory over NVLink) and
@@ -218,6 +224,20 @@ int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const
 //                mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
 int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
                          cudaStream_t st);
+// Strip solver: end of a checked sweep with the all-reduce of the stop rule fused in.  Every rank owns a small
+// "box" in device memory that all ranks have peer-mapped: [2 parities][world][GSB_MAX_RHS] doubles followed by
+// [2 parities][world] int flags.  The kernel folds the local partials, stores the k sums into slot `rank` of every
+// rank's box (NVLink peer stores) and raises that slot's flag (release, system scope) to `epoch`; it then waits for
+// all `world` flags of its own box, adds the slots in rank order (identical on every rank -> identical decision),
+// bumps the sweep counter and decides.  One launch replaces fold + ncclAllReduce + decide.
+#define GSB_DIST_MAX_WORLD 16
+struct GsbEpsExchange {
+    int world, rank;
+    int epoch;  // exchanges issued so far + 1 (monotonic over the lifetime of the handle); parity = epoch & 1
+    double *box[GSB_DIST_MAX_WORLD];
+};
+int gsb_launch_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials, int nrhs, const GsbEpsExchange *ex,
+                              cudaStream_t st);
 
 // gsb_poisson.cu: rows [p0,p1) of the reference's Poisson matrix (global columns)
 int gsb_poisson_launch_row_len(int W, int H, int64_t p0, int64_t p1, int *len, cudaStream_t st);

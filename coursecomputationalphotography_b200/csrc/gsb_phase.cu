@@ -131,6 +131,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; pdl_wait() blocks until the
+// predecessor has completed and its writes are visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// hint: bring [p, p + bytes) into L2 (bytes a multiple of 16, p 16-byte aligned); no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <int NRHS, bool CHECK>
 __global__ void __launch_bounds__(GS_THREADS, 4)
     gs_phase_staged(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
@@ -212,6 +223,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 #define GS_WIN_GRANULE 64      // columns per granule (512 bytes: keeps every window 16-byte aligned)
 #define GS_WIN_CAP_MAX 2048    // doubles per right-hand side per stage
 #define GS_WIN_DESC 12         // ints per tile descriptor
+#define GS_RING_SLOTS_MAX 2048 // upper bound of the persistent grid = stop-rule partial slots per colour phase
 
 struct RingLayout {
     int va_off, dg_off, b_off, xo_off, xw_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
@@ -242,8 +254,10 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
                   const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
                   const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (ctl->done) return; // written only by gs_end_sweep, i.e. constant for the lifetime of this kernel
     const RingLayout L = ring_layout(cap, NRHS, CHECK, WIN ? wcap : 0);
+    // kernel 3 with window descriptors: the x spans a tile will gather from are pulled into L2 when the tile's
+    // stage is issued (one tile ahead), so that the gathers see L2 latency instead of HBM latency
+    const bool xpf = !WIN && tile_win != nullptr;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     unsigned char *stage0 = smem_raw + 64;
     const int tid = threadIdx.x;
@@ -258,7 +272,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         TileDesc d;
         d.k0 = tile_k[t];
         d.k1 = tile_k[t + 1];
-        if (WIN) {
+        if (WIN || xpf) {
             const int4 *wd = reinterpret_cast<const int4 *>(tile_win + (size_t)t * GS_WIN_DESC);
             d.w0 = wd[0];
             d.w1 = wd[1];
@@ -297,10 +311,12 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
         uint32_t total = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
         int nwin = 0, lo[GS_WIN_MAX], len[GS_WIN_MAX];
-        if (WIN) {
+        if (WIN || xpf) {
             nwin = td.w0.x;
             lo[0] = td.w0.y; lo[1] = td.w0.z; lo[2] = td.w0.w; lo[3] = td.w1.x;
             len[0] = td.w1.y; len[1] = td.w1.z; len[2] = td.w1.w; len[3] = td.w2.x;
+        }
+        if (WIN) {
 #pragma unroll
             for (int w = 0; w < GS_WIN_MAX; ++w) total += (uint32_t)NRHS * (uint32_t)len[w] * 8u;
         }
@@ -333,6 +349,15 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
                 }
                 base += len[w];
             }
+        } else if (xpf) {
+            // wcap carries the prefetch mode for kernel 3: 1 = every window, 2 = only the last (highest) window --
+            // with tiles walked in ascending order the lower windows were requested by earlier tiles
+#pragma unroll
+            for (int w = 0; w < GS_WIN_MAX; ++w)
+                if (len[w] > 0 && (wcap != 2 || w == nwin - 1)) {
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) bulk_prefetch_l2(x + r * n + lo[w], (uint32_t)len[w] * 8u);
+                }
         }
     };
 
@@ -341,7 +366,14 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     }
     __syncthreads();
-    if (tid == 0) {
+    // Programmatic dependent launch: the next kernel of the stream may take the SM slots this grid frees as its
+    // CTAs retire, and this grid may itself have started while the previous colour phase was still draining.
+    // Everything the prologue stages is either constant (CSR, diagonal, b) or this colour's own x (x_old), which
+    // the predecessor does not write; the predecessor's x (the gathers, the window copies) and the control block
+    // are only touched after pdl_wait().
+    pdl_launch_dependents();
+    if (WIN) pdl_wait();
+    if (tid == 0 && !(WIN && *(volatile const int *)&ctl->done)) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int tl = blockIdx.x + s * gridDim.x;
@@ -350,6 +382,15 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
                 issue(load_desc(t), t, s);
             }
         }
+    }
+    if (!WIN) pdl_wait();
+    if (*(volatile const int *)&ctl->done) { // written only by gs_end_sweep, i.e. constant from here on
+        if (!WIN) {  // the prologue's bulk copies must land before the shared memory is released
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                if (blockIdx.x + s * gridDim.x < ntiles) mbar_wait(&full[s], 0);
+        }
+        return;
     }
 
     // stop-rule partial: accumulated per thread over the CTA's tiles (static schedule -> fixed order) and folded
@@ -393,7 +434,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
             if (use_win)
                 gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int c, int r) { return xw_s[(size_t)r * wcap + c]; }, sig);
             else
-                gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int c, int r) { return __ldg(x + r * n + c); }, sig);
+                gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int c, int r) { return x[r * n + c]; }, sig);
             if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
 #pragma unroll
                 for (int r = 0; r < NRHS; ++r) {
@@ -432,7 +473,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     }
     if (CHECK) {
         gsb_block_reduce_store<NRHS, GS_THREADS>(acc, partials + (size_t)blockIdx.x * NRHS);
-        for (int t2 = blockIdx.x + gridDim.x; t2 < ntiles; t2 += gridDim.x)
+        // the phase owns min(ntiles, GS_RING_SLOTS_MAX) partial slots (gsb_plan_partial_slots); unused ones are zero
+        const int nslots = min(ntiles, GS_RING_SLOTS_MAX);
+        for (int t2 = blockIdx.x + gridDim.x; t2 < nslots; t2 += gridDim.x)
             if (tid < NRHS) partials[(size_t)t2 * NRHS + tid] = 0.0;
     }
 }
@@ -555,7 +598,9 @@ __global__ void __launch_bounds__(GS_THREADS) plan_tile_slots(const int *__restr
 template <int NRHS>
 __global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *__restrict__ partials, int n_partials,
                                                      int checked, int mode) {
-    if (ctl->done) return;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (*(volatile const int *)&ctl->done) return;
     if (mode == 2) {
         if (threadIdx.x == 0) {
             bool all_ok = checked != 0;
@@ -576,7 +621,7 @@ __global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *_
         for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
         for (int i = threadIdx.x; i < n_partials; i += 1024) {
 #pragma unroll
-            for (int r = 0; r < NRHS; ++r) s[r] += partials[(size_t)i * NRHS + r];
+            for (int r = 0; r < NRHS; ++r) s[r] += __ldcg(partials + (size_t)i * NRHS + r); // L2: written by the predecessor
         }
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
@@ -605,6 +650,117 @@ __global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *_
     }
 }
 
+// end of a checked sweep of the strip solver, stop-rule all-reduce fused in (see GsbEpsExchange)
+template <int NRHS>
+__global__ void __launch_bounds__(1024) gs_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials,
+                                                          const GsbEpsExchange ex) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (*(volatile const int *)&ctl->done) return;
+    __shared__ double ws[NRHS][32];
+    __shared__ double tot[NRHS];
+    __shared__ double all[GSB_DIST_MAX_WORLD][NRHS];
+    __shared__ int timed_out;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double s[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += 1024) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] += __ldcg(partials + (size_t)i * NRHS + r);
+    }
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+        double t = s[r];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+        if (lane == 0) ws[r][wid] = t;
+    }
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    if (threadIdx.x < NRHS) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += ws[threadIdx.x][w];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int par = ex.epoch & 1;
+    const size_t flag_off = (size_t)2 * ex.world * GSB_MAX_RHS; // in doubles
+    if (threadIdx.x < ex.world) { // push this rank's sums into slot `rank` of rank q's box
+        const int q = threadIdx.x;
+        double *dst = ex.box[q] + (size_t)(par * ex.world + ex.rank) * GSB_MAX_RHS;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + r), "d"(tot[r]) : "memory");
+        int *flag = reinterpret_cast<int *>(ex.box[q] + flag_off) + par * ex.world + ex.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(ex.epoch) : "memory");
+    }
+    if (threadIdx.x < ex.world) { // collect slot q of the own box
+        const int q = threadIdx.x;
+        const int *flag = reinterpret_cast<const int *>(ex.box[ex.rank] + flag_off) + par * ex.world + q;
+        int v = 0;
+        long long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v >= ex.epoch) break;
+            if (++spins > (1ll << 25)) { // ~10 s: a rank is missing
+                timed_out = 1;
+                break;
+            }
+            __nanosleep(spins < 64 ? 20 : 200);
+        }
+        const double *src = ex.box[ex.rank] + (size_t)(par * ex.world + q) * GSB_MAX_RHS;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            double t;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t) : "l"(src + r) : "memory");
+            all[q][r] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool all_ok = true;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            double t = 0.0;
+            for (int q = 0; q < ex.world; ++q) t += all[q][r];
+            ctl->eps_last[r] = t;
+            if (t > ctl->epsilon) all_ok = false; // v2 :356
+        }
+        const int cnt = ctl->sweeps + 1;
+        ctl->sweeps = cnt;
+        if (timed_out) ctl->error = 1;
+        if (all_ok || cnt >= ctl->max_iter || timed_out) ctl->done = 1;
+    }
+}
+
+int gsb_launch_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials, int nrhs, const GsbEpsExchange *ex,
+                              cudaStream_t st) {
+    if (n_partials > 8192) {
+        gsb_set_error("end_sweep_peer: %d partials (the ring kernels write at most %d per colour)", n_partials,
+                      GS_RING_SLOTS_MAX);
+        return GSB_ERR_ARG;
+    }
+    void (*kern)(GsCtl *, const double *, int, const GsbEpsExchange) = nullptr;
+    switch (nrhs) {
+        case 1: kern = gs_end_sweep_peer<1>; break;
+        case 2: kern = gs_end_sweep_peer<2>; break;
+        case 3: kern = gs_end_sweep_peer<3>; break;
+        case 4: kern = gs_end_sweep_peer<4>; break;
+        default: return GSB_ERR_ARG;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gsb_pdl_enabled() ? 1 : 0;
+    GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, ctl, partials, n_partials, (const GsbEpsExchange)*ex));
+    return GSB_OK;
+}
+
 // first level of the fold for many partials: GS_FOLD_BLOCKS blocks, each folds one contiguous chunk in a
 // fixed order -> out[b * NRHS + r]; gs_end_sweep then folds those.  The grouping depends only on n_partials.
 #define GS_FOLD_BLOCKS 64
@@ -626,7 +782,7 @@ __global__ void __launch_bounds__(256) gs_fold_partials(const double *__restrict
 // partials must have room for GS_FOLD_BLOCKS * nrhs more doubles after the n_partials * nrhs used ones
 int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
                          cudaStream_t st) {
-    if (checked && mode != 2 && n_partials > 4 * GS_FOLD_BLOCKS) {
+    if (checked && mode != 2 && n_partials > 8192) {
         double *scratch = const_cast<double *>(partials) + (size_t)n_partials * nrhs;
         switch (nrhs) {
             case 1: gs_fold_partials<1><<<GS_FOLD_BLOCKS, 256, 0, st>>>(partials, n_partials, scratch); break;
@@ -639,15 +795,38 @@ int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int
         partials = scratch;
         n_partials = GS_FOLD_BLOCKS;
     }
+    void (*kern)(GsCtl *, const double *, int, int, int) = nullptr;
     switch (nrhs) {
-        case 1: gs_end_sweep<1><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        case 2: gs_end_sweep<2><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        case 3: gs_end_sweep<3><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
-        case 4: gs_end_sweep<4><<<1, 1024, 0, st>>>(ctl, partials, n_partials, checked, mode); break;
+        case 1: kern = gs_end_sweep<1>; break;
+        case 2: kern = gs_end_sweep<2>; break;
+        case 3: kern = gs_end_sweep<3>; break;
+        case 4: kern = gs_end_sweep<4>; break;
         default: return GSB_ERR_ARG;
     }
-    GSB_KERNEL_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gsb_pdl_enabled() ? 1 : 0;
+    GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, ctl, partials, n_partials, checked, mode));
     return GSB_OK;
+}
+
+// Programmatic dependent launch is used for the ring kernels and gs_end_sweep unless GSB_PDL=0 or the caller is
+// capturing a CUDA graph (gsb_pdl_suppress).
+static thread_local int g_pdl_suppress = 0;
+void gsb_pdl_suppress(int on) { g_pdl_suppress = on; }
+bool gsb_pdl_enabled() {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("GSB_PDL");
+        env = e ? atoi(e) : 1;
+    }
+    return env != 0 && !g_pdl_suppress;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -675,6 +854,14 @@ int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
     if (p->requested == 4) return 4;
     if (p->requested == 3) return 3;
     return nrhs >= 2 ? 3 : 4;
+}
+
+// stop-rule partial slots colour phase c writes (and gs_end_sweep folds) for `nrhs` right-hand sides
+int gsb_plan_partial_slots(const GsbPlan *p, int c, int nrhs) {
+    const int eff = gsb_plan_effective_kernel(p, nrhs);
+    const int nb = p->blocks[c];
+    if (eff == 3 || eff == 4) return nb < GS_RING_SLOTS_MAX ? nb : GS_RING_SLOTS_MAX;
+    return nb;
 }
 
 int GsbPlan::total_blocks() const {
@@ -816,15 +1003,22 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
             env_ctas = e ? atoi(e) : 0;
         }
         const bool win = eff == 4;
-        const int wcap = win ? p->wcap : 0;
-        const int stage_bytes = ring_layout(p->cap, NRHS, check, wcap).stage_bytes;
+        const int stage_bytes = ring_layout(p->cap, NRHS, check, win ? p->wcap : 0).stage_bytes;
         int stages = env_stages ? env_stages : GS_RING_STAGES_DEFAULT;
         if (stages < 2) stages = 2;
         if (stages > GS_RING_STAGES_MAX) stages = GS_RING_STAGES_MAX;
         while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
         const int smem = 64 + stages * stage_bytes;
         const int *tk = p->tile_k.p + p->tile_off[c];
-        const int *tw = win ? p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC : nullptr;
+        // window descriptors: kernel 4 stages the windows; kernel 3 uses them as L2 prefetch hints (GSB_X_PREFETCH=0: off)
+        static int env_xpf = -1;
+        if (env_xpf < 0) {
+            const char *e = getenv("GSB_X_PREFETCH");
+            env_xpf = e ? atoi(e) : 1;
+        }
+        const bool have_win = p->kernel == 4 && p->tile_win.p;
+        const int *tw = (win || (have_win && env_xpf)) ? p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC : nullptr;
+        const int wcap = win ? p->wcap : env_xpf; // kernel 3: the prefetch mode travels in the (unused) window capacity
         typedef void (*ring_fn)(const int *, const int *, const double *, const double *, const double *, double *,
                                 int64_t, int, int, int, const int *, const int *, int, int, const GsCtl *, double *,
                                 const GsbHaloArgs);
@@ -861,8 +1055,19 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         int grid = gsb_sm_count() * per_sm;
         if (grid > nb) grid = nb;
-        kern<<<grid, GS_THREADS, smem, st>>>(rp, win ? p->ci_slot.p : ci, va, dg, b, x, ld, row0, row1, nb, tk, tw, p->cap, wcap,
-                                             ctl, partials, halo);
+        if (grid > GS_RING_SLOTS_MAX) grid = GS_RING_SLOTS_MAX;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(GS_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = gsb_pdl_enabled() ? 1 : 0;
+        GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, (const int *)(win ? p->ci_slot.p : ci), va, dg, b, x, ld, row0, row1,
+                                    nb, tk, tw, p->cap, wcap, ctl, partials, (const GsbHaloArgs)halo));
     } else if (eff == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;

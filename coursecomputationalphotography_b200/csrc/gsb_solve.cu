@@ -65,7 +65,7 @@ static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, cudaStream_t st, i
         if (nb == 0) continue;
         GSB_TRY(gsb_plan_launch(m->plan, c, m->rp.p, m->ci.p, m->va.p, m->dg.p, m->bw.p, m->xw.p, n, nrhs, check, ctl,
                                 m->partials.p + (size_t)poff * nrhs, st));
-        poff += nb;
+        poff += gsb_plan_partial_slots(m->plan, c, nrhs);
         ++*launches;
     }
     GSB_TRY(gsb_launch_end_sweep(ctl, m->partials.p, poff, nrhs, check ? 1 : 0, 0, st));
@@ -186,7 +186,9 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
                 cudaGraph_t g = nullptr;
                 int64_t dummy = 0;
                 GSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                gsb_pdl_suppress(1); // plain kernel nodes inside the graph
                 for (int s = 0; s < batch && status == GSB_OK; ++s) status = enqueue_sweep(m, nrhs, true, st, &dummy);
+                gsb_pdl_suppress(0);
                 cudaError_t ce = cudaStreamEndCapture(st, &g);
                 if (status != GSB_OK) break;
                 if (ce != cudaSuccess) {

@@ -102,7 +102,12 @@ def run(args, pkg, wl, dist, rank, world, local):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2]), %d row strips" % (W, H, ch, world),
                        "n": n, "nnz": int(nnz), "sweeps_per_step": args.sweeps, "ordering": "red-black (global parity)",
-                       "check_every": args.check_every, "halo": "1 image row per neighbour per colour phase, NCCL send/recv",
+                       "check_every": args.check_every,
+                       "halo": "1 image row per neighbour per colour phase, " +
+                               ("stored into the neighbour's ghost slots by the phase kernel (NVLink peer memory)"
+                                if st.kernel_used >= 10 else "packed ncclSend/ncclRecv"),
+                       "stop_rule_allreduce": ("fused into the end-of-sweep kernel (peer memory)" if st.kernel_used >= 30
+                                               else "ncclAllReduce"),
                        "l2": "per-GPU working set %.2f GB per sweep" % (abytes / 1e9),
                        "sweeps_per_s": sweeps_done / (total_ms * 1e-3), "residual_l2": resid},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

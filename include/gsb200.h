@@ -137,7 +137,8 @@ typedef struct gsb_gs_stats {
     int sweeps;          /* cnt at exit (v2 :377)                                                     */
     int n_colors;
     int ordering_used;
-    int kernel_used;     /* 1..4 as above; +10 when the strip solver fused the halo exchange into it   */
+    int kernel_used;     /* 1..4 as above; strip solver: +10 halo exchange fused into the phase kernels,
+                            +20 more when the stop-rule all-reduce is fused into the end-of-sweep kernel */
     int64_t kernel_launches; /* launches of this library's kernels enqueued by the call              */
     double last_eps[4];  /* L1 norm of the last evaluated sweep update, per right-hand side (v2 :376) */
     double residual_l2[4];

@@ -149,6 +149,36 @@ def gpu_mode(rank, world, local):
             assert abs(r1 - res) <= 1e-9 * max(1.0, r1), (r1, res)
             print("gpu strips ok: %dx%dx%d world %d sweeps %d residual %.6e" % (W, H, ch, world, sweeps, res))
         dist.barrier()
+    # a real epsilon: every rank must stop at the same sweep, and the stop-rule all-reduce fused into the
+    # end-of-sweep kernel (peer memory) must agree with the fold + ncclAllReduce + decide path, bit for bit
+    W, H, ch = 96, 64, 3
+    y0, y1 = wl.strip_bounds(H, world)[rank]
+    s.poisson_strip(W, H, y0, y1)
+    bd = torch.from_numpy(strips.strip_rhs(W, H, ch, y0, y1)).to(dev)
+    xd = torch.empty_like(bd)
+    os.environ["GSB_DIST_TRANSPORT"] = "peer"
+    st = s.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, 15)
+    eps = 1.5 * max(st.last_eps[:ch])
+    got = {}
+    for mode in ("nccl", "peer"):
+        os.environ["GSB_DIST_EPS"] = mode
+        xd.zero_()
+        st = s.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, eps, 40)
+        assert 1 <= st.sweeps <= 15, st.sweeps
+        assert max(st.last_eps[:ch]) <= eps
+        if world > 1:
+            assert (st.kernel_used >= 30) == (mode == "peer"), (mode, st.kernel_used)
+        cnt = torch.tensor([st.sweeps], device=dev)
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        assert all(int(c[0]) == st.sweeps for c in cnts), "ranks disagree on the stop sweep"
+        got[mode] = (st.sweeps, xd.clone(), list(st.last_eps[:ch]))
+    os.environ.pop("GSB_DIST_EPS")
+    assert got["nccl"][0] == got["peer"][0] and torch.equal(got["nccl"][1], got["peer"][1])
+    assert np.allclose(got["nccl"][2], got["peer"][2], rtol=1e-12)
+    if rank == 0:
+        print("gpu strips stop rule ok: world %d stopped after %d sweeps (eps %.3e)" % (world, got["peer"][0], eps))
+    dist.barrier()
     s.close()
 
 
