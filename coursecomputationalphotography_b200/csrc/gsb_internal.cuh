@@ -212,6 +212,7 @@ struct GsbHaloArgs {
     int wait_epoch, signal_epoch;
     int *counter;              // halo tiles finished in this phase
     int has_peer[2];
+    int pdl_early;             // set by the launcher: stage the first tiles before griddepcontrol.wait (kernel 3)
 };
 
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles

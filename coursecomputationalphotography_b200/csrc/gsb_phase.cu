@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     // the predecessor does not write; the predecessor's x (the gathers, the window copies) and the control block
     // are only touched after pdl_wait().
     pdl_launch_dependents();
-    if (WIN) pdl_wait();
-    if (tid == 0 && !(WIN && *(volatile const int *)&ctl->done)) {
+    const bool early = !WIN && halo.pdl_early; // prologue before the predecessor has finished
+    if (!early) pdl_wait();
+    if (tid == 0 && (early || !*(volatile const int *)&ctl->done)) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int tl = blockIdx.x + s * gridDim.x;
@@ -383,9 +384,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
             }
         }
     }
-    if (!WIN) pdl_wait();
+    if (early) pdl_wait();
     if (*(volatile const int *)&ctl->done) { // written only by gs_end_sweep, i.e. constant from here on
-        if (!WIN) {  // the prologue's bulk copies must land before the shared memory is released
+        if (early) { // the prologue's bulk copies must land before the shared memory is released
 #pragma unroll
             for (int s = 0; s < STAGES; ++s)
                 if (blockIdx.x + s * gridDim.x < ntiles) mbar_wait(&full[s], 0);
@@ -779,6 +780,28 @@ __global__ void __launch_bounds__(256) gs_fold_partials(const double *__restrict
     gsb_block_reduce_store<NRHS, 256>(s, out + (size_t)blockIdx.x * NRHS);
 }
 
+// Programmatic dependent launch is used for the ring kernels and gs_end_sweep unless GSB_PDL=0 or the caller is
+// capturing a CUDA graph (gsb_pdl_suppress).
+// Measured on B200 (profiles/README.md): at 4096^2 (8.4 M rows per phase, 0.22 ms) the overlap costs 3 %, at
+// 1024^2 (0.5 M rows, 12 us) it gains 8 %; a strip of an 8-GPU solve is on the small side.  Policy: unset = auto
+// (on for phases of at most GS_PDL_AUTO_ROWS rows), GSB_PDL=0 off, 1 on, 2 on without the early prologue.
+#define GS_PDL_AUTO_ROWS (3 << 20)
+static thread_local int g_pdl_suppress = 0;
+static thread_local int g_pdl_last = 0; // decision of the most recent ring launch: gs_end_sweep follows it
+void gsb_pdl_suppress(int on) { g_pdl_suppress = on; }
+static int gsb_pdl_mode(int64_t phase_rows) {
+    static int env = -2;
+    if (env == -2) {
+        const char *e = getenv("GSB_PDL");
+        env = e ? atoi(e) : -1;
+    }
+    int mode = env >= 0 ? env : (phase_rows <= GS_PDL_AUTO_ROWS ? 1 : 0);
+    if (g_pdl_suppress) mode = 0;
+    g_pdl_last = mode;
+    return mode;
+}
+bool gsb_pdl_enabled() { return g_pdl_last != 0 && !g_pdl_suppress; }
+
 // partials must have room for GS_FOLD_BLOCKS * nrhs more doubles after the n_partials * nrhs used ones
 int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int nrhs, int checked, int mode,
                          cudaStream_t st) {
@@ -814,19 +837,6 @@ int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int
     cfg.numAttrs = gsb_pdl_enabled() ? 1 : 0;
     GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, ctl, partials, n_partials, checked, mode));
     return GSB_OK;
-}
-
-// Programmatic dependent launch is used for the ring kernels and gs_end_sweep unless GSB_PDL=0 or the caller is
-// capturing a CUDA graph (gsb_pdl_suppress).
-static thread_local int g_pdl_suppress = 0;
-void gsb_pdl_suppress(int on) { g_pdl_suppress = on; }
-bool gsb_pdl_enabled() {
-    static int env = -1;
-    if (env < 0) {
-        const char *e = getenv("GSB_PDL");
-        env = e ? atoi(e) : 1;
-    }
-    return env != 0 && !g_pdl_suppress;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1010,11 +1020,11 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
         const int smem = 64 + stages * stage_bytes;
         const int *tk = p->tile_k.p + p->tile_off[c];
-        // window descriptors: kernel 4 stages the windows; kernel 3 uses them as L2 prefetch hints (GSB_X_PREFETCH=0: off)
+        // window descriptors: kernel 4 stages the windows; kernel 3 can use them as L2 prefetch hints (GSB_X_PREFETCH=1|2)
         static int env_xpf = -1;
         if (env_xpf < 0) {
             const char *e = getenv("GSB_X_PREFETCH");
-            env_xpf = e ? atoi(e) : 1;
+            env_xpf = e ? atoi(e) : 0; // measured: the kernel already runs at ~93 % of the copy bandwidth; the hints cost 4 %
         }
         const bool have_win = p->kernel == 4 && p->tile_win.p;
         const int *tw = (win || (have_win && env_xpf)) ? p->tile_win.p + (size_t)p->win_off[c] * GS_WIN_DESC : nullptr;
@@ -1065,7 +1075,9 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = gsb_pdl_enabled() ? 1 : 0;
+        const int pdl = gsb_pdl_mode((int64_t)row1 - row0);
+        cfg.numAttrs = pdl ? 1 : 0;
+        halo.pdl_early = pdl == 1 ? 1 : 0;
         GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, (const int *)(win ? p->ci_slot.p : ci), va, dg, b, x, ld, row0, row1,
                                     nb, tk, tw, p->cap, wcap, ctl, partials, (const GsbHaloArgs)halo));
     } else if (eff == 2) {
