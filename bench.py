@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--strips", action="store_true", help="N = 1 through the strip solver (measurement aid)")
     return p.parse_args()
 
 
@@ -212,7 +213,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     L = pkg.load()
     pkg._lib.check(L.gsb_set_device(local), "gsb_set_device")
-    if world > 1:
+    if world > 1 or args.strips:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29555")
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from coursecomputationalphotography_b200 import dist_bench
         return dist_bench.run(args, pkg, wl, dist, rank, world, local)

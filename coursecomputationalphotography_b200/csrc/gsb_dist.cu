@@ -809,7 +809,7 @@ static int dist_halo_meta(gsb_dist *d, cudaStream_t st) {
         std::vector<int> order;
         order.reserve((size_t)nt);
         for (int t = 0; t < nt; ++t)
-            if (hi[t]) order.push_back(t);
+            if (hi[t]) order.push_back(t | ((int)hi[t] << 24)); // tile | info << 24: one load in the kernel
         d->n_halo_tiles[c] = (int)order.size();
         for (int t = 0; t < nt; ++t)
             if (!hi[t]) order.push_back(t);
@@ -891,6 +891,20 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         if (d->peer_failed || !d->peer_ready || !d->halo_meta || d->n_halo_tiles[0] == 0 || d->n_halo_tiles[1] == 0)
             use_peer = false;
     }
+    // measurement aid: one rank, but the halo variant of the ring kernels (no tile is a halo tile, no flag is ever
+    // touched) -- isolates what the variant itself costs from what the exchange costs
+    bool force_halo = false;
+    if (d->world == 1 && (d->plan.kernel == 3 || d->plan.kernel == 4)) {
+        const char *e = getenv("GSB_DIST_FORCE_HALO");
+        if (e && atoi(e) == 1) {
+            GSB_TRY(dist_halo_meta(d, st));
+            if (!d->flags.p) {
+                GSB_TRY(d->flags.alloc(8));
+                GSB_CUDA(cudaMemsetAsync(d->flags.p, 0, 8 * sizeof(int), st));
+            }
+            force_halo = d->halo_meta;
+        }
+    }
     d->used_peer = use_peer ? 1 : 0;
     // stop-rule all-reduce: fused into the end-of-sweep kernel over peer memory, or fold + ncclAllReduce + decide
     bool fused_eps = use_peer;
@@ -936,12 +950,30 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     GSB_CUDA(cudaEventCreate(&ev1));
     GSB_CUDA(cudaEventRecord(ev0, st));
     int issued = 0, status = GSB_OK;
+    // GSB_TRACE_PHASES=1: CUDA events around every launch of the first sweeps, averages printed to stderr
+    // (a measurement aid; the events break programmatic dependent launch, so use it with GSB_PDL=0)
+    std::vector<cudaEvent_t> tev;
+    const int trace_sweeps = 48;
+    {
+        const char *e = getenv("GSB_TRACE_PHASES");
+        if (e && atoi(e) == 1) tev.reserve(4 * trace_sweeps + 4);
+    }
+    const bool tracing = tev.capacity() > 0;
+    auto trace_mark = [&]() {
+        if (!tracing || (int)tev.size() >= 4 * trace_sweeps) return;
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) == cudaSuccess) {
+            cudaEventRecord(ev, st);
+            tev.push_back(ev);
+        }
+    };
     while (!h.done && status == GSB_OK) {
         int todo = max_iteration - issued;
         if (todo > batch) todo = batch;
         if (todo <= 0) todo = 1;
         for (int s = 0; s < todo && status == GSB_OK; ++s) {
             const int sweep_no = issued + s + 1;
+            trace_mark(); // 4 marks per sweep: start, after phase 0, after phase 1, after the end-of-sweep step
             const bool check = (sweep_no % opts.check_every) == 0 || sweep_no == max_iteration;
             int poff = 0;
             for (int c = 0; c < 2 && status == GSB_OK; ++c) {
@@ -949,12 +981,12 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 if (r1 > r0) {
                     GsbHaloArgs ha;
                     memset(&ha, 0, sizeof(ha));
-                    if (use_peer) {
+                    if (use_peer || force_halo) {
                         const long long sidx = (long long)issued + s; // sweeps of this call issued before this one
                         ha.enabled = 1;
                         ha.n_halo_tiles = d->n_halo_tiles[c];
                         ha.order = d->tile_order[c].p;
-                        ha.info = d->tile_info[c].p;
+                        ha.info = d->tile_info[c].p; // (the kernels read the copy packed into `order`)
                         for (int p = 0; p < 2; ++p) {
                             ha.has_peer[p] = d->has_peer(p) ? 1 : 0;
                             ha.push_map[p] = d->push_map[p].p;
@@ -970,11 +1002,12 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         ha.counter = d->flags.p + 4 + c;
                     }
                     status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p, d->xw.p, ld, nrhs, check,
-                                             ctl, d->partials.p + (size_t)poff * nrhs, st, use_peer ? &ha : nullptr);
+                                             ctl, d->partials.p + (size_t)poff * nrhs, st, (use_peer || force_halo) ? &ha : nullptr);
                     poff += gsb_plan_partial_slots(&d->plan, c, nrhs);
                     ++launches;
                 }
                 if (status == GSB_OK && !use_peer) status = dist_exchange(d, c, nrhs, st, &launches);
+                trace_mark();
             }
             if (status != GSB_OK) break;
             if (check && fused_eps) {
@@ -1001,6 +1034,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 status = gsb_launch_end_sweep(ctl, d->partials.p, 0, nrhs, 0, 2, st);
                 ++launches;
             }
+            trace_mark();
         }
         issued += todo;
         d->epoch = epoch_base + issued;
@@ -1024,6 +1058,22 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     cudaEventElapsedTime(&solve_ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    if (tracing && tev.size() >= 8) {
+        double acc[3] = {0, 0, 0};
+        const int ns = (int)tev.size() / 4;
+        for (int q = 1; q < ns; ++q) // skip the first sweep (cold)
+            for (int j = 0; j < 3; ++j) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, tev[(size_t)q * 4 + j], tev[(size_t)q * 4 + j + 1]);
+                acc[j] += ms;
+            }
+        float span = 0.f;
+        cudaEventElapsedTime(&span, tev[4], tev[(size_t)(ns - 1) * 4 + 3]);
+        fprintf(stderr, "gsb trace: rank %d of %d, %d sweeps: phase0 %.1f us  phase1 %.1f us  end-of-sweep %.1f us  "
+                        "sweep (span) %.1f us\n", d->rank, d->world, ns - 1, 1e3 * acc[0] / (ns - 1),
+                1e3 * acc[1] / (ns - 1), 1e3 * acc[2] / (ns - 1), 1e3 * span / (ns - 1));
+    }
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
     if (status != GSB_OK) return status;
     d_scatter<<<(n_local + 255) / 256, 256, 0, st>>>(d->xw.p, ld, d->perm.p, n_local, nrhs, n_local, x_dev);
     GSB_KERNEL_CHECK();

@@ -201,7 +201,7 @@ static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
 struct GsbHaloArgs {
     int enabled;
     int n_halo_tiles;          // tiles (first in `order`) that read ghosts and/or own rows a neighbour reads
-    const int *order;          // processing order of this colour's tiles: halo tiles first
+    const int *order;          // processing order of this colour's tiles, halo tiles first: tile | info << 24
     const unsigned char *info; // per tile: bit0 reads ghosts, bit1 has rows to push
     const int *push_map[2];    // per neighbour: row (permuted local index) -> slot in the neighbour's ghost range, or -1
     double *peer_x[2];         // neighbour's x workspace (peer mapping)

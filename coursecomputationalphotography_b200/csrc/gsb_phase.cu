@@ -282,10 +282,12 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         }
         return d;
     };
-    // strip solver: halo tiles come first in the processing order
-    auto tile_of = [&](int logical) -> int { return HALO ? halo.order[logical] : logical; };
-    auto issue = [&](const TileDesc &td, int t, int s) { // thread 0 only
-        if (HALO && halo.wait_epoch > 0 && (halo.info[t] & 1)) {
+    // strip solver: halo tiles come first in the processing order.  order[logical] = tile | info << 24 (one load
+    // yields both; info bit0: the tile reads ghosts, bit1: it owns rows a neighbour reads)
+    auto entry_of = [&](int logical) -> int { return HALO ? halo.order[logical] : logical; };
+    auto issue = [&](const TileDesc &td, int te, int s) { // thread 0 only; te: entry_of(logical tile)
+        const int t = HALO ? (te & 0xffffff) : te;
+        if (HALO && halo.wait_epoch > 0 && ((te >> 24) & 1)) {
             // this tile reads ghost unknowns: the neighbours' values of the other colour must have landed
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr)
@@ -379,8 +381,8 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         for (int s = 0; s < STAGES; ++s) {
             const int tl = blockIdx.x + s * gridDim.x;
             if (tl < ntiles) {
-                const int t = tile_of(tl);
-                issue(load_desc(t), t, s);
+                const int te = entry_of(tl);
+                issue(load_desc(HALO ? (te & 0xffffff) : te), te, s);
             }
         }
     }
@@ -400,8 +402,11 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
     int k = 0;
+    int cur = entry_of(blockIdx.x); // the order entry of the next tile is fetched one iteration ahead
     for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
-        const int t = tile_of(tl);
+        const int t = HALO ? (cur & 0xffffff) : tl;
+        const int tinfo = HALO ? (cur >> 24) : 0;
+        if (HALO && tl + (int)gridDim.x < ntiles) cur = entry_of(tl + gridDim.x);
         const int s = k % STAGES;
         const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
@@ -409,10 +414,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         int tn = 0;
         TileDesc next_desc;
         if (tid == 0 && tln < ntiles) {
-            tn = tile_of(tln);
-            next_desc = load_desc(tn);
+            tn = entry_of(tln);
+            next_desc = load_desc(HALO ? (tn & 0xffffff) : tn);
         }
-        const int tinfo = HALO ? halo.info[t] : 0;
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
         mbar_wait(&full[s], parity);

@@ -189,12 +189,23 @@ def main():
     mode = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if mode == "cpu":
-        dist.init_process_group("gloo")
-        cpu_mode(rank, world)
-    else:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        gpu_mode(rank, world, local)
+    try:
+        if mode == "cpu":
+            dist.init_process_group("gloo")
+            cpu_mode(rank, world)
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            gpu_mode(rank, world, local)
+    except BaseException:
+        # the launcher only reports the exit code: say what failed, on stdout (the parent test shows its tail)
+        import traceback
+        msg = "rank %d of %d FAILED:\n%s" % (rank, world, traceback.format_exc())
+        print(msg, flush=True)
+        log = os.environ.get("GSB_WORKER_LOG")
+        if log:
+            with open("%s.rank%d" % (log, rank), "w") as f:
+                f.write(msg)
+        os._exit(1)
     dist.barrier()
     dist.destroy_process_group()
 
