@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsb200.so")
+# GSB_LIB_PATH: development aid -- load an experimental build of the same library (tools/exp/)
+LIB_PATH = os.environ.get("GSB_LIB_PATH") or os.path.join(_HERE, "libgsb200.so")
 
 GSB_F64, GSB_I32 = 0, 1
 ORDER_AUTO, ORDER_REDBLACK, ORDER_MULTICOLOR, ORDER_USER = 0, 1, 2, 3

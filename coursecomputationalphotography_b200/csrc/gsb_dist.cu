@@ -122,6 +122,8 @@ struct gsb_dist {
     DevBuf<int> tile_order[2], push_map[2];
     DevBuf<unsigned char> tile_info[2];
     int n_halo_tiles[2] = {0, 0};
+    int interior_base[2] = {-1, -1}; // first interior tile when the interior tiles are one contiguous range
+    int n_interior[2] = {0, 0};
     long long epoch = 0;       // flags only ever grow: epoch of the last sweep issued so far
     int used_peer = 0;
     // fused stop-rule all-reduce (GsbEpsExchange): this rank's box and every rank's box peer-mapped
@@ -811,6 +813,16 @@ static int dist_halo_meta(gsb_dist *d, cudaStream_t st) {
         for (int t = 0; t < nt; ++t)
             if (hi[t]) order.push_back(t | ((int)hi[t] << 24)); // tile | info << 24: one load in the kernel
         d->n_halo_tiles[c] = (int)order.size();
+        // interior tiles: one contiguous range [a, b) when the halo tiles are a prefix and a suffix of the colour's
+        // tiles (row strips) -> the kernel numbers them arithmetically
+        int a = 0, b = nt;
+        while (a < nt && hi[(size_t)a]) ++a;
+        while (b > a && hi[(size_t)b - 1]) --b;
+        bool contiguous = true;
+        for (int t = a; t < b; ++t)
+            if (hi[(size_t)t]) contiguous = false;
+        d->interior_base[c] = contiguous ? a : -1;
+        d->n_interior[c] = contiguous ? b - a : 0;
         for (int t = 0; t < nt; ++t)
             if (!hi[t]) order.push_back(t);
         GSB_CUDA(cudaMemcpyAsync(d->tile_order[c].p, order.data(), sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, st));
@@ -890,6 +902,9 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         GSB_TRY(dist_halo_meta(d, st));
         if (d->peer_failed || !d->peer_ready || !d->halo_meta || d->n_halo_tiles[0] == 0 || d->n_halo_tiles[1] == 0)
             use_peer = false;
+        // the kernels number the interior tiles arithmetically and give every halo tile its own CTA
+        for (int c = 0; c < 2; ++c)
+            if (d->interior_base[c] < 0 || d->n_halo_tiles[c] > 1024) use_peer = false;
     }
     // measurement aid: one rank, but the halo variant of the ring kernels (no tile is a halo tile, no flag is ever
     // touched) -- isolates what the variant itself costs from what the exchange costs
@@ -902,7 +917,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 GSB_TRY(d->flags.alloc(8));
                 GSB_CUDA(cudaMemsetAsync(d->flags.p, 0, 8 * sizeof(int), st));
             }
-            force_halo = d->halo_meta;
+            force_halo = d->halo_meta && d->interior_base[0] >= 0 && d->interior_base[1] >= 0;
         }
     }
     d->used_peer = use_peer ? 1 : 0;
@@ -985,6 +1000,8 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         const long long sidx = (long long)issued + s; // sweeps of this call issued before this one
                         ha.enabled = 1;
                         ha.n_halo_tiles = d->n_halo_tiles[c];
+                        ha.interior_base = d->interior_base[c];
+                        ha.n_interior = d->n_interior[c];
                         ha.order = d->tile_order[c].p;
                         ha.info = d->tile_info[c].p; // (the kernels read the copy packed into `order`)
                         for (int p = 0; p < 2; ++p) {

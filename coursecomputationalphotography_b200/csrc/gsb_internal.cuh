@@ -201,8 +201,8 @@ static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
 struct GsbHaloArgs {
     int enabled;
     int n_halo_tiles;          // tiles (first in `order`) that read ghosts and/or own rows a neighbour reads
-    const int *order;          // processing order of this colour's tiles, halo tiles first: tile | info << 24
-    const unsigned char *info; // per tile: bit0 reads ghosts, bit1 has rows to push
+    const int *order;          // (host-side bookkeeping; the kernels number the tiles arithmetically)
+    const unsigned char *info; // per tile: bit0 reads ghosts, bit1 has rows to push (likewise)
     const int *push_map[2];    // per neighbour: row (permuted local index) -> slot in the neighbour's ghost range, or -1
     double *peer_x[2];         // neighbour's x workspace (peer mapping)
     long long peer_ld[2];
@@ -213,6 +213,8 @@ struct GsbHaloArgs {
     int *counter;              // halo tiles finished in this phase
     int has_peer[2];
     int pdl_early;             // set by the launcher: stage the first tiles before griddepcontrol.wait (kernel 3)
+    int interior_base;         // the tiles that are not halo tiles: [interior_base, interior_base + n_interior)
+    int n_interior;
 };
 
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles

@@ -244,23 +244,86 @@ __host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check,
     return L;
 }
 
+// The halo CTAs' synchronisation with the neighbour GPUs.  Kept out of line on purpose: with the spin loop, the
+// system-scope fences and the atomic inlined, ptxas stops using the uniform datapath for the whole kernel and the
+// interior tiles run 8 % slower (measured); as calls on a cold path they cost the interior nothing.
+__device__ __noinline__ void halo_wait_flags(const int *f0, const int *f1, int epoch) {
+    const int *f[2] = {f0, f1};
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr)
+        if (f[pr]) {
+            int v;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f[pr]) : "memory");
+            } while (v < epoch);
+        }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __noinline__ void halo_fence_system() { __threadfence_system(); }
+// one halo tile of the phase is complete; the last one raises the neighbours' flags (release at system scope
+// orders this GPU's peer stores before the flag)
+__device__ __noinline__ void halo_tile_done(int *counter, int n_halo_tiles, int *flag0, int *flag1, int epoch) {
+    const int done_tiles = atomicAdd(counter, 1) + 1;
+    if (done_tiles != n_halo_tiles) return;
+    *counter = 0;
+    __threadfence_system();
+    if (flag0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag0), "r"(epoch) : "memory");
+    if (flag1) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag1), "r"(epoch) : "memory");
+}
+
 // resident CTAs per SM the register allocation must allow: 4 wherever shared memory lets 4 stages-pairs fit
 // (k = 3 with windows is limited to 2-3 by its 49 KB stages)
+//
+// HALO (strip solver): the grid is [n_halo_tiles one-tile CTAs | the persistent ring over the interior tiles].
+// CTA b < n_halo_tiles takes the b-th halo tile -- a tile that reads ghost unknowns and/or owns rows a neighbour
+// GPU reads -- and runs the same code as a ring of exactly one tile, plus the flag wait, the peer stores and the
+// completion count.  The other CTAs run the ring over the interior tiles [interior_base, interior_base + n_interior),
+// numbered arithmetically, so the interior path is instruction-for-instruction the single-GPU kernel (a table
+// look-up per tile, or halo code in the tile body, costs 8-13 % -- measured, profiles/README.md).
 template <int NRHS, bool CHECK, int STAGES, bool WIN, bool HALO>
 __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                  const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0,
-                  int row1, int ntiles,
-                  const int *__restrict__ tile_k, const int *__restrict__ tile_win, int cap, int wcap,
+                  const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0_in,
+                  int row1_in, int ntiles_in,
+                  const int *__restrict__ tile_k_in, const int *__restrict__ tile_win_in, int cap, int wcap,
                   const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RingLayout L = ring_layout(cap, NRHS, CHECK, WIN ? wcap : 0);
-    // kernel 3 with window descriptors: the x spans a tile will gather from are pulled into L2 when the tile's
-    // stage is issued (one tile ahead), so that the gathers see L2 latency instead of HBM latency
-    const bool xpf = !WIN && tile_win != nullptr;
+    // kernel 3 with window descriptors: the x spans a tile will gather from can be pulled into L2 when the tile's
+    // stage is issued (one tile ahead); off by default (GSB_X_PREFETCH)
+    const bool xpf = !WIN && tile_win_in != nullptr;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     unsigned char *stage0 = smem_raw + 64;
     const int tid = threadIdx.x;
+
+    // the slice of the colour phase this CTA walks: tiles t = bid, bid + gsz, ... < ntiles of rows [row0, row1)
+    int bid = blockIdx.x, gsz = gridDim.x, row0 = row0_in, row1 = row1_in, ntiles = ntiles_in;
+    const int *tile_k = tile_k_in, *tile_win = tile_win_in;
+    int hinfo = 0; // halo CTA: bit0 the tile reads ghosts, bit1 it owns rows a neighbour reads
+    if (HALO) {
+        const int nh = halo.n_halo_tiles;
+        int first, count;
+        if (bid < nh) {
+            // halo tiles are the prefix [0, interior_base) and the suffix [interior_base + n_interior, tiles) of the
+            // colour's tiles; every one of them is treated as "reads ghosts and pushes" (a tile that does only one
+            // of the two waits on a flag that is raised anyway / finds no row to push) -- no table, all uniform
+            first = bid < halo.interior_base ? bid : bid + halo.n_interior;
+            count = 1;
+            hinfo = 3;
+            bid = 0;
+            gsz = 1;
+        } else {
+            first = halo.interior_base;
+            count = halo.n_interior;
+            bid -= nh;
+            gsz -= nh;
+        }
+        row0 = row0_in + first * GS_THREADS;
+        row1 = min(row1_in, row0 + count * GS_THREADS);
+        ntiles = count;
+        tile_k = tile_k_in + first;
+        if (tile_win_in) tile_win = tile_win_in + (size_t)first * GS_WIN_DESC;
+    }
 
     // tile descriptor: fetched by thread 0 one iteration before it is needed, so that its L2 latency hides
     // behind the compute of the current tile
@@ -282,23 +345,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         }
         return d;
     };
-    // strip solver: halo tiles come first in the processing order.  order[logical] = tile | info << 24 (one load
-    // yields both; info bit0: the tile reads ghosts, bit1: it owns rows a neighbour reads)
-    auto entry_of = [&](int logical) -> int { return HALO ? halo.order[logical] : logical; };
-    auto issue = [&](const TileDesc &td, int te, int s) { // thread 0 only; te: entry_of(logical tile)
-        const int t = HALO ? (te & 0xffffff) : te;
-        if (HALO && halo.wait_epoch > 0 && ((te >> 24) & 1)) {
-            // this tile reads ghost unknowns: the neighbours' values of the other colour must have landed
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr)
-                if (halo.has_peer[pr]) {
-                    int v;
-                    do {
-                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(halo.wait_flag[pr]) : "memory");
-                    } while (v < halo.wait_epoch);
-                }
-            asm volatile("fence.proxy.async;" ::: "memory");
-        }
+    auto issue = [&](const TileDesc &td, int t, int s) { // thread 0 only
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
         int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
         const int r_begin = row0 + t * GS_THREADS;
@@ -363,6 +410,12 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         }
     };
 
+    // halo CTA: its tile reads ghost unknowns -- the neighbours' values of the other colour must have landed before
+    // anything of the tile is staged or gathered.  (The calls sit at the very top and the very bottom of the
+    // kernel: a call inside the tile loop makes ptxas give up the uniform datapath for the whole loop.)
+    if (HALO && hinfo && tid == 0 && halo.wait_epoch > 0)
+        halo_wait_flags(halo.has_peer[0] ? halo.wait_flag[0] : nullptr, halo.has_peer[1] ? halo.wait_flag[1] : nullptr,
+                        halo.wait_epoch);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
@@ -379,11 +432,8 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     if (tid == 0 && (early || !*(volatile const int *)&ctl->done)) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            const int tl = blockIdx.x + s * gridDim.x;
-            if (tl < ntiles) {
-                const int te = entry_of(tl);
-                issue(load_desc(HALO ? (te & 0xffffff) : te), te, s);
-            }
+            const int t = bid + s * gsz;
+            if (t < ntiles) issue(load_desc(t), t, s);
         }
     }
     if (early) pdl_wait();
@@ -391,7 +441,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         if (early) { // the prologue's bulk copies must land before the shared memory is released
 #pragma unroll
             for (int s = 0; s < STAGES; ++s)
-                if (blockIdx.x + s * gridDim.x < ntiles) mbar_wait(&full[s], 0);
+                if (bid + s * gsz < ntiles) mbar_wait(&full[s], 0);
         }
         return;
     }
@@ -402,21 +452,13 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
     int k = 0;
-    int cur = entry_of(blockIdx.x); // the order entry of the next tile is fetched one iteration ahead
-    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
-        const int t = HALO ? (cur & 0xffffff) : tl;
-        const int tinfo = HALO ? (cur >> 24) : 0;
-        if (HALO && tl + (int)gridDim.x < ntiles) cur = entry_of(tl + gridDim.x);
+    for (int t = bid; t < ntiles; t += gsz, ++k) {
         const int s = k % STAGES;
         const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
         unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
-        const int tln = tl + STAGES * gridDim.x; // the (logical) tile that will reuse this stage
-        int tn = 0;
+        const int tn = t + STAGES * gsz; // the tile that will reuse this stage
         TileDesc next_desc;
-        if (tid == 0 && tln < ntiles) {
-            tn = entry_of(tln);
-            next_desc = load_desc(HALO ? (tn & 0xffffff) : tn);
-        }
+        if (tid == 0 && tn < ntiles) next_desc = load_desc(tn);
         const int r_begin = row0 + t * GS_THREADS;
         const int rows = min(GS_THREADS, row1 - r_begin);
         mbar_wait(&full[s], parity);
@@ -441,45 +483,44 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
             else
                 gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int c, int r) { return x[r * n + c]; }, sig);
             if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+                double xn[NRHS];
 #pragma unroll
-                for (int r = 0; r < NRHS; ++r) {
+                for (int r = 0; r < NRHS; ++r) { // the k divisions are independent: keep them in one straight-line block
                     const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
-                    const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
-                    if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
-                    x[r * n + i] = xn;
-                    if (HALO && (tinfo & 2)) { // a neighbour GPU reads this row: store it into its ghost slot as well
+                    xn[r] = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
+                    if (CHECK) acc[r] += fabs(xn[r] - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
+                    x[r * n + i] = xn[r];
+                }
+                if (HALO && (hinfo & 2)) { // a neighbour GPU reads rows of this tile: store them into its ghost slots too
 #pragma unroll
-                        for (int pr = 0; pr < 2; ++pr)
-                            if (halo.has_peer[pr]) {
-                                const int slot = halo.push_map[pr][i];
-                                if (slot >= 0) halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn;
+                    for (int pr = 0; pr < 2; ++pr)
+                        if (halo.has_peer[pr]) {
+                            const int slot = halo.push_map[pr][i];
+                            if (slot >= 0) {
+#pragma unroll
+                                for (int r = 0; r < NRHS; ++r)
+                                    halo.peer_x[pr][r * halo.peer_ld[pr] + halo.peer_gs[pr] + slot] = xn[r];
                             }
-                    }
+                        }
                 }
             }
         }
-        if (HALO && (tinfo & 2)) __threadfence_system(); // peer stores visible before this tile is counted as done
         __syncthreads(); // every thread is done with stage s
-        if (HALO && tid == 0 && tinfo) {
-            // last halo tile of the phase: every ghost read and every push of this phase is complete ->
-            // raise the neighbours' flags (release at system scope orders the pushes before the flag)
-            const int done_tiles = atomicAdd(halo.counter, 1) + 1;
-            if (done_tiles == halo.n_halo_tiles) {
-                *halo.counter = 0;
-                __threadfence_system();
-#pragma unroll
-                for (int pr = 0; pr < 2; ++pr)
-                    if (halo.has_peer[pr])
-                        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(halo.peer_flag[pr]), "r"(halo.signal_epoch)
-                                     : "memory");
-            }
-        }
-        if (tid == 0 && tln < ntiles) issue(next_desc, tn, s);
+        if (tid == 0 && tn < ntiles) issue(next_desc, tn, s);
+    }
+    if (HALO && hinfo) {
+        // halo CTA, its one tile done: peer stores visible (system scope) before the tile is counted; the last
+        // halo tile of the phase raises the neighbours' flags
+        halo_fence_system();
+        __syncthreads();
+        if (tid == 0)
+            halo_tile_done(halo.counter, halo.n_halo_tiles, halo.has_peer[0] ? halo.peer_flag[0] : nullptr,
+                           halo.has_peer[1] ? halo.peer_flag[1] : nullptr, halo.signal_epoch);
     }
     if (CHECK) {
         gsb_block_reduce_store<NRHS, GS_THREADS>(acc, partials + (size_t)blockIdx.x * NRHS);
-        // the phase owns min(ntiles, GS_RING_SLOTS_MAX) partial slots (gsb_plan_partial_slots); unused ones are zero
-        const int nslots = min(ntiles, GS_RING_SLOTS_MAX);
+        // the phase owns min(tiles, GS_RING_SLOTS_MAX) partial slots (gsb_plan_partial_slots); unused ones are zero
+        const int nslots = min(ntiles_in, GS_RING_SLOTS_MAX);
         for (int t2 = blockIdx.x + gridDim.x; t2 < nslots; t2 += gridDim.x)
             if (tid < NRHS) partials[(size_t)t2 * NRHS + tid] = 0.0;
     }
@@ -1067,9 +1108,22 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         }
         int per_sm = cf->occ;
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
+        // halo variant: n_halo_tiles one-tile CTAs first, then the persistent ring over the interior tiles
+        const int ring_tiles = halo.enabled ? halo.n_interior : nb;
         int grid = gsb_sm_count() * per_sm;
-        if (grid > nb) grid = nb;
-        if (grid > GS_RING_SLOTS_MAX) grid = GS_RING_SLOTS_MAX;
+        if (grid > ring_tiles) grid = ring_tiles;
+        if (halo.enabled) grid += halo.n_halo_tiles;
+        if (grid > GS_RING_SLOTS_MAX) {
+            if (halo.enabled) {
+                gsb_set_error("fused halo exchange: %d halo tiles exceed the partial-slot budget", halo.n_halo_tiles);
+                return GSB_ERR_ARG;
+            }
+            grid = GS_RING_SLOTS_MAX;
+        }
+        if (halo.enabled && (halo.interior_base < 0 || halo.n_halo_tiles + halo.n_interior != nb)) {
+            gsb_set_error("fused halo exchange needs the interior tiles to be one contiguous range");
+            return GSB_ERR_ARG;
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(GS_THREADS);
