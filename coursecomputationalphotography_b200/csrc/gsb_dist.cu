@@ -114,6 +114,7 @@ struct gsb_dist {
     bool peer_ready = false;   // peer pointers valid for the current xw allocation
     bool peer_failed = false;  // IPC unavailable: stay on the NCCL send/recv path
     bool halo_meta = false;    // tile order / info / push maps built for the current plan
+    bool halo_agreed_valid = false, halo_agreed = false; // all ranks can fuse the exchange for the current plan
     DevBuf<int> flags;         // [peer][colour] raised by the neighbours, then [4..5] halo-tile counters per colour
     double *peer_x[2] = {nullptr, nullptr};
     int *peer_flags[2] = {nullptr, nullptr};
@@ -542,6 +543,7 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     d->ws_nrhs = 0;
     d->plan.valid = false; // the launch plan belongs to the previous matrix
     d->halo_meta = false;
+    d->halo_agreed_valid = false;
     d->built = true;
     return GSB_OK;
 }
@@ -884,6 +886,8 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     if (!d->plan.valid || d->plan.requested != opts.kernel) {
         GSB_TRY(gsb_plan_build(&d->plan, d->rp.p, d->ci.p, d->color_start, 2, opts.kernel, st));
         GSB_TRY(d->partials.alloc((int64_t)(d->plan.total_blocks() + 1 + 64) * GSB_MAX_RHS));
+        d->halo_meta = false;
+        d->halo_agreed_valid = false;
     }
     if (d->ws_nrhs < nrhs) {
         GSB_TRY(d->xw.alloc(ld * nrhs + 128));
@@ -892,19 +896,36 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
         d->peer_ready = false; // x moved: the neighbours' mappings of it are stale
     }
     // transport of the halo: fused peer stores inside the ring kernels (default), or packed ncclSend/ncclRecv
-    bool use_peer = d->world > 1 && !d->peer_failed && (d->plan.kernel == 3 || d->plan.kernel == 4);
+    bool use_peer = false;
     {
+        bool want = d->world > 1 && !d->peer_failed;
         const char *e = getenv("GSB_DIST_TRANSPORT");
-        if (e && strcmp(e, "nccl") == 0) use_peer = false;
-    }
-    if (use_peer) {
-        if (!d->peer_ready) GSB_TRY(dist_peer_setup(d, st));
-        GSB_TRY(dist_halo_meta(d, st));
-        if (d->peer_failed || !d->peer_ready || !d->halo_meta || d->n_halo_tiles[0] == 0 || d->n_halo_tiles[1] == 0)
-            use_peer = false;
-        // the kernels number the interior tiles arithmetically and give every halo tile its own CTA
-        for (int c = 0; c < 2; ++c)
-            if (d->interior_base[c] < 0 || d->n_halo_tiles[c] > 1024) use_peer = false;
+        if (e && strcmp(e, "nccl") == 0) want = false;
+        use_peer = false;
+        if (want) {
+            if (!d->peer_ready) GSB_TRY(dist_peer_setup(d, st)); // collective; agrees on peer_failed itself
+            if (d->peer_ready && !d->peer_failed) {
+                if (!d->halo_agreed_valid) {
+                    int cap = (d->plan.kernel == 3 || d->plan.kernel == 4) ? 1 : 0;
+                    if (cap) {
+                        GSB_TRY(dist_halo_meta(d, st));
+                        if (!d->halo_meta || d->n_halo_tiles[0] == 0 || d->n_halo_tiles[1] == 0) cap = 0;
+                        // the kernels number the interior tiles arithmetically and give every halo tile its own CTA
+                        for (int c = 0; c < 2; ++c)
+                            if (d->interior_base[c] < 0 || d->n_halo_tiles[c] > 1024) cap = 0;
+                    }
+                    DevBuf<int> agree;
+                    GSB_TRY(agree.alloc(1));
+                    GSB_CUDA(cudaMemcpyAsync(agree.p, &cap, sizeof(int), cudaMemcpyHostToDevice, st));
+                    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
+                    GSB_CUDA(cudaMemcpyAsync(&cap, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    GSB_CUDA(cudaStreamSynchronize(st));
+                    d->halo_agreed = cap != 0;
+                    d->halo_agreed_valid = true;
+                }
+                use_peer = d->halo_agreed;
+            }
+        }
     }
     // measurement aid: one rank, but the halo variant of the ring kernels (no tile is a halo tile, no flag is ever
     // touched) -- isolates what the variant itself costs from what the exchange costs
@@ -1036,10 +1057,13 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 for (int q = 0; q < d->world; ++q) ex.box[q] = d->peer_box[q];
                 status = gsb_launch_end_sweep_peer(ctl, d->partials.p, poff, nrhs, &ex, st);
                 ++launches;
+            } else if (check && d->world == 1) {
+                status = gsb_launch_end_sweep(ctl, d->partials.p, poff, nrhs, 1, 0, st);
+                ++launches;
             } else if (check) {
                 status = gsb_launch_end_sweep(ctl, d->partials.p, poff, nrhs, 1, 1, st);
-                if (status == GSB_OK && d->world > 1) {
-                    ncclResult_t r = g_nccl.AllReduce(ctl->eps_last, ctl->eps_last, nrhs, ncclFloat64, ncclSum, d->comm, st);
+                if (status == GSB_OK) {
+                    ncclResult_t r = g_nccl.AllReduce(ctl->eps_local, ctl->eps_last, nrhs, ncclFloat64, ncclSum, d->comm, st);
                     if (r != ncclSuccess) {
                         gsb_set_error("ncclAllReduce -> %s", g_nccl.GetErrorString(r));
                         status = GSB_ERR_NCCL;

@@ -164,6 +164,7 @@ struct GsCtl {
     double eps_last[GSB_MAX_RHS];
     int error; // 1: the peer stop-rule exchange timed out (a rank is missing); the solve stops
     int pad_;
+    double eps_local[GSB_MAX_RHS]; // strip solver, ncclAllReduce path: this rank's share of eps_last
 };
 
 // how the colour phases of one colour-major CSR are launched (gsb_phase.cu)

@@ -410,12 +410,6 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         }
     };
 
-    // halo CTA: its tile reads ghost unknowns -- the neighbours' values of the other colour must have landed before
-    // anything of the tile is staged or gathered.  (The calls sit at the very top and the very bottom of the
-    // kernel: a call inside the tile loop makes ptxas give up the uniform datapath for the whole loop.)
-    if (HALO && hinfo && tid == 0 && halo.wait_epoch > 0)
-        halo_wait_flags(halo.has_peer[0] ? halo.wait_flag[0] : nullptr, halo.has_peer[1] ? halo.wait_flag[1] : nullptr,
-                        halo.wait_epoch);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
@@ -427,23 +421,35 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     // the predecessor does not write; the predecessor's x (the gathers, the window copies) and the control block
     // are only touched after pdl_wait().
     pdl_launch_dependents();
-    const bool early = !WIN && halo.pdl_early; // prologue before the predecessor has finished
-    if (!early) pdl_wait();
-    if (tid == 0 && (early || !*(volatile const int *)&ctl->done)) {
+    // prologue before the predecessor has finished -- not for halo CTAs, which must know that the solve is still
+    // running before they wait for a neighbour (after the stop decision no flag is raised any more)
+    const bool early = !WIN && halo.pdl_early && !(HALO && hinfo);
+    if (!early) {
+        pdl_wait();
+        if (*(volatile const int *)&ctl->done) return; // nothing staged yet
+    }
+    // halo CTA: its tile reads ghost unknowns -- the neighbours' values of the other colour must have landed before
+    // anything of the tile is staged or gathered.  (The halo calls sit before and after the tile loop: a call
+    // inside it makes ptxas give up the uniform datapath for the whole loop.)
+    if (HALO && hinfo && tid == 0 && halo.wait_epoch > 0)
+        halo_wait_flags(halo.has_peer[0] ? halo.wait_flag[0] : nullptr, halo.has_peer[1] ? halo.wait_flag[1] : nullptr,
+                        halo.wait_epoch);
+    if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const int t = bid + s * gsz;
             if (t < ntiles) issue(load_desc(t), t, s);
         }
     }
-    if (early) pdl_wait();
-    if (*(volatile const int *)&ctl->done) { // written only by gs_end_sweep, i.e. constant from here on
-        if (early) { // the prologue's bulk copies must land before the shared memory is released
+    if (early) {
+        pdl_wait();
+        if (*(volatile const int *)&ctl->done) { // written only by gs_end_sweep, i.e. constant from here on
+            // the prologue's bulk copies must land before the shared memory is released
 #pragma unroll
             for (int s = 0; s < STAGES; ++s)
                 if (bid + s * gsz < ntiles) mbar_wait(&full[s], 0);
+            return;
         }
-        return;
     }
 
     // stop-rule partial: accumulated per thread over the CTA's tiles (static schedule -> fixed order) and folded
@@ -685,7 +691,10 @@ __global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *_
             for (int r = 0; r < NRHS; ++r) {
                 double t = 0.0;
                 for (int w = 0; w < 32; ++w) t += ws[r][w];
-                ctl->eps_last[r] = t;
+                if (mode == 1)
+                    ctl->eps_local[r] = t; // this rank's share; the all-reduce writes eps_last (idempotent after the stop)
+                else
+                    ctl->eps_last[r] = t;
                 if (t > ctl->epsilon) all_ok = false; // v2 :356: the loop continues while eps > epsilon
             }
         }
