@@ -418,14 +418,16 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     // Programmatic dependent launch: the next kernel of the stream may take the SM slots this grid frees as its
     // CTAs retire, and this grid may itself have started while the previous colour phase was still draining.
     // Everything the prologue stages is either constant (CSR, diagonal, b) or this colour's own x (x_old), which
-    // the predecessor does not write; the predecessor's x (the gathers, the window copies) and the control block
-    // are only touched after pdl_wait().
-    pdl_launch_dependents();
+    // the predecessor does not write (and the kernel that did write it has completed, see below); the
+    // predecessor's x (the gathers, the window copies) and the control block are only touched after pdl_wait().
+    // The dependents are released only AFTER this kernel's own wait: the kernel after this one may then overlap
+    // this one, but never the one before it (whose x -- this colour's x_old two phases later -- it stages early).
     // prologue before the predecessor has finished -- not for halo CTAs, which must know that the solve is still
     // running before they wait for a neighbour (after the stop decision no flag is raised any more)
     const bool early = !WIN && halo.pdl_early && !(HALO && hinfo);
     if (!early) {
         pdl_wait();
+        pdl_launch_dependents();
         if (*(volatile const int *)&ctl->done) return; // nothing staged yet
     }
     // halo CTA: its tile reads ghost unknowns -- the neighbours' values of the other colour must have landed before
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     }
     if (early) {
         pdl_wait();
+        pdl_launch_dependents();
         if (*(volatile const int *)&ctl->done) { // written only by gs_end_sweep, i.e. constant from here on
             // the prologue's bulk copies must land before the shared memory is released
 #pragma unroll

@@ -325,3 +325,25 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     # auto on the grid picks the window kernel
     sp.gaussSeidel(bb, epsilon=0.0, max_iteration=1)
     assert sp.last_stats.kernel_used == (4 if nrhs == 1 else 3)  # measured policy, see gsb_plan_effective_kernel
+
+
+@pytest.mark.parametrize("W,H,nrhs", [(64, 48, 3), (300, 217, 1), (300, 217, 3), (1024, 512, 3)])
+def test_dependent_launch_equals_graph_replay(gsb, W, H, nrhs):
+    """Plain launches use programmatic dependent launch (the next colour phase stages its first tiles while the
+    previous one drains); the CUDA-graph path does not.  Solution AND stop norm must agree bit for bit, every
+    sweep -- a kernel that staged x_old before its writer had finished would show up in the norm only."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
+    bb = b[:nrhs] if nrhs > 1 else b[0]
+    for k in (3, 4):
+        for sweeps in (1, 2, 7):
+            out = []
+            for graph in (1, 0):
+                o = gsb.SparseMatrix.options(kernel=k, use_graph=graph, batch_sweeps=7)
+                x = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=sweeps, options=o)
+                out.append((x, list(sp.last_stats.last_eps)[:nrhs], sp.last_stats.sweeps))
+            assert out[0][2] == out[1][2] == sweeps
+            assert np.array_equal(out[0][0], out[1][0]), (k, sweeps)
+            assert out[0][1] == out[1][1], (k, sweeps, out[0][1], out[1][1])
