@@ -200,6 +200,7 @@ def main():
         # the launcher only reports the exit code: say what failed, on stdout (the parent test shows its tail)
         import traceback
         msg = "rank %d of %d FAILED:\n%s" % (rank, world, traceback.format_exc())
+        sys.stdout.flush()
         print(msg, flush=True)
         log = os.environ.get("GSB_WORKER_LOG")
         if log:

@@ -1,0 +1,10 @@
+# 2-GPU call (short): PDL-vs-graph equivalence test, strip-solver parity incl. the real-epsilon stop at world 2, one N = 2 bench line
+mkdir -p gpurun_out
+(timeout 200 python -m pytest tests/test_gs_gpu.py -m gpu -x -q -k "dependent_launch or all_kernels" 2>&1 | tail -8) > gpurun_out/c7_pytest.log
+cat gpurun_out/c7_pytest.log
+export GSB_WORKER_LOG=$PWD/gpurun_out/c7_worker
+(timeout 150 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29941 tests/dist_worker.py gpu 2>&1 | grep "FAILED\|strips ok\|stop rule ok\|Error\|assert" | head -30) > gpurun_out/c7_worker2.log
+cat gpurun_out/c7_worker2.log; cat gpurun_out/c7_worker.rank* 2>/dev/null | tail -30
+unset GSB_WORKER_LOG
+(timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29942 bench.py --gpus 2 --steps 3 --warmup 3 --sweeps 100 --no-e2e 2>&1 | grep "^{" | tail -1) > gpurun_out/c7_n2_ce1.json
+cut -c1-200 gpurun_out/c7_n2_ce1.json
