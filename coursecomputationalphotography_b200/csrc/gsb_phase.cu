@@ -1101,21 +1101,27 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
 #undef GSB_RING_PICK_ST
 #undef GSB_RING_PICK
         // per (variant) cache of the opt-in shared-memory size and the resident CTAs per SM
-        struct Cfg { const void *fn; int smem, occ; };
-        static Cfg cfgs[64];
+        struct Cfg { const void *fn; int smem, occ, dev; };
+        const int dev_now = gsb_current_device(); // function attributes and occupancy are per device
+        static Cfg cfgs[256];
         static int ncfg = 0;
         Cfg *cf = nullptr;
         for (int q = 0; q < ncfg; ++q)
-            if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem) cf = &cfgs[q];
+            if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem && cfgs[q].dev == dev_now) cf = &cfgs[q];
         if (!cf) {
-            if (smem > 48 * 1024)
-                GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            // opt in to the planner's upper bound once per variant (the attribute is per function, not per launch:
+            // setting it to this matrix' size would break a later launch for a matrix with larger tiles)
+            bool seen = false;
+            for (int q = 0; q < ncfg; ++q) seen = seen || (cfgs[q].fn == (const void *)kern && cfgs[q].dev == dev_now);
+            if (!seen)
+                GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             int o = 0;
             GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
-            if (ncfg == 64) ncfg = 0;
+            if (ncfg == 256) ncfg = 0; // (entries overwritten after a wrap-around just get their attribute set again)
             cf = &cfgs[ncfg++];
             cf->fn = (const void *)kern;
             cf->smem = smem;
+            cf->dev = dev_now;
             cf->occ = o < 1 ? 1 : o;
         }
         int per_sm = cf->occ;
