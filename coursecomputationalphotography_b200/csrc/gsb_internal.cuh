@@ -44,7 +44,8 @@ int gsb_ensure_device(); // GSB_OK or GSB_ERR_NO_DEVICE
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
-    int64_t n = 0;
+    int64_t n = 0;   // elements requested by the last alloc()
+    int64_t cap = 0; // elements actually allocated (>= n)
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -53,10 +54,18 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        cap = 0;
     }
+    // Contents are undefined after alloc().  An existing allocation is kept when it is large enough and not more
+    // than twice what is asked for: re-importing / re-analysing a matrix of the same shape into the same handle
+    // then costs no cudaFree + cudaMalloc of GB-sized buffers (each of which synchronises the device).
     int alloc(int64_t count) {
-        release();
         if (count <= 0) count = 1;
+        if (p && cap >= count && cap <= 2 * count + 4096) {
+            n = count;
+            return GSB_OK;
+        }
+        release();
         cudaError_t e = cudaMalloc((void **)&p, sizeof(T) * (size_t)count);
         if (e != cudaSuccess) {
             p = nullptr;
@@ -66,11 +75,13 @@ struct DevBuf {
             return GSB_ERR_ALLOC;
         }
         n = count;
+        cap = count;
         return GSB_OK;
     }
     void swap(DevBuf &o) {
         T *tp = p; p = o.p; o.p = tp;
         int64_t tn = n; n = o.n; o.n = tn;
+        int64_t tc = cap; cap = o.cap; o.cap = tc;
     }
 };
 
@@ -134,6 +145,7 @@ struct gsb_matrix {
     // solver workspaces (lazily sized for nrhs)
     DevBuf<double> xw, bw; // permuted x and b, nrhs * n_rows
     int ws_nrhs = 0;
+    DevBuf<double> stage_b, stage_x; // natural-order device copies of host b / x for the host-pointer entry points
     DevBuf<double> partials;   // per-block partial sums of the stop rule
     DevBuf<unsigned char> ctl; // GsCtl
     void *ctl_host = nullptr;  // pinned mirror

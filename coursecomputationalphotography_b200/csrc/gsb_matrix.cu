@@ -13,30 +13,22 @@
 
 #define MAX_COLORS 64
 
+// Invalidates the solver format.  The device buffers stay with the handle (DevBuf::alloc reuses them when the next
+// analysis needs the same sizes): a caller that re-imports a matrix of the same shape -- one Poisson system per
+// image, as the reference's SolveChannel does -- pays no cudaFree / cudaMalloc of GB-sized buffers.  They are freed
+// when the handle is destroyed or a differently sized matrix arrives.
 void gsb_matrix::drop_analysis() {
     analyzed = false;
     n_colors = 0;
     ordering_used = 0;
     grid_width = 0;
-    perm.release();
-    iperm.release();
-    colors.release();
-    rp.release();
-    ci.release();
-    va.release();
-    dg.release();
-    tiles.release();
-    xw.release();
-    bw.release();
     ws_nrhs = 0;
     if (graph_exec) {
         cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
         graph_exec = nullptr;
     }
     memset(graph_key, 0, sizeof(graph_key));
-    delete plan;
-    plan = nullptr;
-    partials.release();
+    if (plan) plan->valid = false; // (its tile tables are rebuilt, into the same allocations, by gsb_plan_build)
 }
 
 // ---------------------------------------------------------------------------------------------

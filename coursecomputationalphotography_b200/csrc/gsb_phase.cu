@@ -1127,8 +1127,15 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         int per_sm = cf->occ;
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         // halo variant: n_halo_tiles one-tile CTAs first, then the persistent ring over the interior tiles
+        // (the halo CTAs start first and occupy resident slots: the ring gets the remaining slots, so that every
+        // ring CTA is resident from the start -- a ring CTA that had to wait for a halo CTA to retire would finish its
+        // statically assigned tiles that much later and stretch the phase)
         const int ring_tiles = halo.enabled ? halo.n_interior : nb;
         int grid = gsb_sm_count() * per_sm;
+        if (halo.enabled) {
+            const int floor_grid = gsb_sm_count(); // many halo tiles: still at least one ring CTA per SM
+            grid = grid - halo.n_halo_tiles > floor_grid ? grid - halo.n_halo_tiles : floor_grid;
+        }
         if (grid > ring_tiles) grid = ring_tiles;
         if (halo.enabled) grid += halo.n_halo_tiles;
         if (grid > GS_RING_SLOTS_MAX) {

@@ -290,7 +290,8 @@ static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, d
     GSB_TRY(gs_check_args(m, b, nrhs, x_out));
     cudaStream_t st = gsb_cur_stream();
     const int64_t n = m->n_rows;
-    DevBuf<double> db, dx;
+    // device staging of the caller's host vectors: kept with the handle (repeated solves reuse it)
+    DevBuf<double> &db = m->stage_b, &dx = m->stage_x;
     GSB_TRY(db.alloc(n * nrhs));
     GSB_TRY(dx.alloc(n * nrhs));
     size_t bytes = sizeof(double) * (size_t)(n * nrhs);
