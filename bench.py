@@ -184,7 +184,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "gauss_seidel_throughput", "value": val, "unit": "Gnnz/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, args.channels),
                    "sweeps_per_step": sweeps, "nnz": nnz},
         "cpu_baseline": {"value": val, "unit": "Gnnz/s", "cores": cores, "kind": kind,
@@ -276,7 +276,10 @@ def run_ours(args):
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("gs_phase_bytes_per_launch")
+            # measured for the default shape only (4096^2, 3 or 1 right-hand sides, stop rule every sweep)
+            if W == 4096 and H == 4096 and args.check_every == 1 and ch in (1, 3):
+                roofline["traffic"] = json.load(open(tr)).get("gs_phase_bytes_per_launch" if ch == 3
+                                                              else "gs_phase_k1_bytes_per_launch")
         except Exception:
             pass
 
