@@ -38,6 +38,18 @@ class GsStats(C.Structure):
                 ("solve_ms", C.c_double), ("setup_ms", C.c_double)]
 
 
+class GdfOptions(C.Structure):
+    _fields_ = [("solver", C.c_int), ("max_iteration", C.c_int), ("epsilon", C.c_double), ("gs", GsOptions),
+                ("reserved", C.c_int * 4)]
+
+
+class GdfStats(C.Structure):
+    _fields_ = [("iterations", C.c_int * 4), ("last_eps", C.c_double * 4), ("residual_l2", C.c_double * 4),
+                ("solve_ms", C.c_double), ("total_ms", C.c_double)]
+
+
+GDF_GS, GDF_CG = 0, 1
+
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _ip, _i64p, _dp = C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_double)
 
@@ -83,6 +95,12 @@ SIGNATURES = {
     "gsb_poisson_rhs_rows_dev": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "gsb_writeback_u8": [_vp, _i64, _vp],
     "gsb_writeback_u8_dev": [_vp, _i64, _vp],
+    "gsb_gdf_default_options": [C.POINTER(GdfOptions)],
+    "gsb_gdf_gradients": [_vp, _i, _vp, _i, _i, _vp, _vp],
+    "gsb_gdf_composite": [_vp, _i, _vp, _i, _i, _vp],
+    "gsb_gdf_solve": [_i, _i, _vp, _vp, _vp, _vp, C.POINTER(GdfOptions), _vp, C.POINTER(GdfStats)],
+    "gsb_gdf_fuse": [_vp, _i, _vp, _i, _i, _i, C.POINTER(GdfOptions), _vp, C.POINTER(GdfStats)],
+    "gsb_gdf_release": [],
     "gsb_dist_unique_id": [_vp],
     "gsb_dist_init": [C.POINTER(_vp), _vp, _i, _i, _i],
     "gsb_dist_finalize": [_vp],
@@ -93,7 +111,8 @@ SIGNATURES = {
     "gsb_host_alloc": [C.POINTER(_vp), _i64],
     "gsb_host_free": [_vp],
 }
-_RESTYPE = {"gsb_last_error": C.c_char_p, "gsb_stream": C.c_void_p}
+_RESTYPE = {"gsb_last_error": C.c_char_p, "gsb_stream": C.c_void_p, "gsb_gs_default_options": None,
+            "gsb_gdf_default_options": None}
 
 _lib = None
 

@@ -78,9 +78,9 @@ static int cg_common_check(gsb_matrix *m, const double *b, double *x) {
     return gsb_set_device(m->device);
 }
 
-extern "C" int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
-                                      const double *x0, double *x_out, int *iters) {
-    GSB_TRY(cg_common_check(m, b, x_out));
+// device-pointer core of conjugateGradient (v2 :396-434): b_dev, x_dev natural order; x0_dev may be null (zero start)
+int gsb_cg_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_dev, double epsilon, int max_iteration,
+                        double *x_dev, int *iters) {
     CgWork w;
     w.st = gsb_cur_stream();
     w.n = m->n_rows;
@@ -88,20 +88,18 @@ extern "C" int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double eps
     GSB_TRY(w.scal.alloc(1));
     const int64_t n = w.n;
     const size_t bytes = sizeof(double) * (size_t)n;
-    DevBuf<double> db, x, r, r1, p, Ap;
-    GSB_TRY(db.alloc(n));
+    DevBuf<double> x, r, r1, p, Ap;
     GSB_TRY(x.alloc(n));
     GSB_TRY(r.alloc(n));
     GSB_TRY(r1.alloc(n));
     GSB_TRY(p.alloc(n));
     GSB_TRY(Ap.alloc(n));
-    GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, w.st));
-    if (x0)
-        GSB_CUDA(cudaMemcpyAsync(x.p, x0, bytes, cudaMemcpyHostToDevice, w.st));
+    if (x0_dev)
+        GSB_CUDA(cudaMemcpyAsync(x.p, x0_dev, bytes, cudaMemcpyDeviceToDevice, w.st));
     else
         GSB_CUDA(cudaMemsetAsync(x.p, 0, bytes, w.st));
     GSB_TRY(gsb_spmv_dev(m, x.p, r.p)); // r0 = b - A x   (:405-407)
-    cg_sub<<<w.nb, 256, 0, w.st>>>(db.p, r.p, n, r.p);
+    cg_sub<<<w.nb, 256, 0, w.st>>>(b_dev, r.p, n, r.p);
     GSB_KERNEL_CHECK();
     GSB_CUDA(cudaMemcpyAsync(p.p, r.p, bytes, cudaMemcpyDeviceToDevice, w.st));
     int cnt = 0;
@@ -121,8 +119,25 @@ extern "C" int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double eps
         ++cnt;
     }
     if (iters) *iters = cnt;
-    GSB_CUDA(cudaMemcpyAsync(x_out, x.p, bytes, cudaMemcpyDeviceToHost, w.st));
+    GSB_CUDA(cudaMemcpyAsync(x_dev, x.p, bytes, cudaMemcpyDeviceToDevice, w.st));
     GSB_CUDA(cudaStreamSynchronize(w.st));
+    return GSB_OK;
+}
+
+extern "C" int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
+                                      const double *x0, double *x_out, int *iters) {
+    GSB_TRY(cg_common_check(m, b, x_out));
+    cudaStream_t st = gsb_cur_stream();
+    const int64_t n = m->n_rows;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    DevBuf<double> db, dx;
+    GSB_TRY(db.alloc(n));
+    GSB_TRY(dx.alloc(n));
+    GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    if (x0) GSB_CUDA(cudaMemcpyAsync(dx.p, x0, bytes, cudaMemcpyHostToDevice, st));
+    GSB_TRY(gsb_cg_solve_device(m, db.p, x0 ? dx.p : nullptr, epsilon, max_iteration, dx.p, iters));
+    GSB_CUDA(cudaMemcpyAsync(x_out, dx.p, bytes, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
     return GSB_OK;
 }
 

@@ -255,6 +255,12 @@ struct GsbEpsExchange {
 int gsb_launch_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials, int nrhs, const GsbEpsExchange *ex,
                               cudaStream_t st);
 
+// device-pointer solver cores shared with the gradient-domain-fusion driver (gsb_gdf.cu)
+int gsb_gs_solve_device_x0(gsb_matrix *m, const double *b_dev, const double *x0_dev, int nrhs, double epsilon,
+                           int max_iteration, const gsb_gs_options *opts, double *x_dev, gsb_gs_stats *stats);
+int gsb_cg_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_dev, double epsilon, int max_iteration,
+                        double *x_dev, int *iters);
+
 // gsb_poisson.cu: rows [p0,p1) of the reference's Poisson matrix (global columns)
 int gsb_poisson_launch_row_len(int W, int H, int64_t p0, int64_t p1, int *len, cudaStream_t st);
 int gsb_poisson_launch_fill(int W, int H, int64_t p0, int64_t p1, const int *rp, int *ci, double *va,

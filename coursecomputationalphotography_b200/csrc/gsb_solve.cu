@@ -285,6 +285,14 @@ extern "C" int gsb_gauss_seidel_dev(gsb_matrix *m, const double *b_dev, int nrhs
     return gs_solve_device(m, b_dev, nullptr, nrhs, epsilon, max_iteration, opts, x_dev, stats);
 }
 
+// device pointers with an initial guess (x0_dev may alias x_dev, or be null for the reference's 1.0): used by the
+// gradient-domain-fusion driver (gsb_gdf.cu)
+int gsb_gs_solve_device_x0(gsb_matrix *m, const double *b_dev, const double *x0_dev, int nrhs, double epsilon,
+                           int max_iteration, const gsb_gs_options *opts, double *x_dev, gsb_gs_stats *stats) {
+    GSB_TRY(gs_check_args(m, b_dev, nrhs, x_dev));
+    return gs_solve_device(m, b_dev, x0_dev, nrhs, epsilon, max_iteration, opts, x_dev, stats);
+}
+
 static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, double epsilon, int max_iteration,
                    const gsb_gs_options *opts, double *x_out, gsb_gs_stats *stats) {
     GSB_TRY(gs_check_args(m, b, nrhs, x_out));

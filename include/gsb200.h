@@ -210,6 +210,54 @@ int gsb_writeback_u8(const double *x, int64_t n, unsigned char *out);
 int gsb_writeback_u8_dev(const double *x_dev, int64_t n, unsigned char *out_dev);
 
 /* ---------------------------------------------------------------------------------------
+ * Gradient-domain fusion driver ("next" rows N2 + N4): the callers either side of the solve,
+ * so that the whole stage -- images / gradients in, fused image out -- stays on the device.
+ *
+ * Layouts are the reference's cv::Mat layouts:
+ *   images  n_images x (H x W x 3) bytes, channel-interleaved (CV_8UC3, continuous), back to back
+ *   labels  H x W bytes: ResultLabel.at<uchar>(y, x) < n_images
+ *   gx, gy  3 planes of H x W float32 (plane c = component c of the reference's Vec3f gradient)
+ *   x / init 3 planes of H x W doubles (the reference solves one channel at a time)
+ *   out     H x W x 3 bytes, channel-interleaved
+ * ------------------------------------------------------------------------------------- */
+#define GSB_GDF_GS 0 /* gaussSeidel, the three channels fused into one pass over the matrix   */
+#define GSB_GDF_CG 1 /* conjugateGradient per channel -- what the reference's drivers call     */
+typedef struct gsb_gdf_options {
+    int solver;          /* GSB_GDF_GS (default) or GSB_GDF_CG                                        */
+    int max_iteration;   /* GS: 1000 (v2 :350); CG: the reference's `iterations` (50 with an init)    */
+    double epsilon;      /* GS: 1e-6 (v2 :350); CG: 1e-10 (PhotoMontage.cpp:613, hw8_pa.cc:972)       */
+    gsb_gs_options gs;   /* ordering / kernel / check_every of the GS path                            */
+    int reserved[4];
+} gsb_gdf_options;
+typedef struct gsb_gdf_stats {
+    int iterations[4];     /* GS: sweeps (same for all channels); CG: loop count per channel          */
+    double last_eps[4];    /* GS: L1 norm of the last evaluated sweep update per channel              */
+    double residual_l2[4]; /* ||A^T b - A^T A x||_2 per channel at exit                               */
+    double solve_ms;       /* device time of the solver loop(s)                                       */
+    double total_ms;       /* wall time of the call                                                   */
+} gsb_gdf_stats;
+void gsb_gdf_default_options(gsb_gdf_options *o);
+/* N2  GradientAt of the labelled source image   PhotoMontage.cpp:399-408, :419-425
+ * (last row / column, which the reference never reads, are written as 0) */
+int gsb_gdf_gradients(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                      float *gx, float *gy);
+/* N4  fast_init_value: init = the composite   PhotoMontage.cpp:599-610 */
+int gsb_gdf_composite(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                      double *x0);
+/* SolveChannel for the three channels with the gradients given (hw8_pa.cc:902-986, called at :808-810;
+ * PhotoMontage.cpp:535-628): A^T b from gx / gy / constraint[3], the Poisson matrix built on the device (kept
+ * and reused by later calls of the same size), solve, clamp and interleave.  init = 3*W*H doubles or NULL
+ * (GS: the reference's 1.0; CG: zero).  An initial guess for GS is an extension of the reference API. */
+int gsb_gdf_solve(int W, int H, const float *gx, const float *gy, const double *constraint, const double *init,
+                  const gsb_gdf_options *opts, unsigned char *out, gsb_gdf_stats *stats);
+/* BuildSolveGradientFusion (PhotoMontage.cpp:410-433): gradients picked by the label map, constraint =
+ * Images[0](0,0), fast_init != 0 starts from the composite (:599-610), three SolveChannel calls, result image. */
+int gsb_gdf_fuse(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                 int fast_init, const gsb_gdf_options *opts, unsigned char *out, gsb_gdf_stats *stats);
+/* drops the Poisson matrix the driver keeps between calls */
+int gsb_gdf_release(void);
+
+/* ---------------------------------------------------------------------------------------
  * Multi-GPU row strips: one rank per GPU, halo exchange per colour phase
  * ------------------------------------------------------------------------------------- */
 #define GSB_UNIQUE_ID_BYTES 128

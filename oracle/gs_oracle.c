@@ -409,3 +409,66 @@ void orc_writeback_u8(const double *x, int64_t n, unsigned char *out) {
         out[i] = (unsigned char)v;
     }
 }
+
+/* ---- gradient-domain-fusion driver ("next" rows N2 + N4) ------------------------------------------------
+ * Restated from project/src/PhotoMontage/PhotoMontage.cpp; the arithmetic is integer differences of 8-bit
+ * values stored as float, so any correct restatement is exact.  Parity unpinned against a reference RUN
+ * (the driver needs OpenCV + Eigen, absent here); tests/test_gdf_host.py checks these loops against an
+ * independent numpy formulation instead.
+ * Layouts: images n x (H x W x 3) bytes interleaved (cv::Mat CV_8UC3), labels H x W bytes,
+ * gx / gy 3 planes of H x W float, x 3 planes of H x W double, out H x W x 3 bytes interleaved. */
+
+/* GradientAt (:399-408) of Images[ResultLabel(y,x)] for y < H-1, x < W-1 (:419-425); the rest 0.
+ * Returns the number of pixels whose label is >= n_images (0 = ok). */
+int64_t orc_gdf_gradients(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                          float *gx, float *gy) {
+    const int64_t n = (int64_t)W * H;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < 3 * n; ++i) gx[i] = gy[i] = 0.0f;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int64_t p = (int64_t)y * W + x;
+            const int l = labels[p];
+            if (l >= n_images) {
+                ++bad;
+                continue;
+            }
+            if (y >= H - 1 || x >= W - 1) continue;
+            const unsigned char *img = images + (int64_t)l * n * 3;
+            for (int c = 0; c < 3; ++c) {
+                const int color1 = img[p * 3 + c];       /* Image.at<Vec3b>(y, x)     */
+                const int color2 = img[(p + 1) * 3 + c]; /* Image.at<Vec3b>(y, x + 1) */
+                const int color3 = img[(p + W) * 3 + c]; /* Image.at<Vec3b>(y + 1, x) */
+                gx[c * n + p] = (float)(color2 - color1);
+                gy[c * n + p] = (float)(color3 - color1);
+            }
+        }
+    return bad;
+}
+
+/* fast_init_value (:599-610): init[y*W+x] = Images[label(y,x)].at<Vec3b>(y,x)[channel] */
+int64_t orc_gdf_composite(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                          double *x0) {
+    const int64_t n = (int64_t)W * H;
+    int64_t bad = 0;
+    for (int64_t p = 0; p < n; ++p) {
+        const int l = labels[p];
+        if (l >= n_images) {
+            ++bad;
+            continue;
+        }
+        for (int c = 0; c < 3; ++c) x0[c * n + p] = (double)images[((int64_t)l * n + p) * 3 + c];
+    }
+    return bad;
+}
+
+/* write-back of three solved channels into the interleaved image (:617-626) */
+void orc_gdf_writeback(const double *x, int64_t n, unsigned char *out) {
+    for (int c = 0; c < 3; ++c)
+        for (int64_t p = 0; p < n; ++p) {
+            double v = x[c * n + p];
+            if (v > 255.0) v = 255.0;
+            if (!(v > 0.0)) v = 0.0;
+            out[p * 3 + c] = (unsigned char)v;
+        }
+}

@@ -73,6 +73,12 @@ void orc_poisson_csr(int W, int H, int *row_off /* W*H+1 */, int *col_idx, doubl
 void orc_poisson_rhs(int W, int H, const float *gx, const float *gy, double constraint, double *b);
 /* A10: PhotoMontage.cpp:617-626: uchar(clamp(x,0,255)), truncating */
 void orc_writeback_u8(const double *x, int64_t n, unsigned char *out);
+/* gradient-domain-fusion driver (PhotoMontage.cpp:399-425, :599-610, :617-626) */
+int64_t orc_gdf_gradients(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                          float *gx, float *gy);
+int64_t orc_gdf_composite(const unsigned char *images, int n_images, const unsigned char *labels, int W, int H,
+                          double *x0);
+void orc_gdf_writeback(const double *x, int64_t n, unsigned char *out);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,11 @@ def _oracle():
         L.orc_poisson_csr.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p]
         L.orc_poisson_rhs.argtypes = [C.c_int, C.c_int, _f32p, _f32p, C.c_double, _f64p]
         L.orc_writeback_u8.argtypes = [_f64p, C.c_int64, _u8p]
+        L.orc_gdf_gradients.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, _f32p, _f32p]
+        L.orc_gdf_gradients.restype = C.c_int64
+        L.orc_gdf_composite.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, _f64p]
+        L.orc_gdf_composite.restype = C.c_int64
+        L.orc_gdf_writeback.argtypes = [_f64p, C.c_int64, _u8p]
         _lib = L
     return _lib
 
@@ -219,6 +224,36 @@ def writeback_u8(x):
     out = np.empty(len(x), np.uint8)
     _oracle().orc_writeback_u8(x, len(x), out)
     return out
+
+
+def gdf_gradients(images, labels):
+    """PhotoMontage.cpp:399-425.  images (n, H, W, 3) uint8, labels (H, W) uint8 -> gx, gy (3, H, W) float32."""
+    images, labels = _a(images, np.uint8), _a(labels, np.uint8)
+    n, H, W, _ = images.shape
+    gx, gy = np.empty((3, H, W), np.float32), np.empty((3, H, W), np.float32)
+    bad = _oracle().orc_gdf_gradients(images.reshape(-1), n, labels.reshape(-1), W, H, gx.reshape(-1), gy.reshape(-1))
+    if bad:
+        raise ValueError("%d labels out of range" % bad)
+    return gx, gy
+
+
+def gdf_composite(images, labels):
+    """PhotoMontage.cpp:599-610 -> (3, H*W) float64"""
+    images, labels = _a(images, np.uint8), _a(labels, np.uint8)
+    n, H, W, _ = images.shape
+    x0 = np.empty((3, H * W), np.float64)
+    bad = _oracle().orc_gdf_composite(images.reshape(-1), n, labels.reshape(-1), W, H, x0.reshape(-1))
+    if bad:
+        raise ValueError("%d labels out of range" % bad)
+    return x0
+
+
+def gdf_writeback(x, H, W):
+    """PhotoMontage.cpp:617-626: (3, H*W) float64 -> (H, W, 3) uint8"""
+    x = _a(x, np.float64).reshape(-1)
+    out = np.empty(H * W * 3, np.uint8)
+    _oracle().orc_gdf_writeback(x, H * W, out)
+    return out.reshape(H, W, 3)
 
 
 # --------------------------------------------------------------------------------------
