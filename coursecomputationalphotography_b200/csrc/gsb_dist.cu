@@ -912,7 +912,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         if (!d->halo_meta || d->n_halo_tiles[0] == 0 || d->n_halo_tiles[1] == 0) cap = 0;
                         // the kernels number the interior tiles arithmetically and give every halo tile its own CTA
                         for (int c = 0; c < 2; ++c)
-                            if (d->interior_base[c] < 0 || d->n_halo_tiles[c] > 1024) cap = 0;
+                            if (d->interior_base[c] < 0 || d->n_halo_tiles[c] > GSB_HALO_TILES_MAX) cap = 0;
                     }
                     DevBuf<int> agree;
                     GSB_TRY(agree.alloc(1));

@@ -179,6 +179,12 @@ struct GsCtl {
     double eps_local[GSB_MAX_RHS]; // strip solver, ncclAllReduce path: this rank's share of eps_last
 };
 
+// Ring kernels: a colour phase writes one stop-rule partial per CTA into at most GSB_RING_SLOTS_MAX slots (the
+// end-of-sweep kernel folds all of them, so the bound is kept close to the largest grid a B200 runs: 148 SMs x 4
+// resident CTAs = 592, plus the halo CTAs of the strip solver, at most GSB_HALO_TILES_MAX per colour).
+#define GSB_RING_SLOTS_MAX 1024
+#define GSB_HALO_TILES_MAX 256
+
 // how the colour phases of one colour-major CSR are launched (gsb_phase.cu)
 struct GsbPlan {
     bool valid = false;

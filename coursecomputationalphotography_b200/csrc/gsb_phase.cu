@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 #define GS_WIN_GRANULE 64      // columns per granule (512 bytes: keeps every window 16-byte aligned)
 #define GS_WIN_CAP_MAX 2048    // doubles per right-hand side per stage
 #define GS_WIN_DESC 12         // ints per tile descriptor
-#define GS_RING_SLOTS_MAX 2048 // upper bound of the persistent grid = stop-rule partial slots per colour phase
+#define GS_RING_SLOTS_MAX GSB_RING_SLOTS_MAX // upper bound of the grid = stop-rule partial slots per colour phase
 
 struct RingLayout {
     int va_off, dg_off, b_off, xo_off, xw_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
