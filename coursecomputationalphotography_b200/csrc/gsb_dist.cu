@@ -1012,6 +1012,11 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             trace_mark(); // 4 marks per sweep: start, after phase 0, after phase 1, after the end-of-sweep step
             const bool check = (sweep_no % opts.check_every) == 0 || sweep_no == max_iteration;
             int poff = 0;
+            // opt-in (GSB_FUSED_END=1): the second colour phase ends the sweep itself -- fold, peer exchange, decision
+            // (GsbEndArgs); needs the fused stop-rule exchange on checked sweeps and both colours non-empty
+            const bool fuse_end = use_peer && fused_eps && gsb_fused_end_enabled() &&
+                                  gsb_plan_can_fuse_end(&d->plan, nrhs) && d->color_start[1] > d->color_start[0] &&
+                                  d->color_start[2] > d->color_start[1];
             for (int c = 0; c < 2 && status == GSB_OK; ++c) {
                 const int r0 = d->color_start[c], r1 = d->color_start[c + 1];
                 if (r1 > r0) {
@@ -1039,8 +1044,25 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         ha.signal_epoch = (int)(epoch_base + sidx + 1);
                         ha.counter = d->flags.p + 4 + c;
                     }
+                    GsbEndArgs ea;
+                    memset(&ea, 0, sizeof(ea));
+                    if (fuse_end && c == 1) {
+                        ea.enabled = 1;
+                        ea.checked = check ? 1 : 0;
+                        ea.n_partials = gsb_plan_partial_slots(&d->plan, 0, nrhs) + gsb_plan_partial_slots(&d->plan, 1, nrhs);
+                        ea.ctl = ctl;
+                        ea.partials = d->partials.p;
+                        if (check) {
+                            ea.exchange = 1;
+                            ea.ex.world = d->world;
+                            ea.ex.rank = d->rank;
+                            ea.ex.epoch = (int)(++d->xcount);
+                            for (int q = 0; q < d->world; ++q) ea.ex.box[q] = d->peer_box[q];
+                        }
+                    }
                     status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p, d->xw.p, ld, nrhs, check,
-                                             ctl, d->partials.p + (size_t)poff * nrhs, st, (use_peer || force_halo) ? &ha : nullptr);
+                                             ctl, d->partials.p + (size_t)poff * nrhs, st,
+                                             (use_peer || force_halo) ? &ha : nullptr, ea.enabled ? &ea : nullptr);
                     poff += gsb_plan_partial_slots(&d->plan, c, nrhs);
                     ++launches;
                 }
@@ -1048,7 +1070,9 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 trace_mark();
             }
             if (status != GSB_OK) break;
-            if (check && fused_eps) {
+            if (fuse_end) {
+                // the sweep was ended by the second colour phase
+            } else if (check && fused_eps) {
                 GsbEpsExchange ex;
                 memset(&ex, 0, sizeof(ex));
                 ex.world = d->world;

@@ -175,7 +175,7 @@ struct GsCtl {
     double epsilon;
     double eps_last[GSB_MAX_RHS];
     int error; // 1: the peer stop-rule exchange timed out (a rank is missing); the solve stops
-    int pad_;
+    int ticket; // fused end of sweep: CTAs of the sweep's last colour phase that have retired
     double eps_local[GSB_MAX_RHS]; // strip solver, ncclAllReduce path: this rank's share of eps_last
 };
 
@@ -236,11 +236,36 @@ struct GsbHaloArgs {
     int n_interior;
 };
 
+// (layout of the stop-rule exchange: see gsb_launch_end_sweep_peer below)
+#define GSB_DIST_MAX_WORLD 16
+struct GsbEpsExchange {
+    int world, rank;
+    int epoch;  // exchanges issued so far + 1 (monotonic over the lifetime of the handle); parity = epoch & 1
+    double *box[GSB_DIST_MAX_WORLD];
+};
+
+// Fused end of sweep (opt-in: GSB_FUSED_END=1; ring kernels only).  The launch of the sweep's last colour phase
+// carries these arguments; every CTA takes a ticket when it retires and the last one does what gs_end_sweep /
+// gs_end_sweep_peer would do in a kernel of their own: fold the partial slots of all colour phases, (strip
+// solver) exchange the sums with the peers, bump the sweep counter, decide.  Saves one launch and one
+// drain / fill of the GPU per sweep.  Not yet measured (written after round 1's GPU budget was spent).
+struct GsbEndArgs {
+    int enabled;
+    int checked;            // the stop rule is evaluated this sweep
+    int n_partials;         // slots of all colour phases of the sweep, this launch's included
+    int exchange;           // 1: strip solver, sums are exchanged through `ex` (GsbEpsExchange)
+    GsCtl *ctl;
+    const double *partials; // slot 0 of the sweep's first colour phase
+    GsbEpsExchange ex;
+};
+bool gsb_fused_end_enabled();                          // GSB_FUSED_END=1
+bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs); // the effective kernel is a ring kernel
+
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles
 // rp/ci/va: off-diagonal CSR in colour-major order; dg: the diagonal (0 = row skipped)
 int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
                     const double *b, double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
-                    cudaStream_t st, const GsbHaloArgs *halo = nullptr);
+                    cudaStream_t st, const GsbHaloArgs *halo = nullptr, const GsbEndArgs *end = nullptr);
 // end of sweep.  mode 0: fold partials, bump the counter, decide (single GPU)
 //                mode 1: fold partials into ctl->eps_last only (strip solver, before the all-reduce)
 //                mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
@@ -252,12 +277,6 @@ int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int
 // rank's box (NVLink peer stores) and raises that slot's flag (release, system scope) to `epoch`; it then waits for
 // all `world` flags of its own box, adds the slots in rank order (identical on every rank -> identical decision),
 // bumps the sweep counter and decides.  One launch replaces fold + ncclAllReduce + decide.
-#define GSB_DIST_MAX_WORLD 16
-struct GsbEpsExchange {
-    int world, rank;
-    int epoch;  // exchanges issued so far + 1 (monotonic over the lifetime of the handle); parity = epoch & 1
-    double *box[GSB_DIST_MAX_WORLD];
-};
 int gsb_launch_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials, int nrhs, const GsbEpsExchange *ex,
                               cudaStream_t st);
 

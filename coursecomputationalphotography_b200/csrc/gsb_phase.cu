@@ -271,6 +271,103 @@ __device__ __noinline__ void halo_tile_done(int *counter, int n_halo_tiles, int 
     if (flag1) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag1), "r"(epoch) : "memory");
 }
 
+// Fused end of sweep (GsbEndArgs): run by the last CTA of the sweep's last colour phase to retire, all GS_THREADS
+// threads.  Same steps as gs_end_sweep (mode 0) / gs_end_sweep_peer, folded by 256 threads instead of 1024 (the
+// stop norm therefore agrees with the separate kernels to rounding, not bit for bit; the fold order is fixed).
+// Out of line: it runs once per sweep and must not weigh on the tile loop's register allocation.
+template <int NRHS>
+__device__ __noinline__ void ring_end_of_sweep(GsCtl *ctl, const double *partials, int n_partials, int checked,
+                                               int exchange, const GsbEpsExchange ex) {
+    __shared__ double ws[NRHS][GS_THREADS / 32];
+    __shared__ double tot[NRHS];
+    __shared__ double all[GSB_DIST_MAX_WORLD][NRHS];
+    __shared__ int timed_out;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (!checked) {
+        if (tid == 0) {
+            const int cnt = ctl->sweeps + 1;
+            ctl->sweeps = cnt;
+            if (cnt >= ctl->max_iter) ctl->done = 1;
+        }
+        return;
+    }
+    double s[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+    for (int i = tid; i < n_partials; i += GS_THREADS) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] += __ldcg(partials + (size_t)i * NRHS + r); // L2: written by other CTAs
+    }
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+        double t = s[r];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+        if (lane == 0) ws[r][wid] = t;
+    }
+    if (tid == 0) timed_out = 0;
+    __syncthreads();
+    if (tid < NRHS) {
+        double t = 0.0;
+        for (int w = 0; w < GS_THREADS / 32; ++w) t += ws[tid][w];
+        tot[tid] = t;
+    }
+    __syncthreads();
+    if (exchange) { // strip solver: the same protocol as gs_end_sweep_peer
+        const int par = ex.epoch & 1;
+        const size_t flag_off = (size_t)2 * ex.world * GSB_MAX_RHS; // in doubles
+        if (tid < ex.world) {
+            const int q = tid;
+            double *dst = ex.box[q] + (size_t)(par * ex.world + ex.rank) * GSB_MAX_RHS;
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+                asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + r), "d"(tot[r]) : "memory");
+            int *flag = reinterpret_cast<int *>(ex.box[q] + flag_off) + par * ex.world + ex.rank;
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(ex.epoch) : "memory");
+        }
+        if (tid < ex.world) {
+            const int q = tid;
+            const int *flag = reinterpret_cast<const int *>(ex.box[ex.rank] + flag_off) + par * ex.world + q;
+            int v = 0;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (v >= ex.epoch) break;
+                if (++spins > (1ll << 25)) { // ~10 s: a rank is missing
+                    timed_out = 1;
+                    break;
+                }
+                __nanosleep(spins < 64 ? 20 : 200);
+            }
+            const double *src = ex.box[ex.rank] + (size_t)(par * ex.world + q) * GSB_MAX_RHS;
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                double t;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t) : "l"(src + r) : "memory");
+                all[q][r] = t;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        bool all_ok = true;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            double t = tot[r];
+            if (exchange) {
+                t = 0.0;
+                for (int q = 0; q < ex.world; ++q) t += all[q][r];
+            }
+            ctl->eps_last[r] = t;
+            if (t > ctl->epsilon) all_ok = false; // v2 :356
+        }
+        const int cnt = ctl->sweeps + 1;
+        ctl->sweeps = cnt;
+        if (timed_out) ctl->error = 1;
+        if (all_ok || cnt >= ctl->max_iter || timed_out) ctl->done = 1;
+    }
+}
+
 // resident CTAs per SM the register allocation must allow: 4 wherever shared memory lets 4 stages-pairs fit
 // (k = 3 with windows is limited to 2-3 by its 49 KB stages)
 //
@@ -280,13 +377,14 @@ __device__ __noinline__ void halo_tile_done(int *counter, int n_halo_tiles, int 
 // completion count.  The other CTAs run the ring over the interior tiles [interior_base, interior_base + n_interior),
 // numbered arithmetically, so the interior path is instruction-for-instruction the single-GPU kernel (a table
 // look-up per tile, or halo code in the tile body, costs 8-13 % -- measured, profiles/README.md).
-template <int NRHS, bool CHECK, int STAGES, bool WIN, bool HALO>
+template <int NRHS, bool CHECK, int STAGES, bool WIN, bool HALO, bool FEND>
 __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     gs_phase_ring(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                   const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0_in,
                   int row1_in, int ntiles_in,
                   const int *__restrict__ tile_k_in, const int *__restrict__ tile_win_in, int cap, int wcap,
-                  const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo) {
+                  const GsCtl *__restrict__ ctl, double *__restrict__ partials, const GsbHaloArgs halo,
+                  const GsbEndArgs end) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RingLayout L = ring_layout(cap, NRHS, CHECK, WIN ? wcap : 0);
     // kernel 3 with window descriptors: the x spans a tile will gather from can be pulled into L2 when the tile's
@@ -532,6 +630,23 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         const int nslots = min(ntiles_in, GS_RING_SLOTS_MAX);
         for (int t2 = blockIdx.x + gridDim.x; t2 < nslots; t2 += gridDim.x)
             if (tid < NRHS) partials[(size_t)t2 * NRHS + tid] = 0.0;
+    }
+    if (FEND && end.enabled) {
+        // fused end of sweep (its own instantiation: the tail's call and by-value arguments change the register
+        // allocation of the tile loop, so the default path is compiled without it): this CTA's partials are visible device-wide before it takes its ticket; the CTA that
+        // draws the last ticket sees every other CTA's partials (fence + atomic on both sides) and ends the sweep
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            s_last = atomicAdd(&end.ctl->ticket, 1) == (int)gridDim.x - 1;
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_last) {
+            if (tid == 0) end.ctl->ticket = 0;
+            ring_end_of_sweep<NRHS>(end.ctl, end.partials, end.n_partials, end.checked, end.exchange, end.ex);
+        }
     }
 }
 
@@ -923,6 +1038,21 @@ int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
     return nrhs >= 2 ? 3 : 4;
 }
 
+bool gsb_fused_end_enabled() {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("GSB_FUSED_END");
+        env = e ? atoi(e) : 0; // opt-in until it has been measured
+    }
+    return env == 1;
+}
+bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs) {
+    const int eff = gsb_plan_effective_kernel(p, nrhs);
+    const char *e = getenv("GSB_RING_STAGES"); // fused-end variants are built for the default stage count only
+    if (e && atoi(e) != 0 && atoi(e) != GS_RING_STAGES_DEFAULT) return false;
+    return eff == 3 || eff == 4;
+}
+
 // stop-rule partial slots colour phase c writes (and gs_end_sweep folds) for `nrhs` right-hand sides
 int gsb_plan_partial_slots(const GsbPlan *p, int c, int nrhs) {
     const int eff = gsb_plan_effective_kernel(p, nrhs);
@@ -1048,10 +1178,17 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
 template <int NRHS>
 static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
                          const double *b, double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials,
-                         cudaStream_t st, const GsbHaloArgs *halo_in) {
+                         cudaStream_t st, const GsbHaloArgs *halo_in, const GsbEndArgs *end_in) {
     GsbHaloArgs halo;
     memset(&halo, 0, sizeof(halo));
     if (halo_in) halo = *halo_in;
+    GsbEndArgs end;
+    memset(&end, 0, sizeof(end));
+    if (end_in) end = *end_in;
+    if (end.enabled && !gsb_plan_can_fuse_end(p, NRHS)) {
+        gsb_set_error("fused end of sweep needs the ring kernels (3/4)");
+        return GSB_ERR_ARG;
+    }
     if (halo.enabled && p->kernel != 3 && p->kernel != 4) {
         gsb_set_error("fused halo exchange needs the ring kernels (3/4)");
         return GSB_ERR_ARG;
@@ -1075,6 +1212,7 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         if (stages < 2) stages = 2;
         if (stages > GS_RING_STAGES_MAX) stages = GS_RING_STAGES_MAX;
         while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
+        if (end.enabled) stages = GS_RING_STAGES_DEFAULT;
         const int smem = 64 + stages * stage_bytes;
         const int *tk = p->tile_k.p + p->tile_off[c];
         // window descriptors: kernel 4 stages the windows; kernel 3 can use them as L2 prefetch hints (GSB_X_PREFETCH=1|2)
@@ -1088,16 +1226,19 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         const int wcap = win ? p->wcap : env_xpf; // kernel 3: the prefetch mode travels in the (unused) window capacity
         typedef void (*ring_fn)(const int *, const int *, const double *, const double *, const double *, double *,
                                 int64_t, int, int, int, const int *, const int *, int, int, const GsCtl *, double *,
-                                const GsbHaloArgs);
-#define GSB_RING_PICK(ST, WN, HL) \
-    (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN, HL> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN, HL>)
-#define GSB_RING_PICK_ST(WN, HL) \
-    (stages == 2 ? GSB_RING_PICK(2, WN, HL) : stages == 3 ? GSB_RING_PICK(3, WN, HL) : GSB_RING_PICK(4, WN, HL))
+                                const GsbHaloArgs, const GsbEndArgs);
+#define GSB_RING_PICK(ST, WN, HL, FE) \
+    (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN, HL, FE> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN, HL, FE>)
+#define GSB_RING_PICK_ST(WN, HL, FE) \
+    (stages == 2 ? GSB_RING_PICK(2, WN, HL, FE) : stages == 3 ? GSB_RING_PICK(3, WN, HL, FE) : GSB_RING_PICK(4, WN, HL, FE))
+        // the fused-end variants exist for the default stage count only (gsb_plan_can_fuse_end checks it)
+#define GSB_RING_PICK_FE(WN, HL) (end.enabled ? GSB_RING_PICK(2, WN, HL, true) : GSB_RING_PICK_ST(WN, HL, false))
         ring_fn kern = nullptr;
         if (halo.enabled)
-            kern = win ? GSB_RING_PICK_ST(true, true) : GSB_RING_PICK_ST(false, true);
+            kern = win ? GSB_RING_PICK_FE(true, true) : GSB_RING_PICK_FE(false, true);
         else
-            kern = win ? GSB_RING_PICK_ST(true, false) : GSB_RING_PICK_ST(false, false);
+            kern = win ? GSB_RING_PICK_FE(true, false) : GSB_RING_PICK_FE(false, false);
+#undef GSB_RING_PICK_FE
 #undef GSB_RING_PICK_ST
 #undef GSB_RING_PICK
         // per (variant) cache of the opt-in shared-memory size and the resident CTAs per SM
@@ -1162,7 +1303,8 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         cfg.numAttrs = pdl ? 1 : 0;
         halo.pdl_early = pdl == 1 ? 1 : 0;
         GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, (const int *)(win ? p->ci_slot.p : ci), va, dg, b, x, ld, row0, row1,
-                                    nb, tk, tw, p->cap, wcap, ctl, partials, (const GsbHaloArgs)halo));
+                                    nb, tk, tw, p->cap, wcap, ctl, partials, (const GsbHaloArgs)halo,
+                                    (const GsbEndArgs)end));
     } else if (eff == 2) {
         auto kt = gs_phase_staged<NRHS, true>;
         auto kf = gs_phase_staged<NRHS, false>;
@@ -1194,12 +1336,12 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
 
 int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
                     const double *b, double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
-                    cudaStream_t st, const GsbHaloArgs *halo) {
+                    cudaStream_t st, const GsbHaloArgs *halo, const GsbEndArgs *end) {
     switch (nrhs) {
-        case 1: return plan_launch_t<1>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
-        case 2: return plan_launch_t<2>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
-        case 3: return plan_launch_t<3>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
-        case 4: return plan_launch_t<4>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo);
+        case 1: return plan_launch_t<1>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo, end);
+        case 2: return plan_launch_t<2>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo, end);
+        case 3: return plan_launch_t<3>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo, end);
+        case 4: return plan_launch_t<4>(p, c, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, halo, end);
     }
     gsb_set_error("nrhs must be 1..%d", GSB_MAX_RHS);
     return GSB_ERR_ARG;

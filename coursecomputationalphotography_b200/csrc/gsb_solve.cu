@@ -59,17 +59,36 @@ extern "C" void gsb_gs_default_options(gsb_gs_options *o) {
 static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, cudaStream_t st, int64_t *launches) {
     GsCtl *ctl = (GsCtl *)m->ctl.p;
     const int64_t n = gsb_padded_ld(m->n_rows);
+    // opt-in (GSB_FUSED_END=1): the last non-empty colour phase ends the sweep itself (GsbEndArgs)
+    int carrier = -1, total = 0;
+    for (int c = 0; c < m->n_colors; ++c)
+        if (m->plan->blocks[c] > 0) {
+            carrier = c;
+            total += gsb_plan_partial_slots(m->plan, c, nrhs);
+        }
+    const bool fuse = carrier >= 0 && gsb_fused_end_enabled() && gsb_plan_can_fuse_end(m->plan, nrhs);
     int poff = 0;
     for (int c = 0; c < m->n_colors; ++c) {
         const int nb = m->plan->blocks[c];
         if (nb == 0) continue;
+        GsbEndArgs ea;
+        memset(&ea, 0, sizeof(ea));
+        if (fuse && c == carrier) {
+            ea.enabled = 1;
+            ea.checked = check ? 1 : 0;
+            ea.n_partials = total;
+            ea.ctl = ctl;
+            ea.partials = m->partials.p;
+        }
         GSB_TRY(gsb_plan_launch(m->plan, c, m->rp.p, m->ci.p, m->va.p, m->dg.p, m->bw.p, m->xw.p, n, nrhs, check, ctl,
-                                m->partials.p + (size_t)poff * nrhs, st));
+                                m->partials.p + (size_t)poff * nrhs, st, nullptr, ea.enabled ? &ea : nullptr));
         poff += gsb_plan_partial_slots(m->plan, c, nrhs);
         ++*launches;
     }
-    GSB_TRY(gsb_launch_end_sweep(ctl, m->partials.p, poff, nrhs, check ? 1 : 0, 0, st));
-    ++*launches;
+    if (!fuse) {
+        GSB_TRY(gsb_launch_end_sweep(ctl, m->partials.p, poff, nrhs, check ? 1 : 0, 0, st));
+        ++*launches;
+    }
     return GSB_OK;
 }
 
