@@ -128,7 +128,8 @@ def blob_mask(W, H, coverage=0.30, max_thickness=48, seed=11):
     target = coverage * W * H
     r_max = max(2, max_thickness // 2)
     guard = 0
-    while mask.sum() < target and guard < 200000:
+    covered = 0  # == mask.sum(), kept incrementally (a full count per ellipse is minutes at 4096^2)
+    while covered < target and guard < 200000:
         guard += 1
         ry, rx = rng.integers(max(2, r_max // 3), r_max + 1, 2)
         if H - 2 * ry - 2 <= 1 or W - 2 * rx - 2 <= 1:
@@ -137,7 +138,9 @@ def blob_mask(W, H, coverage=0.30, max_thickness=48, seed=11):
         cx = rng.integers(rx + 1, W - rx - 1)
         yy, xx = np.ogrid[-ry:ry + 1, -rx:rx + 1]
         e = (yy / ry) ** 2 + (xx / rx) ** 2 <= 1.0
-        mask[cy - ry:cy + ry + 1, cx - rx:cx + rx + 1] |= e
+        win = mask[cy - ry:cy + ry + 1, cx - rx:cx + rx + 1]
+        covered += int((e & ~win).sum())
+        win |= e
     mask[0, :] = mask[-1, :] = False
     mask[:, 0] = mask[:, -1] = False
     return mask
