@@ -99,6 +99,17 @@ for sfx in ("i32", "f64"):
     ref = pyoracle.Ref(2, sfx).init_from_vector(rows, colz, valz)
     out["zeros_" + sfx] = {"rows": rows, "cols": colz, "vals": valz, "layout": lay(ref)}
 
+# --- Dirichlet-masked blend (small): the reference's converged Gauss-Seidel solution ---------------
+W = H = 40
+mask = wl.blob_mask(W, H, 0.30, 12, seed=11)
+guide, target = wl.synth_image(W, H, 3, seed=7), wl.synth_image(W, H, 3, seed=9)
+mro, mci, mva, mb, pix, colors = wl.masked_poisson_system(mask, guide, target)
+ref = pyoracle.Ref(2, "f64").import_csr(mva, mro[:-1], mci, len(pix))
+out["masked_blend_40"] = {"W": W, "H": H, "coverage": 0.30, "thickness": 12, "mask_seed": 11, "guide_seed": 7,
+                          "target_seed": 9, "n": int(len(pix)), "nnz": int(len(mva)),
+                          "gs_default": [hx(ref.gauss_seidel(mb[c])) for c in range(3)],
+                          "gs_25": hx(ref.gauss_seidel(mb[0], 0.0, 25))}
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_golden.json")
 json.dump(out, open(path, "w"), indent=0)
 print("wrote", path, os.path.getsize(path), "bytes")

@@ -347,3 +347,33 @@ def test_dependent_launch_equals_graph_replay(gsb, W, H, nrhs):
             assert out[0][2] == out[1][2] == sweeps
             assert np.array_equal(out[0][0], out[1][0]), (k, sweeps)
             assert out[0][1] == out[1][1], (k, sweeps, out[0][1], out[1][1])
+
+
+def test_masked_blend_vs_reference_golden(gsb):
+    """The converged device solution against the golden the UNMODIFIED reference produced (no oracle involved):
+    max-abs <= 1e-4 * 255 (north-star tolerance), for the automatic ordering and for the parity colouring, one
+    right-hand side at a time and the three channels fused."""
+    import json
+    import os
+    from coursecomputationalphotography_b200 import workloads as wl
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.json")))["masked_blend_40"]
+    mask = wl.blob_mask(G["W"], G["H"], G["coverage"], G["thickness"], seed=G["mask_seed"])
+    guide = wl.synth_image(G["W"], G["H"], 3, seed=G["guide_seed"])
+    target = wl.synth_image(G["W"], G["H"], 3, seed=G["target_seed"])
+    ro, ci, va, b, pix, colors = wl.masked_poisson_system(mask, guide, target)
+    n = len(pix)
+    assert n == G["n"] and len(va) == G["nnz"]
+    gold = np.array([[float.fromhex(v) for v in G["gs_default"][c]] for c in range(3)])
+    tol = 1e-4 * 255.0
+    for order in ("auto", "user"):
+        sp = gsb.SparseMatrix(np.float64)
+        sp.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
+        if order == "user":
+            sp.analyze(gsb._lib.ORDER_USER, colors)
+        x3 = sp.gaussSeidel(b)  # reference defaults, three channels fused
+        assert sp.last_stats.sweeps < 1000 and max(list(sp.last_stats.last_eps)[:3]) <= 1e-6
+        assert np.abs(x3 - gold).max() <= tol, (order, np.abs(x3 - gold).max())
+        x1 = sp.gaussSeidel(b[1])
+        assert np.abs(x1 - gold[1]).max() <= tol
+        print("masked 40x40 (%s): max-abs vs reference %.3e, %d sweeps, ||r|| %.3e" %
+              (order, np.abs(x3 - gold).max(), sp.last_stats.sweeps, sp.residual(b[1], x1)))
