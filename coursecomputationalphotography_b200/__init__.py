@@ -4,10 +4,10 @@
 libgsb200.so (include/gsb200.h).  There is no CPU implementation in this package: without the built
 library and a CUDA device every compute call raises.
 """
-from . import _lib, gdf
+from . import _lib, gdf, pano
 from ._lib import GsbError, GsOptions, GsStats, load
 from .sparse_matrix import (SparseMatrix, dotProd, manhattonDist, poisson_rhs, vecadd, vecmul, vecsub, veclen2,
                             writeback_u8)
 
 __all__ = ["SparseMatrix", "manhattonDist", "dotProd", "veclen2", "vecadd", "vecsub", "vecmul", "poisson_rhs",
-           "writeback_u8", "GsbError", "GsOptions", "GsStats", "load", "_lib", "gdf"]
+           "writeback_u8", "GsbError", "GsOptions", "GsStats", "load", "_lib", "gdf", "pano"]

@@ -101,6 +101,13 @@ SIGNATURES = {
     "gsb_gdf_solve": [_i, _i, _vp, _vp, _vp, _vp, C.POINTER(GdfOptions), _vp, C.POINTER(GdfStats)],
     "gsb_gdf_fuse": [_vp, _i, _vp, _i, _i, _i, C.POINTER(GdfOptions), _vp, C.POINTER(GdfStats)],
     "gsb_gdf_release": [],
+    "gsb_pano_mask_image": [_vp, _vp, _i, _i, _vp],
+    "gsb_pano_gradients": [_vp, _i, _i, _vp, _vp],
+    "gsb_pano_merge2_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i],
+    "gsb_pano_merge_u8": [_vp, _vp, _vp, _vp, _i, _d, _i, _i],
+    "gsb_pano_enforce_gradient_bound": [_vp, _vp, _vp, _vp, _i, _i],
+    "gsb_pano_merge_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i],
+    "gsb_pano_split_planes_f32": [_vp, _i, _i, _vp],
     "gsb_dist_unique_id": [_vp],
     "gsb_dist_init": [C.POINTER(_vp), _vp, _i, _i, _i],
     "gsb_dist_finalize": [_vp],

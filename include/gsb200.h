@@ -258,6 +258,34 @@ int gsb_gdf_fuse(const unsigned char *images, int n_images, const unsigned char 
 int gsb_gdf_release(void);
 
 /* ---------------------------------------------------------------------------------------
+ * lab8 panorama: producers of the right-hand side ("next" row N3), labs/lab8/src/OpenCVHW1/hw8_pa.cc.
+ * All buffers are continuous cv::Mat layouts: images H x W x 3 bytes, gradients H x W x 3 float32
+ * (CV_32FC3), masks H x W bytes.  The warps / erosions between these steps are OpenCV calls and stay
+ * with the caller.  The merge functions are the reference's per-row scans (skip to the source mask,
+ * skip what the target already covers, copy the rest of the run).
+ * ------------------------------------------------------------------------------------- */
+/* MaskImage :443-466 */
+int gsb_pano_mask_image(const unsigned char *src, const unsigned char *mask, int W, int H, unsigned char *out);
+/* struct Gradients(m) :604-636 -- GradientAt :314-323 for y < H-1, x < W-1 (0 elsewhere) */
+int gsb_pano_gradients(const unsigned char *img, int W, int H, float *gx, float *gy);
+/* MergeImage2<float>(target, src, target_mask, src_outer_mask, src_inner_mask) :338-385; target in place */
+int gsb_pano_merge2_f32(float *target, const float *src, const unsigned char *target_mask,
+                        const unsigned char *src_outer_mask, const unsigned char *src_inner_mask, int W, int H);
+/* MergeImage<uchar, channel>(target, src, target_mask, src_mask, SkipHowMany) :387-441; channel 3 or 1;
+ * target == target_mask is allowed (the reference's mask merge, :768) */
+int gsb_pano_merge_u8(unsigned char *target, const unsigned char *src, const unsigned char *target_mask,
+                      const unsigned char *src_mask, int channel, double skip_how_many, int W, int H);
+/* EnforceGradientBound(dx, dy, src, mask) :468-498; dx, dy in place */
+int gsb_pano_enforce_gradient_bound(float *dx, float *dy, const unsigned char *src, const unsigned char *mask,
+                                    int W, int H);
+/* one iteration of the stitch loop :740-768 after its warps: raw, dx, dy, mask updated in place from the
+ * warped source image and its two eroded masks (erode_mask = inner, erode_mask2 = outer) */
+int gsb_pano_merge_step(unsigned char *raw, float *dx, float *dy, unsigned char *mask, const unsigned char *warped,
+                        const unsigned char *erode_mask, const unsigned char *erode_mask2, int W, int H);
+/* CV_32FC3 -> three planes: the gradient layout gsb_gdf_solve / gsb_poisson_rhs take */
+int gsb_pano_split_planes_f32(const float *interleaved, int W, int H, float *planes);
+
+/* ---------------------------------------------------------------------------------------
  * Multi-GPU row strips: one rank per GPU, halo exchange per colour phase
  * ------------------------------------------------------------------------------------- */
 #define GSB_UNIQUE_ID_BYTES 128

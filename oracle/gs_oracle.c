@@ -472,3 +472,116 @@ void orc_gdf_writeback(const double *x, int64_t n, unsigned char *out) {
             out[p * 3 + c] = (unsigned char)v;
         }
 }
+
+/* ---- lab8 panorama: producers of the right-hand side ("next" row N3) ----------------------------------------
+ * Restated from labs/lab8/src/OpenCVHW1/hw8_pa.cc as the loops are written there, over flat (continuous cv::Mat)
+ * buffers.  Where the reference walks a pointer past the end of a row it reads the next row's data, as a
+ * continuous Mat does; where it would read or write outside the whole buffer (undefined behaviour upstream) the
+ * access is skipped -- those cases never change a result inside the buffer.  Parity unpinned against a reference
+ * RUN (the translation unit needs OpenCV); tests/test_pano_host.py checks these loops against the bounded,
+ * per-row formulation the device kernels use.
+ * Layouts: images H x W x 3 bytes, gradients H x W x 3 floats (CV_32FC3), masks H x W bytes. */
+
+/* MaskImage (:443-466) */
+void orc_pano_mask_image(const unsigned char *src, const unsigned char *mask, int W, int H, unsigned char *out) {
+    for (int64_t p = 0; p < (int64_t)W * H; ++p)
+        for (int c = 0; c < 3; ++c) out[p * 3 + c] = mask[p] == 0 ? 0 : src[p * 3 + c];
+}
+
+/* struct Gradients, first constructor (:604-636): GradientAt (:314-323) for y < H-1, x < W-1.  The reference
+ * leaves the last row and column of the CV_32FC3 images unset; 0 here. */
+void orc_pano_gradients(const unsigned char *img, int W, int H, float *gx, float *gy) {
+    const int64_t n = (int64_t)W * H;
+    for (int64_t i = 0; i < 3 * n; ++i) gx[i] = gy[i] = 0.0f;
+    for (int y = 0; y < H - 1; ++y)
+        for (int x = 0; x < W - 1; ++x) {
+            const int64_t p = (int64_t)y * W + x;
+            for (int c = 0; c < 3; ++c) {
+                const int color1 = img[p * 3 + c], color2 = img[(p + 1) * 3 + c], color3 = img[(p + W) * 3 + c];
+                gx[p * 3 + c] = (float)(color2 - color1);
+                gy[p * 3 + c] = (float)(color3 - color1);
+            }
+        }
+}
+
+/* MergeImage2<float> (:338-385): per row, skip to the source's outer mask, skip on while the source's inner mask
+ * is 0 and the target is already covered, then copy the rest of the outer-mask run.  `end` = H*W guards the
+ * reads the reference makes past the buffer. */
+void orc_pano_merge2_f32(float *target, const float *src, const unsigned char *target_mask,
+                         const unsigned char *src_outer_mask, const unsigned char *src_inner_mask, int W, int H) {
+    const int64_t end = (int64_t)W * H;
+    for (int i = 0; i < H; ++i) {
+        int64_t q = (int64_t)i * W; /* flat pixel index of dp / sp / tgp / sop / sip */
+        int k = 0;
+        while (k < W && src_outer_mask[q] == 0) {
+            ++q;
+            ++k;
+        }
+        while (q < end && src_inner_mask[q] == 0 && target_mask[q] != 0) { /* no bound on k upstream */
+            ++q;
+            ++k;
+        }
+        int c = 0;
+        int64_t s = q;
+        while (s < end && src_outer_mask[s] && k < W) {
+            ++s;
+            ++c;
+            ++k;
+        }
+        for (int64_t j = 0; j < (int64_t)3 * c; ++j) target[q * 3 + j] = src[q * 3 + j]; /* memcpy(dp, sp, ...) */
+    }
+}
+
+/* MergeImage<uchar, channel> (:387-441), channel = 3 (image) or 1 (mask; target and target_mask may alias) */
+void orc_pano_merge_u8(unsigned char *target, const unsigned char *src, const unsigned char *target_mask,
+                       const unsigned char *src_mask, int channel, double skip_how_many, int W, int H) {
+    const int64_t end = (int64_t)W * H;
+    for (int i = 0; i < H; ++i) {
+        int64_t q = (int64_t)i * W;  /* dp / sp / smp */
+        int64_t tq = (int64_t)i * W; /* tgp: advanced by the first loop only */
+        int k = 0;
+        while (k < W && src_mask[q] == 0) {
+            ++q;
+            ++tq;
+            ++k;
+        }
+        int c = 0;
+        if (tq < end && target_mask[tq] != 0 && skip_how_many > 0) {
+            while (c < skip_how_many) {
+                ++q;
+                ++k;
+                ++c;
+            }
+        }
+        c = 0;
+        int64_t s = q;
+        while (s < end && src_mask[s] && k < W) {
+            ++s;
+            ++c;
+            ++k;
+        }
+        for (int64_t j = 0; j < (int64_t)channel * c; ++j) target[q * channel + j] = src[q * channel + j];
+    }
+}
+
+/* EnforceGradientBound (:468-498): where the mask is set, GradientAt(src) into rows i, i-1, i+1 of dx / dy.
+ * Flat indexing as Mat::at on a continuous Mat (x + 1 == W reads the next row's first pixel); rows outside
+ * [0, H-2] would touch memory outside the buffers and are skipped. */
+void orc_pano_enforce_gradient_bound(float *dx, float *dy, const unsigned char *src, const unsigned char *mask, int W,
+                                     int H) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            if (!mask[(int64_t)i * W + j]) continue;
+            const int rows[3] = {i, i - 1, i + 1};
+            for (int t = 0; t < 3; ++t) {
+                const int r = rows[t];
+                if (r < 0 || r > H - 2) continue;
+                const int64_t p = (int64_t)r * W + j;
+                for (int c = 0; c < 3; ++c) {
+                    const int color1 = src[p * 3 + c], color2 = src[(p + 1) * 3 + c], color3 = src[(p + W) * 3 + c];
+                    dx[p * 3 + c] = (float)(color2 - color1);
+                    dy[p * 3 + c] = (float)(color3 - color1);
+                }
+            }
+        }
+}

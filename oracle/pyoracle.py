@@ -76,6 +76,14 @@ def _oracle():
         L.orc_gdf_composite.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, _f64p]
         L.orc_gdf_composite.restype = C.c_int64
         L.orc_gdf_writeback.argtypes = [_f64p, C.c_int64, _u8p]
+        L.orc_pano_mask_image.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _u8p]
+        L.orc_pano_gradients.argtypes = [_u8p, C.c_int, C.c_int, _f32p, _f32p]
+        L.orc_pano_merge2_f32.argtypes = [_f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int]
+        L.orc_pano_merge_u8.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.orc_pano_enforce_gradient_bound.argtypes = [_f32p, _f32p, _u8p, _u8p, C.c_int, C.c_int]
+        for fn in (L.orc_pano_mask_image, L.orc_pano_gradients, L.orc_pano_merge2_f32, L.orc_pano_merge_u8,
+                   L.orc_pano_enforce_gradient_bound):
+            fn.restype = None
         _lib = L
     return _lib
 
@@ -254,6 +262,61 @@ def gdf_writeback(x, H, W):
     out = np.empty(H * W * 3, np.uint8)
     _oracle().orc_gdf_writeback(x, H * W, out)
     return out.reshape(H, W, 3)
+
+
+# ---- lab8 panorama right-hand-side producers (hw8_pa.cc:338-498, :604-636); arrays in cv::Mat layouts ----------
+def pano_mask_image(src, mask):
+    src, mask = _a(src, np.uint8), _a(mask, np.uint8)
+    H, W = mask.shape
+    out = np.empty_like(src)
+    _oracle().orc_pano_mask_image(src.reshape(-1), mask.reshape(-1), W, H, out.reshape(-1))
+    return out
+
+
+def pano_gradients(img):
+    img = _a(img, np.uint8)
+    H, W, _ = img.shape
+    gx, gy = np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32)
+    _oracle().orc_pano_gradients(img.reshape(-1), W, H, gx.reshape(-1), gy.reshape(-1))
+    return gx, gy
+
+
+def pano_merge2_f32(target, src, target_mask, src_outer_mask, src_inner_mask):
+    """MergeImage2<float>: returns the updated copy of `target` (H, W, 3) float32."""
+    out = _a(target, np.float32).copy()
+    H, W, _ = out.shape
+    _oracle().orc_pano_merge2_f32(out.reshape(-1), _a(src, np.float32).reshape(-1), _a(target_mask, np.uint8).reshape(-1),
+                                  _a(src_outer_mask, np.uint8).reshape(-1), _a(src_inner_mask, np.uint8).reshape(-1),
+                                  W, H)
+    return out
+
+
+def pano_merge_u8(target, src, target_mask, src_mask, skip_how_many):
+    """MergeImage<uchar, channel>: channel = 3 for (H, W, 3) images, 1 for (H, W) masks; returns the updated copy."""
+    out = _a(target, np.uint8).copy()
+    H, W = out.shape[:2]
+    ch = 3 if out.ndim == 3 else 1
+    _oracle().orc_pano_merge_u8(out.reshape(-1), _a(src, np.uint8).reshape(-1), _a(target_mask, np.uint8).reshape(-1),
+                                _a(src_mask, np.uint8).reshape(-1), ch, float(skip_how_many), W, H)
+    return out
+
+
+def pano_merge_step(raw, dx, dy, mask, warped, erode_mask, erode_mask2):
+    """One iteration of the stitch loop, hw8_pa.cc:740-768, after its warps -> new (raw, dx, dy, mask)."""
+    gx, gy = pano_gradients(pano_mask_image(warped, erode_mask2))
+    dx = pano_merge2_f32(dx, gx, mask, erode_mask2, erode_mask)
+    dy = pano_merge2_f32(dy, gy, mask, erode_mask2, erode_mask)
+    raw = pano_merge_u8(raw, warped, mask, erode_mask, 1)
+    mask = pano_merge_u8(mask, erode_mask, mask, erode_mask, 0)
+    return raw, dx, dy, mask
+
+
+def pano_enforce_gradient_bound(dx, dy, src, mask):
+    dx, dy = _a(dx, np.float32).copy(), _a(dy, np.float32).copy()
+    H, W, _ = dx.shape
+    _oracle().orc_pano_enforce_gradient_bound(dx.reshape(-1), dy.reshape(-1), _a(src, np.uint8).reshape(-1),
+                                              _a(mask, np.uint8).reshape(-1), W, H)
+    return dx, dy
 
 
 # --------------------------------------------------------------------------------------

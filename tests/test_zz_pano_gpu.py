@@ -1,0 +1,111 @@
+"""GPU parity of the lab8 panorama right-hand-side producers (gsb_pano_* in include/gsb200.h)
+against the oracle's literal restatement of hw8_pa.cc, bit for bit, and the two-image stitch flow end to end.
+First GPU contact is the driver's round-end run (written after round 1's GPU budget was spent); the per-row /
+per-pixel bodies the kernels are made of are already held to the oracle on the CPU (tests/test_pano_host.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def row_masks(rng, H, W, style):
+    m = np.zeros((H, W), np.uint8)
+    for i in range(H):
+        kind = style if style != "mixed" else rng.choice(["run", "empty", "full", "to_end", "holes", "noise"])
+        if kind == "run":
+            a = rng.integers(0, W)
+            m[i, a:rng.integers(a, W + 1)] = 255
+        elif kind == "full":
+            m[i] = 255
+        elif kind == "to_end":
+            m[i, rng.integers(0, W):] = 255
+        elif kind == "holes":
+            m[i] = 255
+            m[i, rng.integers(0, W, max(1, W // 5))] = 0
+        elif kind == "noise":
+            m[i] = rng.integers(0, 2, W) * 255
+    return m
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (1, 9), (7, 1), (23, 31), (130, 257), (300, 200)])
+def test_primitives_bitexact(gsb, oracle_mod, H, W):
+    from coursecomputationalphotography_b200 import pano
+    rng = np.random.default_rng(H * 31 + W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    tmask, outer = row_masks(rng, H, W, "mixed"), row_masks(rng, H, W, "run")
+    inner = outer & row_masks(rng, H, W, "holes")
+    assert np.array_equal(pano.MaskImage(img, tmask), oracle_mod.pano_mask_image(img, tmask))
+    gx, gy = pano.Gradients(img)
+    ox, oy = oracle_mod.pano_gradients(img)
+    assert np.array_equal(gx, ox) and np.array_equal(gy, oy)
+    assert np.array_equal(pano.split_planes(gx), np.moveaxis(ox, 2, 0))
+    tgt = rng.standard_normal((H, W, 3)).astype(np.float32)
+    assert np.array_equal(pano.MergeImage2(tgt, gx, tmask, outer, inner),
+                          oracle_mod.pano_merge2_f32(tgt, ox, tmask, outer, inner))
+    for skip in (0, 1, 10):
+        assert np.array_equal(pano.MergeImage(img, src, tmask, outer, skip),
+                              oracle_mod.pano_merge_u8(img, src, tmask, outer, skip))
+    assert np.array_equal(pano.MergeImage(tmask, outer, tmask, outer, 0), oracle_mod.pano_merge_u8(tmask, outer, tmask, outer, 0))
+    bound = row_masks(rng, H, W, "mixed")
+    dx, dy = pano.EnforceGradientBound(gx, gy, src, bound)
+    wx, wy = oracle_mod.pano_enforce_gradient_bound(ox, oy, src, bound)
+    assert np.array_equal(dx, wx) and np.array_equal(dy, wy)
+
+
+def _erode_cross(m):
+    """3x3 cross erosion of a 0/255 mask (what cv::erode with MORPH_CROSS does away from the border)."""
+    k = m > 0
+    e = k.copy()
+    e[1:, :] &= k[:-1, :]
+    e[:-1, :] &= k[1:, :]
+    e[:, 1:] &= k[:, :-1]
+    e[:, :-1] &= k[:, 1:]
+    e[0, :] = e[-1, :] = False
+    e[:, 0] = e[:, -1] = False
+    return (e * 255).astype(np.uint8)
+
+
+def test_two_image_stitch_flow(gsb, oracle_mod):
+    """The stitch loop for two overlapping exposures of one scene (hw8_pa.cc:722-788 without the OpenCV warps):
+    first image placed, second merged by one merge_step, EnforceGradientBound on the mask's rim, then the three
+    SolveChannel calls.  Device results equal the oracle's bit for bit up to the solve; the solve equals the
+    composition of the verified solver entry points (tests/test_zz_gdf_gpu.py)."""
+    from coursecomputationalphotography_b200 import gdf, pano, workloads as wl
+    H, W = 96, 160
+    scene = np.moveaxis(wl.synth_image(W, H, 3, seed=4), 0, 2).astype(np.float64)  # (H, W, 3)
+    left = np.zeros((H, W), np.uint8)
+    left[8:H - 6, 5:100] = 255
+    right = np.zeros((H, W), np.uint8)
+    right[4:H - 10, 70:W - 4] = 255
+    im1 = np.where(left[..., None] > 0, np.clip(scene, 0, 255), 0).astype(np.uint8)
+    im2 = np.where(right[..., None] > 0, np.clip(scene * 0.8 + 20, 0, 255), 0).astype(np.uint8)
+    # first image (hw8_pa.cc:722-733)
+    raw, mask = im1.copy(), left.copy()
+    dx, dy = pano.Gradients(im1)
+    odx, ody = oracle_mod.pano_gradients(im1)
+    assert np.array_equal(dx, odx) and np.array_equal(dy, ody)
+    # second image: eroded masks as :707-716 builds them (outer = 2 erosions, inner = 4)
+    e2 = _erode_cross(_erode_cross(right))
+    e1 = _erode_cross(_erode_cross(e2))
+    got = pano.merge_step(raw, dx, dy, mask, im2, e1, e2)
+    want = oracle_mod.pano_merge_step(raw, odx, ody, mask, im2, e1, e2)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    raw, dx, dy, mask = got
+    assert mask.max() == 255 and (mask > 0).sum() > (left > 0).sum()  # the second image extended the covered area
+    rim = mask - _erode_cross(mask)  # mask - fill_erode_mask, :771-773
+    dx, dy = pano.EnforceGradientBound(dx, dy, raw, rim)
+    wx, wy = oracle_mod.pano_enforce_gradient_bound(want[1], want[2], want[0], rim)
+    assert np.array_equal(dx, wx) and np.array_equal(dy, wy)
+    # Gradient Domain Fusion (:791-810): init = raw's channels, constraint = first image's pixel (0, 0)
+    init = np.moveaxis(raw.astype(np.float64), 2, 0).reshape(3, H * W)
+    opts = gdf.gdf_options(epsilon=0.0, max_iteration=12)
+    out, st = gdf.SolveChannels(pano.split_planes(dx), pano.split_planes(dy), im1[0, 0].astype(np.float64), init, opts)
+    gxp, gyp = np.moveaxis(wx, 2, 0), np.moveaxis(wy, 2, 0)
+    b = gsb.poisson_rhs(W, H, np.ascontiguousarray(gxp), np.ascontiguousarray(gyp), im1[0, 0].astype(np.float64))
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=12, x0=init)
+    assert np.array_equal(out, oracle_mod.gdf_writeback(x, H, W))
+    assert out.shape == (H, W, 3) and list(st.iterations)[:3] == [12, 12, 12]
