@@ -633,8 +633,9 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     }
     if (FEND && end.enabled) {
         // fused end of sweep (its own instantiation: the tail's call and by-value arguments change the register
-        // allocation of the tile loop, so the default path is compiled without it): this CTA's partials are visible device-wide before it takes its ticket; the CTA that
-        // draws the last ticket sees every other CTA's partials (fence + atomic on both sides) and ends the sweep
+        // allocation of the tile loop, so the default path is compiled without it).  This CTA's partials are
+        // visible device-wide before it takes its ticket; the CTA that draws the last ticket sees every other
+        // CTA's partials (fence + atomic on both sides) and ends the sweep
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
