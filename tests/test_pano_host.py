@@ -109,3 +109,54 @@ def test_pixel_bodies_equal_the_literal_restatement(oracle_mod, host, H, W):
         hx, hy = dx.copy(), dy.copy()
         host.host_pano_enforce_gradient_bound(hx.reshape(-1), hy.reshape(-1), img.reshape(-1), bound.reshape(-1), W, H)
         assert np.array_equal(hx, wx) and np.array_equal(hy, wy)
+
+
+def _erode_cross(m):
+    k = m > 0
+    e = k.copy()
+    e[1:, :] &= k[:-1, :]
+    e[:-1, :] &= k[1:, :]
+    e[:, 1:] &= k[:, :-1]
+    e[:, :-1] &= k[:, 1:]
+    e[0, :] = e[-1, :] = False
+    e[:, 0] = e[:, -1] = False
+    return (e * 255).astype(np.uint8)
+
+
+def test_restated_stitch_flow_removes_the_seam(oracle_mod):
+    """The stage's purpose, in oracle terms: two exposures of one scene stitched by the restated merge step
+    (hw8_pa.cc:722-788 without the OpenCV warps) and fused by the reference's own solver call
+    (conjugateGradient, 50 iterations from the raw composite, hw8_pa.cc:808-810, :972) -- the exposure step at the
+    seam shrinks to the level of the image's own gradients.  Pins that the restatement does what the reference
+    does it for, not only that two of my formulations agree."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    H, W = 96, 160
+    scene = np.moveaxis(wl.synth_image(W, H, 3, seed=4), 0, 2).astype(np.float64)
+    left = np.zeros((H, W), np.uint8)
+    left[8:H - 6, 5:100] = 255
+    right = np.zeros((H, W), np.uint8)
+    right[4:H - 10, 70:W - 4] = 255
+    im1 = np.where(left[..., None] > 0, np.clip(scene, 0, 255), 0).astype(np.uint8)
+    im2 = np.where(right[..., None] > 0, np.clip(scene * 0.8 + 20, 0, 255), 0).astype(np.uint8)
+    raw, mask = im1.copy(), left.copy()
+    dx, dy = oracle_mod.pano_gradients(im1)
+    e2 = _erode_cross(_erode_cross(right))
+    e1 = _erode_cross(_erode_cross(e2))
+    raw, dx, dy, mask = oracle_mod.pano_merge_step(raw, dx, dy, mask, im2, e1, e2)
+    assert (mask > 0).sum() > (left > 0).sum()
+    dx, dy = oracle_mod.pano_enforce_gradient_bound(dx, dy, raw, mask - _erode_cross(mask))
+    ro, ci, va = oracle_mod.poisson_csr(W, H)
+    m = oracle_mod.Oracle().import_csr(va, ro[:-1], ci, W * H)
+    sol = np.empty((3, H * W))
+    for c in range(3):
+        b = oracle_mod.poisson_rhs(W, H, np.ascontiguousarray(dx[..., c]), np.ascontiguousarray(dy[..., c]),
+                                   float(im1[0, 0, c]))
+        sol[c], _ = m.cg(b, 1e-10, 50, x0=raw[..., c].astype(np.float64).ravel())
+    out = oracle_mod.gdf_writeback(sol, H, W).astype(np.float64)
+    rows = slice(20, 70)
+    r = raw.astype(np.float64)
+    jump_raw = np.abs(r[rows, 1:] - r[rows, :-1]).mean(axis=(0, 2))
+    jump_out = np.abs(out[rows, 1:] - out[rows, :-1]).mean(axis=(0, 2))
+    seam = int(np.argmax(jump_raw[60:110])) + 60
+    assert jump_raw[seam] > 2.5 * np.median(jump_raw[10:150])  # the composite has a visible exposure step ...
+    assert jump_out[seam] < 0.6 * jump_raw[seam]               # ... which the fusion takes most of the way down
