@@ -867,6 +867,42 @@ static int dist_exchange(gsb_dist *d, int c, int nrhs, cudaStream_t st, int64_t 
     return GSB_OK;
 }
 
+// arguments of the fused halo exchange for colour phase c of the sweep with index `sidx` (sweeps of this call issued
+// before it); flag epochs only ever grow: epoch_base = sweeps issued by earlier calls
+static void dist_fill_halo_args(const gsb_dist *d, int c, long long sidx, long long epoch_base, GsbHaloArgs *ha) {
+    memset(ha, 0, sizeof(*ha));
+    ha->enabled = 1;
+    ha->n_halo_tiles = d->n_halo_tiles[c];
+    ha->interior_base = d->interior_base[c];
+    ha->n_interior = d->n_interior[c];
+    ha->order = d->tile_order[c].p;
+    ha->info = d->tile_info[c].p; // (host-side bookkeeping; the kernels number the tiles arithmetically)
+    for (int p = 0; p < 2; ++p) {
+        ha->has_peer[p] = d->has_peer(p) ? 1 : 0;
+        ha->push_map[p] = d->push_map[p].p;
+        ha->peer_x[p] = d->peer_x[p];
+        ha->peer_ld[p] = d->peer_ld[p];
+        ha->peer_gs[p] = d->peer_gs[p][c];
+        // this rank is peer (1-p) in the neighbour's numbering
+        ha->peer_flag[p] = d->peer_flags[p] ? d->peer_flags[p] + ((1 - p) * 2 + c) : nullptr;
+        ha->wait_flag[p] = d->flags.p + (p * 2 + (1 - c));
+    }
+    // phase 0 reads what the neighbours' phase 1 of the previous sweep pushed (nothing before the first sweep: the
+    // ghosts were filled with the start value); phase 1 reads what their phase 0 of this sweep pushed
+    ha->wait_epoch = c == 0 ? (sidx == 0 ? 0 : (int)(epoch_base + sidx)) : (int)(epoch_base + sidx + 1);
+    ha->signal_epoch = (int)(epoch_base + sidx + 1);
+    ha->counter = d->flags.p + 4 + c;
+}
+
+// the next stop-rule exchange of this handle (GsbEpsExchange): monotonic count, every rank's box
+static void dist_fill_exchange(gsb_dist *d, GsbEpsExchange *ex) {
+    memset(ex, 0, sizeof(*ex));
+    ex->world = d->world;
+    ex->rank = d->rank;
+    ex->epoch = (int)(++d->xcount);
+    for (int q = 0; q < d->world; ++q) ex->box[q] = d->peer_box[q];
+}
+
 extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int nrhs, double epsilon,
                                          int max_iteration, const gsb_gs_options *opts_in, double *x_dev,
                                          gsb_gs_stats *stats) {
@@ -1022,28 +1058,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 if (r1 > r0) {
                     GsbHaloArgs ha;
                     memset(&ha, 0, sizeof(ha));
-                    if (use_peer || force_halo) {
-                        const long long sidx = (long long)issued + s; // sweeps of this call issued before this one
-                        ha.enabled = 1;
-                        ha.n_halo_tiles = d->n_halo_tiles[c];
-                        ha.interior_base = d->interior_base[c];
-                        ha.n_interior = d->n_interior[c];
-                        ha.order = d->tile_order[c].p;
-                        ha.info = d->tile_info[c].p; // (the kernels read the copy packed into `order`)
-                        for (int p = 0; p < 2; ++p) {
-                            ha.has_peer[p] = d->has_peer(p) ? 1 : 0;
-                            ha.push_map[p] = d->push_map[p].p;
-                            ha.peer_x[p] = d->peer_x[p];
-                            ha.peer_ld[p] = d->peer_ld[p];
-                            ha.peer_gs[p] = d->peer_gs[p][c];
-                            // this rank is peer (1-p) in the neighbour's numbering
-                            ha.peer_flag[p] = d->peer_flags[p] ? d->peer_flags[p] + ((1 - p) * 2 + c) : nullptr;
-                            ha.wait_flag[p] = d->flags.p + (p * 2 + (1 - c));
-                        }
-                        ha.wait_epoch = c == 0 ? (sidx == 0 ? 0 : (int)(epoch_base + sidx)) : (int)(epoch_base + sidx + 1);
-                        ha.signal_epoch = (int)(epoch_base + sidx + 1);
-                        ha.counter = d->flags.p + 4 + c;
-                    }
+                    if (use_peer || force_halo) dist_fill_halo_args(d, c, (long long)issued + s, epoch_base, &ha);
                     GsbEndArgs ea;
                     memset(&ea, 0, sizeof(ea));
                     if (fuse_end && c == 1) {
@@ -1054,10 +1069,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         ea.partials = d->partials.p;
                         if (check) {
                             ea.exchange = 1;
-                            ea.ex.world = d->world;
-                            ea.ex.rank = d->rank;
-                            ea.ex.epoch = (int)(++d->xcount);
-                            for (int q = 0; q < d->world; ++q) ea.ex.box[q] = d->peer_box[q];
+                            dist_fill_exchange(d, &ea.ex);
                         }
                     }
                     status = gsb_plan_launch(&d->plan, c, d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p, d->xw.p, ld, nrhs, check,
@@ -1074,11 +1086,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                 // the sweep was ended by the second colour phase
             } else if (check && fused_eps) {
                 GsbEpsExchange ex;
-                memset(&ex, 0, sizeof(ex));
-                ex.world = d->world;
-                ex.rank = d->rank;
-                ex.epoch = (int)(++d->xcount);
-                for (int q = 0; q < d->world; ++q) ex.box[q] = d->peer_box[q];
+                dist_fill_exchange(d, &ex);
                 status = gsb_launch_end_sweep_peer(ctl, d->partials.p, poff, nrhs, &ex, st);
                 ++launches;
             } else if (check && d->world == 1) {
