@@ -82,3 +82,46 @@ def test_python_mirror_host_side_insert_matches_oracle(gsb, oracle_mod):
         cc = cols[rb[i]:rb[i] + rn[i]]
         assert np.all(np.diff(cc) > 0)  # rows stay sorted (the reference's insert does not guarantee this)
     assert rb[-1] + rn[-1] + rl[-1] == len(vals)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): one JSON line with the contract's
+    keys, produced by the compiled reference when it is present, else by the restatement."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "256",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Gnnz/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_bench_gpu_arm_fails_loudly_without_a_gpu(gsb):
+    """No CPU fallback behind the GPU arm; the time-to-tolerance child reports its failure instead of raising."""
+    if gsb._lib.device_count() > 0:
+        pytest.skip("needs a machine without a GPU")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+    sys.path.insert(0, root)
+    import bench
+
+    class A:
+        size, channels, check_every = 64, 3, 1
+    out = bench.time_to_tol_child(A)
+    assert "error" in out and "NO_DEVICE" in out["error"]
