@@ -119,6 +119,34 @@ def pinned_like(pkg, a):
     return out
 
 
+def lib_sha16():
+    import hashlib
+    try:
+        return hashlib.sha256(open(os.path.join(ROOT, "coursecomputationalphotography_b200", "libgsb200.so"), "rb").read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
+def recorded_traffic(kernel_used, W, H, ch, check_every):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
+    recorded in profiles/traffic.json (one entry per kernel / shape).  It is a recorded number, not a measurement of
+    this run: `traffic_source` names the capture and `traffic_stale` says when the library has been rebuilt since."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        db = json.load(open(path))
+    except Exception:
+        return {}
+    key = "k%d_%dx%d_rhs%d_ce%d" % (kernel_used, W, H, ch, check_every)
+    ent = db.get("captures", {}).get(key)
+    if not ent:
+        return {"traffic_source": "no ncu capture recorded for %s" % key}
+    out = {"traffic": ent["dram_bytes_per_launch"], "traffic_source": ent.get("source")}
+    sha = lib_sha16()
+    if ent.get("lib_sha16") and sha and ent["lib_sha16"] != sha:
+        out["traffic_stale"] = "captured on libgsb200.so %s, this run uses %s" % (ent["lib_sha16"], sha)
+    return out
+
+
 def algorithmic_bytes_per_sweep(nnz, n, k):
     return 12.0 * nnz + 4.0 * n + 24.0 * k * n
 
@@ -268,22 +296,19 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     abytes = algorithmic_bytes_per_sweep(nnz, n, ch)
-    n_phase_launches = sweeps_done * info["n_colors"]
-    per_launch_ms = solve_ms / n_phase_launches
-    achieved = (abytes / info["n_colors"]) / (per_launch_ms * 1e-3) / 1e9
+    # dominant kernel: kernel 5 runs a whole sweep (both colours) per launch, kernels 1-4 one colour phase per launch
+    kernel_used = int(st.kernel_used)
+    launches_per_sweep = 1 if kernel_used == 5 else info["n_colors"]
+    kname = ("gs_sweep_fused<%d,%s,2> (one sweep, both colours, %d RHS)" % (ch, "true" if args.check_every == 1 else "false", ch)
+             if kernel_used == 5 else "gs_phase (one colour phase, %d RHS, kernel %d)" % (ch, kernel_used))
+    per_launch_ms = solve_ms / (sweeps_done * launches_per_sweep)
+    achieved = (abytes / launches_per_sweep) / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gs_phase (one colour phase, %d RHS)" % ch, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": abytes / info["n_colors"], "avg_launch_ms": per_launch_ms,
+                "traffic": None, "kernel": kname, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": abytes / launches_per_sweep, "avg_launch_ms": per_launch_ms,
+                "avg_launch_ms_includes": "the sweep loop's gs_end_sweep launches (library CUDA events / launches)",
                 "frac_of_8TBps_nominal": achieved / 8000.0}
-    tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
-        try:
-            # measured for the default shape only (4096^2, 3 or 1 right-hand sides, stop rule every sweep)
-            if W == 4096 and H == 4096 and args.check_every == 1 and ch in (1, 3):
-                roofline["traffic"] = json.load(open(tr)).get("gs_phase_bytes_per_launch" if ch == 3
-                                                              else "gs_phase_k1_bytes_per_launch")
-        except Exception:
-            pass
+    roofline.update(recorded_traffic(kernel_used, W, H, ch, args.check_every))
 
     # ---- e2e: reference-facing API, host buffers, copies inside the timed region -------------------
     e2e = None

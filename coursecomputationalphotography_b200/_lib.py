@@ -29,7 +29,8 @@ class GsbError(RuntimeError):
 
 class GsOptions(C.Structure):
     _fields_ = [("ordering", C.c_int), ("check_every", C.c_int), ("batch_sweeps", C.c_int), ("use_graph", C.c_int),
-                ("kernel", C.c_int), ("compute_residual", C.c_int), ("reserved", C.c_int * 2)]
+                ("kernel", C.c_int), ("compute_residual", C.c_int), ("fused_lead", C.c_int),
+                ("reserved", C.c_int * 1)]
 
 
 class GsStats(C.Structure):

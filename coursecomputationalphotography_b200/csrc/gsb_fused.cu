@@ -1,0 +1,416 @@
+// gsb_fused.cu -- kernel 5: one launch per Gauss-Seidel sweep for two-colour (red-black) systems.
+//
+// The per-colour phase kernels (gsb_phase.cu) move every byte at copy speed but run colour 0 over the whole system
+// before colour 1 starts, so nothing survives in L2 between the phases (2.3 GB per sweep at 4096^2 against 126 MB):
+// the values colour 1 gathers are read back from HBM after colour 0 wrote them, and the stop rule's x_old of a colour
+// is a second HBM read of what the other colour gathered half a sweep earlier.  DRAM traffic = algorithmic + 8k B/row.
+//
+// Here both colours run in ONE persistent kernel as a software wavefront.  The work items of a sweep are the tiles
+// of both colours in one static sequence
+//       R_0 .. R_{L-1},  B_0, R_L, B_1, R_{L+1}, ...            (R = colour 0, B = colour 1, L = lead)
+// walked round-robin by the resident CTAs (item p -> CTA p mod grid), each CTA keeping the ring of bulk-copy
+// stages of kernel 3.  A colour-1 tile B_j may run once the colour-0 tiles in dep[j] = [lo, hi] have finished:
+// those are the tiles whose new values it gathers (read after write) and the tiles that gather ITS rows' old values
+// (write after read); the plan computes the range from the column indices, and L >= max_j(hi_j - j) + 1 puts every
+// dependency earlier in the sequence, so the in-order walk cannot deadlock (all CTAs are resident: grid = SMs x
+// occupancy).  Colour-0 tiles never wait: what they read is the previous sweep's output (kernel boundary).
+// A finished colour-0 tile publishes flags[t] = sweep number with a release store; a colour-1 tile's first warp
+// polls its range with acquire loads before the tile's gathers.  With L a few hundred tiles the dependencies are
+// long finished when a tile comes up, and the reuse distance (~2L tiles, some tens of MB) sits inside L2:
+// colour 1's gathers and x_old hit L2, every x is read from HBM once and written once per sweep -- the
+// algorithmic count -- and the stop rule costs no traffic at all.
+//
+// Arithmetic is the row body of the phase kernels (gs_row_sigma, unfused, storage order): x after every sweep is
+// bit-identical to kernels 1-4 (tests/test_gs_gpu.py::test_all_kernels_agree_bitwise).
+#include "gsb_ring.cuh"
+
+#include <limits.h>
+#include <stdlib.h>
+
+struct GsbFusedArgs { // (scalar members, selected with ?: -- indexing a by-value array would put it on the stack)
+    int row0_0, row0_1, row1_0, row1_1, nt0, nt1;
+    const int *tile_k0, *tile_k1; // CSR offset at every tile boundary of the colour
+    const int2 *dep;      // per colour-1 tile: first / last colour-0 tile it waits for
+    int *flags;           // per colour-0 tile
+    int lead, nalt;       // colour 0 runs `lead` tiles ahead; `nalt` = alternating (B, R) pairs after the lead
+};
+
+// item p of the sweep's sequence -> (colour, tile)
+__device__ __forceinline__ void fused_item(const GsbFusedArgs &fa, int p, int &c, int &t) {
+    if (p < fa.lead) {
+        c = 0;
+        t = p;
+        return;
+    }
+    const int q = p - fa.lead;
+    if (q < 2 * fa.nalt) {
+        c = (q & 1) ? 0 : 1;
+        t = (q & 1) ? fa.lead + (q >> 1) : (q >> 1);
+        return;
+    }
+    const int rest = q - 2 * fa.nalt;
+    if (fa.lead + fa.nalt < fa.nt0) { // colour 1 exhausted first: the remaining colour-0 tiles
+        c = 0;
+        t = fa.lead + fa.nalt + rest;
+    } else {
+        c = 1;
+        t = fa.nalt + rest;
+    }
+}
+
+// First warp of a colour-1 tile: every colour-0 tile in [lo, hi] has published `epoch`.  Bounded: a flag that never
+// comes (it cannot, short of a device fault) raises ctl->error instead of hanging the GPU.  Out of line so that the
+// spin loop does not weigh on the tile loop's register allocation / uniform datapath (as the halo helpers).
+__device__ __noinline__ void fused_wait_tiles(const int *flags, int lo, int hi, int epoch, GsCtl *ctl) {
+    if (*(volatile int *)&ctl->error) return; // some tile already gave up: the sweep's result is void, just finish
+    for (int i = lo + (int)(threadIdx.x & 31); i <= hi; i += 32) {
+        int v, spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            if (v >= epoch) break;
+            if (++spins > (1 << 22) || ((spins & 1023) == 0 && *(volatile int *)&ctl->error)) { // ~1 s
+                ctl->error = 2;
+                return;
+            }
+            __nanosleep(spins < 32 ? 32 : 256);
+        }
+    }
+}
+__device__ __noinline__ void fused_publish_tile(int *flag, int epoch) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
+template <int NRHS, bool CHECK, int STAGES>
+__global__ void __launch_bounds__(GS_THREADS, 4)
+    gs_sweep_fused(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                   const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int cap, GsCtl *ctl,
+                   double *__restrict__ partials, const GsbFusedArgs fa) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const RingLayout L = ring_layout(cap, NRHS, CHECK, 0);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    unsigned char *stage0 = smem_raw + 64;
+    const int tid = threadIdx.x, bid = blockIdx.x, gsz = gridDim.x;
+    const int total = fa.nt0 + fa.nt1;
+
+    struct Desc {
+        int c, t, k0, k1;
+    };
+    auto load_desc = [&](int p) -> Desc { // thread 0; fetched one iteration early (hides the L2 latency of tile_k)
+        Desc d;
+        fused_item(fa, p, d.c, d.t);
+        const int *tk = d.c ? fa.tile_k1 : fa.tile_k0;
+        d.k0 = tk[d.t];
+        d.k1 = tk[d.t + 1];
+        return d;
+    };
+    auto issue = [&](const Desc &d, int s) { // thread 0: every per-tile input is one contiguous span
+        unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+        const int r_begin = (d.c ? fa.row0_1 : fa.row0_0) + d.t * GS_THREADS;
+        const int rows = min(GS_THREADS, (d.c ? fa.row1_1 : fa.row1_0) - r_begin);
+        const int k0 = d.k0, k1 = d.k1;
+        const int kv0 = k0 & ~1, kc0 = k0 & ~3;
+        const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+        const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+        const int ra = r_begin & ~3;
+        const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
+        const int ea = r_begin & ~1; // the leading dimension is even: the same alignment for every plane
+        const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
+        const uint32_t tx = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
+        reinterpret_cast<int *>(st + L.hdr_off)[0] = k0;
+        mbar_expect_tx(&full[s], tx);
+        if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
+        if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
+        bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
+        bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
+            // x_old: this tile's own rows, which nobody but this tile writes during the sweep
+            if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    }
+    __syncthreads();
+    // the previous sweep (and its end-of-sweep kernel) is complete and visible from here on
+    pdl_wait();
+    pdl_launch_dependents();
+    if (*(volatile const int *)&ctl->done) return;
+    const int epoch = *(volatile const int *)&ctl->sweeps + 1;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const int p = bid + s * gsz;
+            if (p < total) issue(load_desc(p), s);
+        }
+    }
+
+    double acc[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
+    int k = 0;
+    for (int p = bid; p < total; p += gsz, ++k) {
+        const int s = k % STAGES;
+        const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
+        unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+        int c, t;
+        fused_item(fa, p, c, t);
+        const int pn = p + STAGES * gsz; // the item that will reuse this stage
+        Desc next_desc;
+        if (tid == 0 && pn < total) next_desc = load_desc(pn);
+        if (c == 1) { // uniform over the CTA
+            if (tid < 32) {
+                const int2 d = fa.dep[t];
+                fused_wait_tiles(fa.flags, d.x, d.y, epoch, ctl);
+            }
+            __syncthreads();
+        }
+        const int r_begin = (c ? fa.row0_1 : fa.row0_0) + t * GS_THREADS;
+        const int rows = min(GS_THREADS, (c ? fa.row1_1 : fa.row1_0) - r_begin);
+        mbar_wait(&full[s], parity);
+
+        const int k0 = reinterpret_cast<const int *>(st + L.hdr_off)[0];
+        const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
+        const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
+        const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
+        const int i = r_begin + tid;
+        if (tid < rows) {
+            const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
+            const int po = (r_begin & 1) + tid;
+            const double d = reinterpret_cast<const double *>(st + L.dg_off)[po];
+            double sig[NRHS];
+            gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int col, int r) { return x[r * n + col]; }, sig);
+            if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
+                    const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
+                    if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
+                    x[r * n + i] = xn;
+                }
+            }
+        }
+        __syncthreads(); // every thread is done with stage s, and with its stores of this tile
+        if (tid == 0) {
+            if (c == 0) fused_publish_tile(fa.flags + t, epoch);
+            if (pn < total) issue(next_desc, s);
+        }
+    }
+    if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(acc, partials + (size_t)blockIdx.x * NRHS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: dependency ranges
+// ---------------------------------------------------------------------------------------------
+// smallest / largest column of the tile's off-diagonal entries ({INT_MAX, -1}: none)
+__global__ void __launch_bounds__(GS_THREADS) plan_tile_colspan(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                                int row0, int row1, int2 *__restrict__ span) {
+    __shared__ int lo_s, hi_s;
+    if (threadIdx.x == 0) {
+        lo_s = INT_MAX;
+        hi_s = -1;
+    }
+    __syncthreads();
+    const int i = row0 + blockIdx.x * GS_THREADS + threadIdx.x;
+    if (i < row1) {
+        int lo = INT_MAX, hi = -1;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+            const int c = ci[k];
+            lo = min(lo, c);
+            hi = max(hi, c);
+        }
+        if (hi >= 0) {
+            atomicMin(&lo_s, lo);
+            atomicMax(&hi_s, hi);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) span[blockIdx.x] = make_int2(lo_s, hi_s);
+}
+
+// dep[j] over the colour-1 tiles.  side 0: the colour-0 tiles a colour-1 tile reads; side 1: the colour-1 tiles a
+// colour-0 tile reads (whose old values must be consumed before they are overwritten).  stats[0] |= 1 when a
+// column lies outside the other colour's rows (not a two-colour system this kernel can run).
+__global__ void __launch_bounds__(256) plan_fused_deps(const int2 *__restrict__ span, int ntiles, int side, int o_row0,
+                                                       int o_row1, int o_ntiles, int *__restrict__ dep,
+                                                       int *__restrict__ stats) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ntiles) return;
+    const int2 sp = span[t];
+    if (sp.y < 0) return; // no off-diagonal entries
+    if (sp.x < o_row0 || sp.y >= o_row1) {
+        atomicOr(&stats[0], 1);
+        return;
+    }
+    const int lo = (sp.x - o_row0) / GS_THREADS, hi = min((sp.y - o_row0) / GS_THREADS, o_ntiles - 1);
+    if (side == 0) {
+        atomicMin(&dep[2 * t], lo);
+        atomicMax(&dep[2 * t + 1], hi);
+    } else {
+        if (hi - lo > 4096) { // not a banded system: the fused walk would serialise
+            atomicOr(&stats[0], 2);
+            return;
+        }
+        for (int j = lo; j <= hi; ++j) {
+            atomicMin(&dep[2 * j], t);
+            atomicMax(&dep[2 * j + 1], t);
+        }
+    }
+}
+
+// stats[1] = max_j (hi_j - j), stats[2] = max_j (hi_j - lo_j + 1)
+__global__ void __launch_bounds__(256) plan_fused_stats(int *__restrict__ dep, int ntiles, int *__restrict__ stats) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= ntiles) return;
+    const int lo = dep[2 * j], hi = dep[2 * j + 1];
+    if (hi < 0) { // the tile neither reads nor is read: an empty range the wait loop skips
+        dep[2 * j] = 0;
+        return;
+    }
+    atomicMax(&stats[1], hi - j);
+    atomicMax(&stats[2], hi - lo + 1);
+}
+
+__global__ void __launch_bounds__(256) plan_fused_init(int *__restrict__ dep, int ntiles) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= ntiles) return;
+    dep[2 * j] = INT_MAX;
+    dep[2 * j + 1] = -1;
+}
+
+#define GS_FUSED_DEP_WIDTH_MAX 256 // colour-0 tiles one colour-1 tile may wait for (8 polls per lane)
+
+// Called by gsb_plan_build once the ring kernel (3/4) is available: decides p->fused_ok.
+int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t st) {
+    p->fused_ok = false;
+    if (!p->fused_allowed || p->n_colors != 2 || p->tile_rows != GS_THREADS) return GSB_OK;
+    const int nt0 = p->blocks[0], nt1 = p->blocks[1];
+    if (nt0 <= 0 || nt1 <= 0) return GSB_OK;
+    DevBuf<int2> span;
+    DevBuf<int> stats;
+    GSB_TRY(span.alloc((int64_t)nt0 + nt1));
+    GSB_TRY(stats.alloc(4));
+    GSB_TRY(p->fused_dep.alloc((int64_t)2 * nt1));
+    GSB_TRY(p->fused_flags.alloc(nt0));
+    GSB_CUDA(cudaMemsetAsync(stats.p, 0, 4 * sizeof(int), st));
+    GSB_CUDA(cudaMemsetAsync(p->fused_flags.p, 0, sizeof(int) * (size_t)nt0, st));
+    const int *cs = p->color_start;
+    plan_tile_colspan<<<nt0, GS_THREADS, 0, st>>>(rp, ci, cs[0], cs[1], span.p);
+    plan_tile_colspan<<<nt1, GS_THREADS, 0, st>>>(rp, ci, cs[1], cs[2], span.p + nt0);
+    plan_fused_init<<<(nt1 + 255) / 256, 256, 0, st>>>(p->fused_dep.p, nt1);
+    plan_fused_deps<<<(nt1 + 255) / 256, 256, 0, st>>>(span.p + nt0, nt1, 0, cs[0], cs[1], nt0, p->fused_dep.p, stats.p);
+    plan_fused_deps<<<(nt0 + 255) / 256, 256, 0, st>>>(span.p, nt0, 1, cs[1], cs[2], nt1, p->fused_dep.p, stats.p);
+    plan_fused_stats<<<(nt1 + 255) / 256, 256, 0, st>>>(p->fused_dep.p, nt1, stats.p);
+    GSB_KERNEL_CHECK();
+    int h[4] = {0, 0, 0, 0};
+    GSB_CUDA(cudaMemcpyAsync(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (h[0] != 0 || h[2] > GS_FUSED_DEP_WIDTH_MAX) {
+        p->fused_dep.release();
+        p->fused_flags.release();
+        return GSB_OK;
+    }
+    p->fused_lead_min = h[1] + 1 > 1 ? h[1] + 1 : 1;
+    p->fused_ok = true;
+    return GSB_OK;
+}
+
+int gsb_plan_fused_reset(const GsbPlan *p, cudaStream_t st) {
+    if (!p->fused_ok) return GSB_OK;
+    GSB_CUDA(cudaMemsetAsync(p->fused_flags.p, 0, sizeof(int) * (size_t)p->blocks[0], st));
+    return GSB_OK;
+}
+
+template <int NRHS>
+static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const double *va, const double *dg,
+                          const double *b, double *x, int64_t ld, bool check, GsCtl *ctl, double *partials,
+                          cudaStream_t st, int *slots) {
+    typedef void (*fused_fn)(const int *, const int *, const double *, const double *, const double *, double *, int64_t,
+                             int, GsCtl *, double *, const GsbFusedArgs);
+    fused_fn kern = check ? (fused_fn)gs_sweep_fused<NRHS, true, GS_RING_STAGES_DEFAULT>
+                          : (fused_fn)gs_sweep_fused<NRHS, false, GS_RING_STAGES_DEFAULT>;
+    const int smem = 64 + GS_RING_STAGES_DEFAULT * ring_layout(p->cap, NRHS, check, 0).stage_bytes;
+    // opt-in shared-memory size and resident CTAs per SM: per (function, size, device)
+    struct Cfg { const void *fn; int smem, occ, dev; };
+    static Cfg cfgs[64];
+    static int ncfg = 0;
+    const int dev_now = gsb_current_device();
+    Cfg *cf = nullptr;
+    for (int q = 0; q < ncfg; ++q)
+        if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem && cfgs[q].dev == dev_now) cf = &cfgs[q];
+    if (!cf) {
+        GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        int o = 0;
+        GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
+        if (ncfg == 64) ncfg = 0;
+        cf = &cfgs[ncfg++];
+        cf->fn = (const void *)kern;
+        cf->smem = smem;
+        cf->dev = dev_now;
+        cf->occ = o < 1 ? 1 : o;
+    }
+    static int env_ctas = -1, env_lead = -1;
+    if (env_ctas < 0) {
+        const char *e = getenv("GSB_RING_CTAS");
+        env_ctas = e ? atoi(e) : 0;
+        e = getenv("GSB_FUSED_LEAD"); // extra lead in tiles on top of the dependency distance; default = the grid size
+        env_lead = e ? atoi(e) : 0;
+    }
+    int per_sm = cf->occ;
+    if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
+    const int nt0 = p->blocks[0], nt1 = p->blocks[1];
+    int grid = gsb_sm_count() * per_sm; // every CTA must be resident: the walk waits on other CTAs' tiles
+    if (grid > nt0 + nt1) grid = nt0 + nt1;
+    if (grid > GSB_RING_SLOTS_MAX) grid = GSB_RING_SLOTS_MAX;
+    GsbFusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.row0_0 = p->color_start[0];
+    fa.row1_0 = fa.row0_1 = p->color_start[1];
+    fa.row1_1 = p->color_start[2];
+    fa.nt0 = nt0;
+    fa.nt1 = nt1;
+    fa.tile_k0 = p->tile_k.p + p->tile_off[0];
+    fa.tile_k1 = p->tile_k.p + p->tile_off[1];
+    fa.dep = reinterpret_cast<const int2 *>(p->fused_dep.p);
+    fa.flags = p->fused_flags.p;
+    // lead: the dependency distance plus the items in flight (one per CTA), so that a colour-1 tile's dependencies
+    // are finished, not merely started, when it comes up
+    int lead = p->fused_lead_min + (p->fused_lead_extra > 0 ? p->fused_lead_extra : env_lead > 0 ? env_lead : grid);
+    if (lead > nt0) lead = nt0;
+    fa.lead = lead;
+    fa.nalt = nt1 < nt0 - lead ? nt1 : nt0 - lead;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GS_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gsb_pdl_mode((int64_t)p->color_start[2] - p->color_start[0]) ? 1 : 0;
+    GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, ci, va, dg, b, x, ld, p->cap, ctl, partials, (const GsbFusedArgs)fa));
+    if (slots) *slots = grid;
+    return GSB_OK;
+}
+
+int gsb_plan_launch_fused(const GsbPlan *p, const int *rp, const int *ci, const double *va, const double *dg,
+                          const double *b, double *x, int64_t ld, int nrhs, bool check, GsCtl *ctl, double *partials,
+                          cudaStream_t st, int *slots) {
+    if (!p->fused_ok) {
+        gsb_set_error("fused sweep kernel unavailable for this matrix (needs two colours and banded coupling)");
+        return GSB_ERR_ARG;
+    }
+    switch (nrhs) {
+        case 1: return launch_fused_t<1>(p, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, slots);
+        case 2: return launch_fused_t<2>(p, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, slots);
+        case 3: return launch_fused_t<3>(p, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, slots);
+        case 4: return launch_fused_t<4>(p, rp, ci, va, dg, b, x, ld, check, ctl, partials, st, slots);
+    }
+    gsb_set_error("nrhs must be 1..%d", GSB_MAX_RHS);
+    return GSB_ERR_ARG;
+}

@@ -203,14 +203,30 @@ struct GsbPlan {
     DevBuf<int> ci_slot;  // kernel 4's index array: shared-memory slots for window tiles (-1 = diagonal)
     int win_off[66];      // tile index of the colour's first tile
     int wcap = 0;         // doubles per right-hand side reserved per stage for the windows
+    // kernel 5 (two colours, one launch per sweep): per tile of colour 1 the range of colour-0 tiles it has to see
+    // finished (the ones it reads, and the ones that read its rows' old values); per tile of colour 0 a flag
+    bool fused_allowed = false; // set by the single-GPU solver before gsb_plan_build (strip plans never fuse)
+    bool fused_ok = false;
+    int fused_lead_min = 0;     // colour 0 has to run at least this many tiles ahead of colour 1
+    int fused_lead_extra = 0;   // caller's gsb_gs_options.fused_lead (0 = default)
+    DevBuf<int> fused_dep;      // 2 ints per colour-1 tile: first, last colour-0 tile
+    DevBuf<int> fused_flags;    // per colour-0 tile: number of the last sweep that updated it (reset per solve)
     int total_blocks() const;
 };
 int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_start, int n_colors,
                    int kernel_request, cudaStream_t st);
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs);
+// kernel 5: the whole sweep (both colours) in one launch; *slots = stop-rule partial slots written (== grid size).
+// gsb_plan_fused_reset must be enqueued once before the first sweep of every solve (ctl->sweeps restarts at 0).
+int gsb_plan_fused_reset(const GsbPlan *p, cudaStream_t st);
+int gsb_plan_launch_fused(const GsbPlan *p, const int *rp, const int *ci, const double *va, const double *dg,
+                          const double *b, double *x, int64_t ld, int nrhs, bool check, GsCtl *ctl, double *partials,
+                          cudaStream_t st, int *slots);
 int gsb_plan_partial_slots(const GsbPlan *p, int c, int nrhs); // stop-rule partial slots of colour phase c
 // programmatic dependent launch of the ring kernels / gs_end_sweep (GSB_PDL=0 disables; suppressed during graph capture)
 bool gsb_pdl_enabled();
+int gsb_pdl_mode(int64_t phase_rows); // decision for the launch about to be made (remembered for gs_end_sweep)
+int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t st); // gsb_fused.cu
 void gsb_pdl_suppress(int on);
 static inline int64_t gsb_padded_ld(int64_t n) { return (n + 1) & ~(int64_t)1; }
 // Fused halo exchange of the strip solver (gsb_dist.cu): the phase kernel itself writes the boundary values a

@@ -20,49 +20,9 @@
 // Solver format: the colour-major CSR holds the OFF-DIAGONAL entries only (rp/ci/va) and the diagonal lives in
 // its own array dg[row] (0 when the row has no diagonal -> the row is skipped).  The row body then has no
 // per-entry "is this the diagonal" test, and a 5-point row has at most 4 entries.
-#include "gsb_internal.cuh"
+#include "gsb_ring.cuh"
 
 #include <stdlib.h>
-
-#define GS_THREADS 256
-#define GS_TILE_CAP_MAX 6144 // CSR entries per tile that still leave >= 3 CTAs per SM (72 KB each)
-#define GS_UNROLL 4          // rows with up to this many off-diagonal entries take the gather-prefetch path (5-point rows)
-
-// sigma_r = sum_j v_j * x_r[c_j] over the row's off-diagonal entries, storage order, product and sum rounded
-// separately.  XV(c, r) yields x_r[c] (global memory or a shared-memory window).  For short rows all gathers are
-// issued before the first is consumed; padded positions load index 0 (always valid) and are not accumulated.
-template <int NRHS, typename XV>
-__device__ __forceinline__ void gs_row_sigma(const int *__restrict__ crow, const double *__restrict__ vrow, int len,
-                                             XV xv, double (&sig)[NRHS]) {
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
-    if (len <= GS_UNROLL) {
-        int cc[GS_UNROLL];
-        double vv[GS_UNROLL], xg[GS_UNROLL][NRHS];
-#pragma unroll
-        for (int j = 0; j < GS_UNROLL; ++j) {
-            cc[j] = j < len ? crow[j] : 0;
-            vv[j] = j < len ? vrow[j] : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < GS_UNROLL; ++j)
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) xg[j][r] = xv(cc[j], r);
-#pragma unroll
-        for (int j = 0; j < GS_UNROLL; ++j)
-            if (j < len) {
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(vv[j], xg[j][r]));
-            }
-    } else {
-        for (int j = 0; j < len; ++j) {
-            const int c = crow[j];
-            const double v = vrow[j];
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(v, xv(c, r)));
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel 1: row per thread, direct global loads
@@ -97,51 +57,6 @@ __global__ void __launch_bounds__(GS_THREADS)
 // ---------------------------------------------------------------------------------------------
 // kernel 2: bulk-copy staged CSR tiles
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-
-// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
-// attribute may start while its predecessor in the stream is still running; pdl_wait() blocks until the
-// predecessor has completed and its writes are visible.  Both are no-ops for a normally launched kernel.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// hint: bring [p, p + bytes) into L2 (bytes a multiple of 16, p 16-byte aligned); no completion tracking
-__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 template <int NRHS, bool CHECK>
 __global__ void __launch_bounds__(GS_THREADS, 4)
     gs_phase_staged(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
@@ -217,46 +132,39 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
 //       into the stage too, so the whole phase runs out of shared memory and HBM only sees TMA bursts
 //       plus the coalesced x stores.  Tiles whose gathers do not fit windows fall back to global gathers.
 // ---------------------------------------------------------------------------------------------
-#define GS_RING_STAGES_DEFAULT 2
-#define GS_RING_STAGES_MAX 4
-#define GS_WIN_MAX 4           // windows per tile
-#define GS_WIN_GRANULE 64      // columns per granule (512 bytes: keeps every window 16-byte aligned)
-#define GS_WIN_CAP_MAX 2048    // doubles per right-hand side per stage
-#define GS_WIN_DESC 12         // ints per tile descriptor
-#define GS_RING_SLOTS_MAX GSB_RING_SLOTS_MAX // upper bound of the grid = stop-rule partial slots per colour phase
-
-struct RingLayout {
-    int va_off, dg_off, b_off, xo_off, xw_off, ci_off, rp_off, hdr_off, stage_bytes, plane;
-};
-
-__host__ __device__ inline RingLayout ring_layout(int cap, int nrhs, bool check, int wcap) {
-    RingLayout L;
-    L.plane = GS_THREADS + 2;
-    L.va_off = 0;
-    L.dg_off = L.va_off + cap * 8;
-    L.b_off = L.dg_off + L.plane * 8;
-    L.xo_off = L.b_off + nrhs * L.plane * 8;
-    L.xw_off = L.xo_off + (check ? nrhs * L.plane * 8 : 0);
-    L.ci_off = L.xw_off + nrhs * wcap * 8;
-    L.rp_off = L.ci_off + cap * 4;
-    L.hdr_off = L.rp_off + (GS_THREADS + 8) * 4;
-    L.stage_bytes = L.hdr_off + 64;
-    return L;
-}
-
 // The halo CTAs' synchronisation with the neighbour GPUs.  Kept out of line on purpose: with the spin loop, the
 // system-scope fences and the atomic inlined, ptxas stops using the uniform datapath for the whole kernel and the
 // interior tiles run 8 % slower (measured); as calls on a cold path they cost the interior nothing.
-__device__ __noinline__ void halo_wait_flags(const int *f0, const int *f1, int epoch) {
+#define GS_HALO_ABORT_EPOCH 0x7fffffff // a rank that gave up raises its neighbours' flags to this: nobody waits on it
+__device__ __noinline__ void halo_wait_flags(const int *f0, const int *f1, int epoch, GsCtl *ctl, int *peer_flag0,
+                                             int *peer_flag1) {
     const int *f[2] = {f0, f1};
+    bool gave_up = false;
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr)
         if (f[pr]) {
             int v;
-            do {
+            long long spins = 0;
+            for (;;) {
                 asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f[pr]) : "memory");
-            } while (v < epoch);
+                if (v >= epoch) break;
+                // bounded like the stop-rule exchange (~10 s): a neighbour that crashed or never launched must not
+                // wedge this GPU; also leave as soon as another CTA of this rank has given up
+                if (++spins > (1ll << 25) || ((spins & 1023) == 0 && *(volatile int *)&ctl->error)) {
+                    gave_up = true;
+                    break;
+                }
+                if (spins > 64) __nanosleep(100);
+            }
         }
+    if (gave_up) {
+        ctl->error = 1;
+        ctl->done = 1;
+        // publish the abort: neighbours waiting on this rank's flags fall through instead of spinning forever (their
+        // own stop-rule exchange then times out against this rank and reports the error)
+        if (peer_flag0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flag0), "r"(GS_HALO_ABORT_EPOCH) : "memory");
+        if (peer_flag1) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flag1), "r"(GS_HALO_ABORT_EPOCH) : "memory");
+    }
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __noinline__ void halo_fence_system() { __threadfence_system(); }
@@ -533,7 +441,8 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
     // inside it makes ptxas give up the uniform datapath for the whole loop.)
     if (HALO && hinfo && tid == 0 && halo.wait_epoch > 0)
         halo_wait_flags(halo.has_peer[0] ? halo.wait_flag[0] : nullptr, halo.has_peer[1] ? halo.wait_flag[1] : nullptr,
-                        halo.wait_epoch);
+                        halo.wait_epoch, const_cast<GsCtl *>(ctl), halo.has_peer[0] ? halo.peer_flag[0] : nullptr,
+                        halo.has_peer[1] ? halo.peer_flag[1] : nullptr);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -962,7 +871,7 @@ __global__ void __launch_bounds__(256) gs_fold_partials(const double *__restrict
 static thread_local int g_pdl_suppress = 0;
 static thread_local int g_pdl_last = 0; // decision of the most recent ring launch: gs_end_sweep follows it
 void gsb_pdl_suppress(int on) { g_pdl_suppress = on; }
-static int gsb_pdl_mode(int64_t phase_rows) {
+int gsb_pdl_mode(int64_t phase_rows) {
     static int env = -2;
     if (env == -2) {
         const char *e = getenv("GSB_PDL");
@@ -1032,7 +941,16 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
 // Measured on B200 (profiles/README.md): one right-hand side is fastest with the windows (4); with several
 // fused right-hand sides a window stage (49 KB at k = 3) leaves room for two CTAs per SM only, and the ring
 // with global gathers (3), which fits three, wins.  Kernel 4 stays selectable explicitly.
+static bool fused_sweep_auto() {
+    static int env = -1;
+    if (env < 0) {
+        const char *e = getenv("GSB_FUSED_SWEEP");
+        env = e ? atoi(e) : 1; // measured on B200 (profiles/README.md): on where the plan allows it
+    }
+    return env != 0;
+}
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
+    if (p->fused_ok && (p->requested == 5 || (p->requested == 0 && fused_sweep_auto()))) return 5;
     if (p->kernel != 4) return p->kernel;
     if (p->requested == 4) return 4;
     if (p->requested == 3) return 3;
@@ -1051,7 +969,9 @@ bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs) {
     const int eff = gsb_plan_effective_kernel(p, nrhs);
     const char *e = getenv("GSB_RING_STAGES"); // fused-end variants are built for the default stage count only
     if (e && atoi(e) != 0 && atoi(e) != GS_RING_STAGES_DEFAULT) return false;
-    return eff == 3 || eff == 4;
+    // the window kernel (4) is excluded: with the fused end its solution bits differed on B200 (round 1, (1500, k = 1));
+    // until that is understood the separate end-of-sweep kernel stays the only path for it
+    return eff == 3;
 }
 
 // stop-rule partial slots colour phase c writes (and gs_end_sweep folds) for `nrhs` right-hand sides
@@ -1076,6 +996,7 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
     p->kernel = 1;
     p->tile_rows = GS_THREADS;
     p->smem_bytes = 0;
+    p->fused_ok = false;
     if (kernel_request != 1) {
         DevBuf<int> mx;
         GSB_TRY(mx.alloc(1));
@@ -1153,6 +1074,12 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
             } else {
                 p->tile_win.release();
             }
+        }
+        // kernel 5: both colours of a two-colour system in one launch per sweep (gsb_fused.cu)
+        if (p->kernel == 3 || p->kernel == 4) GSB_TRY(gsb_plan_build_fused(p, rp, ci, st));
+        if (!p->fused_ok && kernel_request == 5) {
+            gsb_set_error("fused sweep kernel unavailable: needs a two-colour system with banded coupling");
+            return GSB_ERR_ARG;
         }
         if (p->kernel != 4 && kernel_request == 4) {
             gsb_set_error("window kernel unavailable: the gathers of this matrix do not form contiguous windows");
@@ -1302,7 +1229,12 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         cfg.attrs = attr;
         const int pdl = gsb_pdl_mode((int64_t)row1 - row0);
         cfg.numAttrs = pdl ? 1 : 0;
-        halo.pdl_early = pdl == 1 ? 1 : 0;
+        // the early prologue stages this colour's x_old while the predecessor may still be running; that is only safe
+        // when the predecessor is ANOTHER colour's phase (with a single non-empty colour the predecessor, through the
+        // end-of-sweep kernel's early release of its dependents, is the phase that writes exactly those values)
+        int nonempty = 0;
+        for (int q = 0; q < p->n_colors; ++q) nonempty += p->blocks[q] > 0 ? 1 : 0;
+        halo.pdl_early = (pdl == 1 && nonempty >= 2) ? 1 : 0;
         GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, (const int *)(win ? p->ci_slot.p : ci), va, dg, b, x, ld, row0, row1,
                                     nb, tk, tw, p->cap, wcap, ctl, partials, (const GsbHaloArgs)halo,
                                     (const GsbEndArgs)end));

@@ -59,6 +59,14 @@ extern "C" void gsb_gs_default_options(gsb_gs_options *o) {
 static int enqueue_sweep(gsb_matrix *m, int nrhs, bool check, cudaStream_t st, int64_t *launches) {
     GsCtl *ctl = (GsCtl *)m->ctl.p;
     const int64_t n = gsb_padded_ld(m->n_rows);
+    if (gsb_plan_effective_kernel(m->plan, nrhs) == 5) { // both colours in one launch (gsb_fused.cu)
+        int slots = 0;
+        GSB_TRY(gsb_plan_launch_fused(m->plan, m->rp.p, m->ci.p, m->va.p, m->dg.p, m->bw.p, m->xw.p, n, nrhs, check, ctl,
+                                      m->partials.p, st, &slots));
+        GSB_TRY(gsb_launch_end_sweep(ctl, m->partials.p, slots, nrhs, check ? 1 : 0, 0, st));
+        *launches += 2;
+        return GSB_OK;
+    }
     // opt-in (GSB_FUSED_END=1): the last non-empty colour phase ends the sweep itself (GsbEndArgs)
     int carrier = -1, total = 0;
     for (int c = 0; c < m->n_colors; ++c)
@@ -104,6 +112,7 @@ static int ensure_workspace(gsb_matrix *m, int nrhs, int kernel_request, cudaStr
     if (!m->plan) m->plan = new (std::nothrow) GsbPlan();
     if (!m->plan) return GSB_ERR_ALLOC;
     if (!m->plan->valid || m->plan->requested != kernel_request) {
+        m->plan->fused_allowed = true;
         GSB_TRY(gsb_plan_build(m->plan, m->rp.p, m->ci.p, m->color_start, m->n_colors, kernel_request, st));
         GSB_TRY(m->partials.alloc((int64_t)(m->plan->total_blocks() + 1 + 64) * MAX_RHS)); // +64: second-level fold
         drop_graph(m);
@@ -150,6 +159,10 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     }
     const int64_t n = m->n_rows;
     GSB_TRY(ensure_workspace(m, nrhs, opts.kernel, st));
+    if (m->plan->fused_lead_extra != opts.fused_lead) {
+        m->plan->fused_lead_extra = opts.fused_lead;
+        drop_graph(m); // the lead is a launch argument baked into a captured batch
+    }
     const int nbv = (int)((n + 255) / 256);
     const int64_t ld = gsb_padded_ld(n);
     gather_perm<<<nbv, 256, 0, st>>>(b_dev, m->perm.p, n, ld, nrhs, m->bw.p);
@@ -172,6 +185,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     GsCtl *hp = (GsCtl *)m->ctl_host;
     *hp = h;
     GSB_CUDA(cudaMemcpyAsync(m->ctl.p, hp, sizeof(GsCtl), cudaMemcpyHostToDevice, st));
+    GSB_TRY(gsb_plan_fused_reset(m->plan, st)); // kernel 5's tile flags count sweeps from 0 again
 
     int batch = opts.batch_sweeps;
     if (batch <= 0) {
@@ -251,6 +265,10 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
             break;
         }
         h = *hp;
+        if (h.error) {
+            gsb_set_error("gauss_seidel: the sweep kernel gave up waiting (code %d)", h.error);
+            status = GSB_ERR_CUDA;
+        }
     }
     cudaEventRecord(ev1, st);
     cudaEventSynchronize(ev1);

@@ -261,6 +261,49 @@ int orc_gauss_seidel(const orc_matrix *m, const double *b, int64_t n, double eps
     return 0;
 }
 
+/* A6 with a trace (test infrastructure for the large goldens): the same loop as orc_gauss_seidel, run ONCE for a
+ * descending list of thresholds.  The iterate of the sweep on which `eps <= eps_list[k]` first holds is exactly what
+ * gaussSeidel(b, eps_list[k], max_iteration) returns (v2 :350-380: the loop tests eps before each sweep), so it is
+ * copied to x_snap[k] and its sweep count to sweeps_at[k]; eps_hist[s] = the L1 update norm of sweep s+1. */
+int orc_gauss_seidel_trace(const orc_matrix *m, const double *b, int64_t n, const double *eps_list, int n_eps,
+                           int max_iteration, double *x_snap, int *sweeps_at, double *eps_hist) {
+    double *prev = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *x = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) x[i] = 1.0;
+    for (int k = 0; k < n_eps; ++k) sweeps_at[k] = -1;
+    double eps = 10;
+    int cnt = 0, next = 0;
+    while (next < n_eps && cnt < max_iteration) {
+        memcpy(prev, x, sizeof(double) * (size_t)n);
+        for (int i = 0; i < m->n_rows; ++i) {
+            double a_ii = orc_at(m, i, i);
+            if (a_ii == 0) continue;
+            double sigma = 0;
+            int k = m->row_begin[i];
+            for (int j = 0; j < m->row_nnz[i]; ++j, ++k) {
+                int c = m->cols[k];
+                if (c != i) sigma = sigma + m->values[k] * x[c];
+            }
+            x[i] = (b[i] - sigma) / a_ii;
+        }
+        eps = orc_l1_dist(x, prev, n);
+        if (eps_hist) eps_hist[cnt] = eps;
+        ++cnt;
+        while (next < n_eps && !(eps > eps_list[next])) {
+            memcpy(x_snap + (size_t)next * (size_t)n, x, sizeof(double) * (size_t)n);
+            sweeps_at[next++] = cnt;
+        }
+    }
+    /* thresholds never reached: the iterate at max_iteration, as the reference would return it */
+    for (int k = next; k < n_eps; ++k) {
+        memcpy(x_snap + (size_t)k * (size_t)n, x, sizeof(double) * (size_t)n);
+        sweeps_at[k] = cnt;
+    }
+    free(prev);
+    free(x);
+    return 0;
+}
+
 /* A7.  v2 :382-393 */
 void orc_spmv(const orc_matrix *m, const double *in, double *out) {
     for (int i = 0; i < m->n_rows; ++i) {

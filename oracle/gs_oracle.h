@@ -53,6 +53,9 @@ void orc_insert(orc_matrix *m, double val, int row, int col);
 /* A6: v2 :350-380.  Returns 0; *sweeps = cnt, *last_eps = eps at exit. x has n entries. */
 int orc_gauss_seidel(const orc_matrix *m, const double *b, int64_t n, double epsilon, int max_iteration,
                      double *x, int *sweeps, double *last_eps);
+/* the same loop traced: snapshots at a descending list of thresholds (large goldens; see gs_oracle.c) */
+int orc_gauss_seidel_trace(const orc_matrix *m, const double *b, int64_t n, const double *eps_list, int n_eps,
+                           int max_iteration, double *x_snap, int *sweeps_at, double *eps_hist);
 /* A7: v2 :382-393 */
 void orc_spmv(const orc_matrix *m, const double *in, double *out);
 /* A8: v2 :45-105 (serial left-to-right order: the reference's PSTL backend is serial without TBB) */

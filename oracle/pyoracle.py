@@ -59,6 +59,7 @@ def _oracle():
         L.orc_insert.argtypes = [P, C.c_double, C.c_int, C.c_int]
         L.orc_gauss_seidel.argtypes = [P, _f64p, C.c_int64, C.c_double, C.c_int, _f64p, C.POINTER(C.c_int),
                                        C.POINTER(C.c_double)]
+        L.orc_gauss_seidel_trace.argtypes = [P, _f64p, C.c_int64, _f64p, C.c_int, C.c_int, _f64p, _i32p, _f64p]
         L.orc_spmv.argtypes = [P, _f64p, _f64p]
         L.orc_l1_dist.argtypes = [_f64p, _f64p, C.c_int64]
         L.orc_l1_dist.restype = C.c_double
@@ -177,6 +178,17 @@ class Oracle:
         sw, le = C.c_int(0), C.c_double(0)
         self.L.orc_gauss_seidel(self.m, b, len(b), eps, max_iter, x, C.byref(sw), C.byref(le))
         return x, sw.value, le.value
+
+    def gauss_seidel_trace(self, b, eps_list, max_iter):
+        """One run, snapshots at every threshold of the descending `eps_list`:
+        -> x (len(eps_list), n), sweeps (len(eps_list),), eps_hist (sweeps run,)"""
+        b, eps_list = _a(b, np.float64), _a(eps_list, np.float64)
+        assert np.all(np.diff(eps_list) <= 0)
+        xs = np.empty((len(eps_list), len(b)), np.float64)
+        sw = np.zeros(len(eps_list), np.int32)
+        hist = np.zeros(max(max_iter, 1), np.float64)
+        self.L.orc_gauss_seidel_trace(self.m, b, len(b), eps_list, len(eps_list), max_iter, xs.reshape(-1), sw, hist)
+        return xs, sw, hist[:int(sw.max())]
 
     def spmv(self, v):
         v = _a(v, np.float64)

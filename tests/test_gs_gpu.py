@@ -287,8 +287,8 @@ def test_full_size_properties_4096(gsb):
 
 @pytest.mark.parametrize("nrhs", [1, 3])
 def test_all_kernels_agree_bitwise(gsb, nrhs):
-    """direct (1), staged (2), ring (3) and window-staged ring (4) kernels implement the same arithmetic in
-    the same order."""
+    """direct (1), staged (2), ring (3), window-staged ring (4) and the fused two-colour sweep (5) implement the
+    same arithmetic in the same order."""
     from coursecomputationalphotography_b200 import workloads as wl
     W, H = 300, 217  # odd sizes: tiles and bulk-copy spans start at unaligned offsets
     sp = gsb.SparseMatrix(np.float64)
@@ -296,7 +296,7 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
     bb = b[:nrhs] if nrhs > 1 else b[0]
     res = {}
-    for k in (1, 2, 3, 4):
+    for k in (1, 2, 3, 4, 5):
         for ce in (1, 3):
             x = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=12, options=gsb.SparseMatrix.options(kernel=k, check_every=ce))
             assert sp.last_stats.kernel_used == k and sp.last_stats.sweeps == 12
@@ -307,7 +307,7 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
         # the stop norm is summed in a fixed but kernel-specific order: equal to rounding
         assert abs(e - e0) <= 1e-12 * abs(e0), key
     # ... and run-to-run identical for one kernel
-    for k in (3, 4):
+    for k in (3, 4, 5):
         o = gsb.SparseMatrix.options(kernel=k)
         sp.gaussSeidel(bb, epsilon=0.0, max_iteration=5, options=o)
         e1 = sp.last_stats.last_eps[0]
@@ -320,11 +320,83 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     outs = [sg.gaussSeidel(b2, epsilon=0.0, max_iteration=6, options=gsb.SparseMatrix.options(kernel=k)) for k in (1, 2, 3, 0)]
     assert sg.last_stats.kernel_used == 3  # random columns do not form windows: auto keeps global gathers
     assert all(np.array_equal(outs[0], o) for o in outs[1:])
-    with pytest.raises(gsb.GsbError):
-        sg.gaussSeidel(b2, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=4))
-    # auto on the grid picks the window kernel
+    for k in (4, 5):  # no gather windows, more than two colours
+        with pytest.raises(gsb.GsbError):
+            sg.gaussSeidel(b2, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=k))
+    # auto on the grid: measured policy, see gsb_plan_effective_kernel
     sp.gaussSeidel(bb, epsilon=0.0, max_iteration=1)
-    assert sp.last_stats.kernel_used == (4 if nrhs == 1 else 3)  # measured policy, see gsb_plan_effective_kernel
+    assert sp.last_stats.kernel_used == AUTO_GRID_KERNEL(nrhs)
+
+
+def AUTO_GRID_KERNEL(nrhs):
+    return 5
+
+
+@pytest.mark.parametrize("W,H,nrhs", [(300, 217, 3), (1024, 512, 1), (1024, 512, 3), (2048, 1500, 3)])
+def test_fused_sweep_wavefront_bitwise(gsb, W, H, nrhs):
+    """Kernel 5 (both colours in one launch, colour 1 trailing colour 0 by `lead` tiles and waiting on per-tile
+    flags) against the per-phase ring kernel: x AND the stop norm bit for bit, for leads from "just the dependency
+    distance" (every colour-1 tile waits on tiles in flight) to "more than there are tiles" (degenerates to two
+    phases), with and without graph replay, on the full grid and on a compact masked system whose two colours
+    have different sizes."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
+    bb = b[:nrhs] if nrhs > 1 else b[0]
+    ref = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=9, options=gsb.SparseMatrix.options(kernel=3, use_graph=0))
+    for lead in (1, 2, 37, 0, 1 << 20):
+        for graph in (0, 1):
+            o = gsb.SparseMatrix.options(kernel=5, fused_lead=lead, use_graph=graph, batch_sweeps=4)
+            x = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=9, options=o)
+            assert sp.last_stats.kernel_used == 5 and sp.last_stats.sweeps == 9
+            assert np.array_equal(x, ref), (lead, graph)
+    # compact masked system (Dirichlet blend): user colouring, unequal colour sizes, ragged tiles
+    mask = wl.blob_mask(W // 2, H // 2, 0.35, 24, seed=5)
+    guide = wl.synth_image(W // 2, H // 2, 3, seed=7)
+    ro, ci, va, bm, pix, colors = wl.masked_poisson_system(mask, guide, guide[:, ::-1, ::-1])
+    n = len(pix)
+    sm = gsb.SparseMatrix(np.float64)
+    sm.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
+    sm.analyze(gsb._lib.ORDER_USER, colors)
+    bq = bm[:nrhs] if nrhs > 1 else bm[0]
+    r1 = sm.gaussSeidel(bq, epsilon=0.0, max_iteration=15, options=gsb.SparseMatrix.options(kernel=1))
+    e1 = list(sm.last_stats.last_eps)[:nrhs]
+    for lead in (1, 5, 0):
+        x = sm.gaussSeidel(bq, epsilon=0.0, max_iteration=15, options=gsb.SparseMatrix.options(kernel=5, fused_lead=lead))
+        assert sm.last_stats.kernel_used == 5 and np.array_equal(x, r1), lead
+        assert all(abs(a - c) <= 1e-12 * abs(c) for a, c in zip(list(sm.last_stats.last_eps)[:nrhs], e1))
+    # the stop rule fires on the same sweep with the same accepted iterate
+    x3 = sm.gaussSeidel(bq, epsilon=1e-2, max_iteration=20000, options=gsb.SparseMatrix.options(kernel=3))
+    s3 = sm.last_stats.sweeps
+    x5 = sm.gaussSeidel(bq, epsilon=1e-2, max_iteration=20000, options=gsb.SparseMatrix.options(kernel=5))
+    assert 15 < s3 < 20000 and sm.last_stats.sweeps == s3 and np.array_equal(x3, x5)
+
+
+def test_fused_sweep_needs_banded_two_colour_system(gsb):
+    """A two-colour (bipartite) matrix with random coupling has no wavefront: kernel 5 is refused, auto keeps the
+    per-phase kernels; a one-colour (diagonal) system likewise."""
+    rng = np.random.default_rng(3)
+    n = 200_000
+    half = n // 2
+    rows = np.repeat(np.arange(n), 3)
+    cols = np.where(rows < half, rng.integers(half, n, rows.size), rng.integers(0, half, rows.size))
+    key = np.unique(rows.astype(np.int64) * n + cols)
+    r, c = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    v = rng.uniform(-1, 0, r.size)
+    r = np.concatenate([r, np.arange(n, dtype=np.int32)])
+    c = np.concatenate([c, np.arange(n, dtype=np.int32)])
+    v = np.concatenate([v, np.full(n, 5.0)])
+    o = np.lexsort((c, r))
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromVector(r[o], c[o], v[o])
+    sp.analyze(gsb._lib.ORDER_USER, (np.arange(n) >= half).astype(np.int32))
+    b = rng.standard_normal(n)
+    x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=4)
+    assert sp.last_stats.kernel_used in (3, 4) and sp.last_stats.n_colors == 2
+    with pytest.raises(gsb.GsbError):
+        sp.gaussSeidel(b, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=5))
+    assert np.array_equal(x, sp.gaussSeidel(b, epsilon=0.0, max_iteration=4, options=gsb.SparseMatrix.options(kernel=1)))
 
 
 @pytest.mark.parametrize("W,H,nrhs", [(64, 48, 3), (300, 217, 1), (300, 217, 3), (1024, 512, 3)])
@@ -337,7 +409,7 @@ def test_dependent_launch_equals_graph_replay(gsb, W, H, nrhs):
     sp.poisson(W, H)
     img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
     bb = b[:nrhs] if nrhs > 1 else b[0]
-    for k in (3, 4):
+    for k in (3, 4, 5):
         for sweeps in (1, 2, 7):
             out = []
             for graph in (1, 0):
