@@ -41,12 +41,13 @@ def parse():
     p.add_argument("--sweeps", type=int, default=100, help="GS sweeps per step")
     p.add_argument("--check-every", type=int, default=1)
     p.add_argument("--kernel", type=int, default=0)
-    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--strips", action="store_true", help="N = 1 through the strip solver (measurement aid)")
     p.add_argument("--no-time-to-tol", action="store_true", help="skip the time-to-tolerance leg (masked blend)")
     p.add_argument("--time-to-tol-only", action="store_true", help=argparse.SUPPRESS)
+    p.add_argument("--no-default-eps", action="store_true", help="time-to-tol: skip the epsilon = 1e-6 run")
     return p.parse_args()
 
 
@@ -147,6 +148,14 @@ def recorded_traffic(kernel_used, W, H, ch, check_every):
     return out
 
 
+def workload_config(W, H, ch, n, nnz):
+    """The workload-defining keys, identical for the GPU arm, the strip arm and the reference arm (what each arm did
+    with the workload -- sweeps per step, ordering, cadence -- goes into "run")."""
+    return {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, ch), "n": int(n), "nnz": int(nnz),
+            "channels": int(ch),
+            "l2": "working set %.2f GB per sweep >> 126 MB L2 (no flush needed)" % (algorithmic_bytes_per_sweep(nnz, n, ch) / 1e9)}
+
+
 def algorithmic_bytes_per_sweep(nnz, n, k):
     return 12.0 * nnz + 4.0 * n + 24.0 * k * n
 
@@ -210,15 +219,17 @@ def run_reference(args):
         return
     W = H = args.size
     sweeps = 2  # bounded sample: 2 sweeps x channels per step (~0.3 s per sweep per channel at 4096^2)
-    val, ms, cores, kind, nnz = cpu_reference_run(W, H, args.channels, sweeps, args.steps, min(args.warmup, 1))
+    warmup = max(args.warmup, 3)  # the same clamp as the GPU arm
+    val, ms, cores, kind, nnz = cpu_reference_run(W, H, args.channels, sweeps, args.steps, warmup)
     line = {
         "impl": "reference", "metric": "gauss_seidel_throughput", "value": val, "unit": "Gnnz/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, args.channels),
-                   "sweeps_per_step": sweeps, "nnz": nnz},
+        "config": workload_config(W, H, args.channels, W * H, nnz),
+        "run": {"sweeps_per_step": sweeps, "ordering": "natural (the reference's lexicographic sweep)",
+                "check_every": 1, "sweeps_per_s": sweeps * args.steps / (ms * args.steps * 1e-3)},
         "cpu_baseline": {"value": val, "unit": "Gnnz/s", "cores": cores, "kind": kind,
-                         "sample": "%d sweeps x %d channels per step, %d steps, %dx%d" %
+                         "sample": "%d sweeps x %d channels per step (one channel per thread), %d steps, %dx%d" %
                                    (sweeps, args.channels, args.steps, W, H)},
         "e2e": {"value": val, "unit": "Gnnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -322,6 +333,7 @@ def run_ours(args):
         x_pin = pinned_like(pkg, np.zeros_like(b_host))
         spe = pkg.SparseMatrix(np.float64)
         t_e2e, t_imp, t_setup, steps_e2e = 0.0, 0.0, 0.0, max(1, args.e2e_steps)
+        per_step = []
         st_e = pkg.GsStats()
         for it in range(steps_e2e + 1):
             torch.cuda.synchronize()
@@ -336,11 +348,13 @@ def run_ours(args):
                 t_e2e += t2 - t0
                 t_imp += t1 - t0
                 t_setup += st_e.setup_ms
+                per_step.append((t2 - t0) * 1e3)
         h2d = va.nbytes + ci.nbytes + ro_in.nbytes + b_pin.nbytes
         d2h = x_pin.nbytes
         e2e = {"value": nnz * ch * args.sweeps * steps_e2e / t_e2e / 1e9, "unit": "Gnnz/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / steps_e2e * 1e3,
-               "steps": steps_e2e, "includes": "CSR import (H2D) + ordering analysis + b H2D + sweeps + x D2H",
+               "steps": steps_e2e, "ms_per_step_min": min(per_step), "ms_per_step_median": float(np.median(per_step)),
+               "includes": "CSR import (H2D) + ordering analysis + b H2D + sweeps + x D2H",
                "import_ms": t_imp / steps_e2e * 1e3, "analysis_ms": t_setup / steps_e2e,
                "host_memory": "pinned (gsb_host_alloc)"}
         assert np.array_equal(x_pin, x_host), "e2e result differs from the resident-input result"
@@ -356,11 +370,10 @@ def run_ours(args):
         "metric": "gauss_seidel_throughput", "value": value, "unit": "Gnnz/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2])" % (W, H, ch),
-                   "n": n, "nnz": int(nnz), "sweeps_per_step": args.sweeps, "ordering": "red-black",
-                   "n_colors": info["n_colors"], "check_every": args.check_every,
-                   "l2": "working set %.2f GB per sweep >> 126 MB L2 (no flush needed)" % (abytes / 1e9),
-                   "sweeps_per_s": sweeps_done / (total_ms * 1e-3), "residual_l2": resid},
+        "config": workload_config(W, H, ch, n, nnz),
+        "run": {"sweeps_per_step": args.sweeps, "ordering": "red-black", "n_colors": info["n_colors"],
+                "check_every": args.check_every, "kernel": kernel_used,
+                "sweeps_per_s": sweeps_done / (total_ms * 1e-3), "residual_l2": resid},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_time_to_tol:
@@ -368,11 +381,7 @@ def run_ours(args):
             # release this process' device memory first: the child builds its own matrices
             del sp, b_dev, x_dev
             torch.cuda.empty_cache()
-            ttt = time_to_tol_child(args)
-            if cpu and "sweeps" in ttt:
-                # the reference's CPU solver on the same system, extrapolated from its measured rate (not run: hours)
-                ttt["cpu_estimate_s"] = ttt["nnz"] * ch * ttt["sweeps"] / (cpu["value"] * 1e9)
-            line["time_to_tol"] = ttt
+            line["time_to_tol"] = time_to_tol_child(args)
         except Exception as e:
             line["time_to_tol"] = {"error": repr(e)[:300]}
     print(json.dumps(line))
@@ -399,34 +408,75 @@ def run_time_to_tol(args):
     ro, ci, va, b, pix, colors = wl.masked_poisson_system(mask, guide, target)
     n, nnz = len(pix), len(va)
     t_gen = time.perf_counter() - t0
+    # golden: the REFERENCE's own gaussSeidel (oracle/_ref) run to its stop rule on this very system, generated once
+    # by tests/golden/make_golden_c3.py (tens of CPU-minutes); strided sample of x, sweeps, residual, CPU seconds
+    gold, gmeta = None, None
+    gpath = os.path.join(ROOT, "tests", "golden", "c3_masked_%d" % W)
+    if ch == 3 and os.path.exists(gpath + ".npz") and os.path.exists(gpath + ".json"):
+        gmeta = json.load(open(gpath + ".json"))
+        if gmeta["n"] == n and gmeta["nnz"] == nnz:
+            gold = np.load(gpath + ".npz")
     sm = pkg.SparseMatrix(np.float64)
     sm.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
     sm.analyze(pkg._lib.ORDER_USER, colors)
-    # epsilon: the reference's rule is an absolute L1 norm (v2 :376), whose rounding floor grows with n; at 5 M
-    # unknowns 1e-6 sits at that floor (3e-7 .. 1e-6), so the leg uses 1e-5 = an average update of 2e-12 per unknown
-    eps, cap = 1e-5, 50000
     opts = pkg.SparseMatrix.options(check_every=args.check_every)
     sm.gaussSeidel(b, epsilon=0.0, max_iteration=20, options=opts)  # warm-up: plan, workspaces
-    t1 = time.perf_counter()
-    x = sm.gaussSeidel(b, epsilon=eps, max_iteration=cap, options=opts)
-    wall_ms = (time.perf_counter() - t1) * 1e3
-    st = sm.last_stats
-    sweeps, solve_ms = int(st.sweeps), float(st.solve_ms)
-    last_eps = [float(v) for v in list(st.last_eps)[:ch]]
-    resid = [float(sm.residual(b[c], x[c])) for c in range(ch)]
-    # independent check: conjugate gradients on the same (SPD, Dirichlet) system
-    diffs, iters = [], []
-    for c in range(ch):
-        xc = sm.conjugateGradient(b[c], 1e-6, 3000)
-        iters.append(int(sm.last_iters))
-        diffs.append(float(np.abs(xc - x[c]).max()))
+    tol = 1e-4 * 255.0
+
+    def one(eps, cap):
+        t1 = time.perf_counter()
+        x = sm.gaussSeidel(b, epsilon=eps, max_iteration=cap, options=opts)
+        wall_ms = (time.perf_counter() - t1) * 1e3
+        st = sm.last_stats
+        sweeps, solve_ms = int(st.sweeps), float(st.solve_ms)
+        out = {"epsilon": eps, "max_iteration": cap, "stopped": bool(sweeps < cap), "sweeps": sweeps, "ms": solve_ms,
+               "wall_ms_with_copies": wall_ms,
+               "Gnnz_per_s": nnz * ch * sweeps / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None,
+               "last_eps": [float(v) for v in list(st.last_eps)[:ch]],
+               "residual_l2": [float(sm.residual(b[c], x[c])) for c in range(ch)],
+               "kernel": int(st.kernel_used), "n_colors": int(st.n_colors)}
+        if gold is not None:
+            runs = [r for r in gmeta["runs"] if r["epsilon"] == eps]
+            if runs:
+                idx = gold["index"]
+                diffs, u8_equal = [], True
+                for c in range(ch):
+                    ref = gold["x_eps%g_ch%d" % (eps, c)]
+                    mine = x[c][idx]
+                    diffs.append(float(np.abs(mine - ref).max()))
+                    # write-back as the reference does it: uchar(clamp(x, 0, 255)), truncation (PhotoMontage.cpp:617-626)
+                    u8 = lambda v: np.clip(v, 0.0, 255.0).astype(np.uint8)
+                    u8_equal = u8_equal and bool(np.array_equal(u8(mine), u8(ref)))
+                out.update({"max_abs_vs_reference": max(diffs), "tolerance": tol,
+                            "within_tolerance": bool(max(diffs) <= tol), "u8_equal_on_sample": u8_equal,
+                            "reference_sample_points": int(len(idx)) * ch,
+                            "reference": {"what": gmeta["source"], "sweeps": [r["sweeps"] for r in runs],
+                                          "stopped": [r["stopped"] for r in runs],
+                                          "residual_l2": [r["residual_l2"] for r in runs],
+                                          "cpu_s": max(r["cpu_s"] for r in runs), "cpu_threads": gmeta["host_threads"],
+                                          "oracle_bitwise": all(r["oracle_bitwise"] for r in runs)}})
+                out["speedup_vs_reference_cpu"] = out["reference"]["cpu_s"] / (wall_ms * 1e-3)
+        return out, x
+
+    # epsilon: the reference's rule is an absolute L1 norm (v2 :376) whose rounding floor grows with n; the default
+    # 1e-6 sits near that floor at 5 M unknowns, so the headline leg uses 1e-5 (an average update of 2e-12 per unknown)
+    # and the default is reported beside it
+    cap = int(gmeta["cap"]) if gmeta else 50000
+    main, x = one(1e-5, cap)
+    if gold is None:
+        # no golden for this size: independent check against conjugate gradients on the same (SPD, Dirichlet) system
+        diffs, iters = [], []
+        for c in range(ch):
+            xc = sm.conjugateGradient(b[c], 1e-6, 3000)
+            iters.append(int(sm.last_iters))
+            diffs.append(float(np.abs(xc - x[c]).max()))
+        main.update({"max_abs_vs_cg": max(diffs), "tolerance": tol, "within_tolerance": bool(max(diffs) <= tol),
+                     "cg_iterations": iters, "note": "no reference golden for this size (tests/golden/make_golden_c3.py)"})
     out = {"workload": "dirichlet_masked_blend_%dx%d_x%dch, blob mask 30 %%, thickness <= 48 px (SURVEY 8d C3)" % (W, H, ch),
-           "n": int(n), "nnz": int(nnz), "epsilon": eps, "x0": 1.0, "max_iteration": cap,
-           "stopped": bool(sweeps < cap), "sweeps": sweeps, "ms": solve_ms, "wall_ms_with_copies": wall_ms,
-           "Gnnz_per_s": nnz * ch * sweeps / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None,
-           "last_eps": last_eps, "residual_l2": resid, "kernel": int(st.kernel_used), "n_colors": int(st.n_colors),
-           "max_abs_vs_cg": max(diffs), "tolerance": 1e-4 * 255.0, "within_tolerance": bool(max(diffs) <= 1e-4 * 255.0),
-           "cg_iterations": iters, "host_generation_s": t_gen}
+           "n": int(n), "nnz": int(nnz), "x0": 1.0, "host_generation_s": t_gen}
+    out.update(main)
+    if gold is not None and not args.no_default_eps:
+        out["default_epsilon_1e-6"], _ = one(1e-6, cap)
     print(json.dumps(out))
 
 

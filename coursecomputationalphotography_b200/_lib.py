@@ -116,6 +116,16 @@ SIGNATURES = {
     "gsb_dist_matrix_rows": [_vp, _vp, _vp, _vp, _i64, _i, _i64, _i],
     "gsb_dist_gauss_seidel_dev": [_vp, _vp, _i, _d, _i, C.POINTER(GsOptions), _vp, C.POINTER(GsStats)],
     "gsb_dist_residual_l2_dev": [_vp, _vp, _vp, _dp],
+    "gsb_dist_set_colors": [_vp, _vp, _i64],
+    "gsb_set_devices": [_vp, _i],
+    "gsb_get_devices": [_vp, _i],
+    "gsb_dist_init_local": [C.POINTER(_vp), _vp, _i],
+    "gsb_dist_group_finalize": [_vp],
+    "gsb_dist_group_size": [_vp],
+    "gsb_dist_group_matrix": [_vp, _vp],
+    "gsb_dist_group_poisson": [_vp, _i, _i],
+    "gsb_dist_group_gauss_seidel": [_vp, _vp, _i, _d, _i, C.POINTER(GsOptions), _vp, C.POINTER(GsStats)],
+    "gsb_dist_group_residual_l2": [_vp, _vp, _vp, _dp],
     "gsb_host_alloc": [C.POINTER(_vp), _i64],
     "gsb_host_free": [_vp],
 }

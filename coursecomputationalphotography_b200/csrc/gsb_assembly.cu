@@ -12,6 +12,8 @@ static inline size_t elem_size(int vtype) { return vtype == GSB_I32 ? 4 : 8; }
 
 gsb_matrix::~gsb_matrix() {
     drop_analysis();
+    if (group) gsb_dist_group_finalize(group);
+    group = nullptr;
     delete plan;
     plan = nullptr;
     if (ctl_host) cudaFreeHost(ctl_host);

@@ -16,7 +16,11 @@
 #include <stdlib.h>
 #include <nccl.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 // ---------------------------------------------------------------------------------------------
@@ -81,11 +85,56 @@ static int nccl_load() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Single-process mode (gsb_dist_init_local): the ranks are worker threads of one process, one per device.  What the
+// one-process-per-GPU mode does with NCCL during SETUP (neighbours exchanging id lists and pointers, small
+// all-gathers / all-reduces of host values, barriers) is done here through this shared block: a barrier, a few
+// published pointers per rank, and peer copies (cudaMemcpyPeerAsync) issued by the receiving rank.  The data path of
+// a solve needs none of it: halo values and the stop-rule sums travel as peer stores inside the kernels.
+// ---------------------------------------------------------------------------------------------
+struct LocalGroup {
+    int world = 1;
+    int dev[GSB_DIST_MAX_WORLD] = {0};
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    long long generation = 0;
+    int aborted = 0; // a rank failed: every barrier returns an error instead of waiting for it
+    const void *ptr[GSB_DIST_MAX_WORLD][2] = {{nullptr}};
+    unsigned char blob[GSB_DIST_MAX_WORLD][256];
+    int barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (aborted) return GSB_ERR_NCCL;
+        const long long gen = generation;
+        if (++arrived == world) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+            return GSB_OK;
+        }
+        cv.wait(lk, [&] { return generation != gen || aborted; });
+        return generation != gen ? GSB_OK : GSB_ERR_NCCL;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lk(mu);
+        aborted = 1;
+        cv.notify_all();
+    }
+    void reset() {
+        std::lock_guard<std::mutex> lk(mu);
+        aborted = 0;
+        arrived = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // the per-rank handle
 // ---------------------------------------------------------------------------------------------
 struct gsb_dist {
     int rank = 0, world = 1, device = 0;
     ncclComm_t comm = nullptr;
+    LocalGroup *lg = nullptr;           // single-process mode: shared with the other ranks (owned by the group)
+    DevBuf<unsigned char> colors8;      // optional: colour (0/1) of every GLOBAL row; absent -> pixel parity with W
+    DevBuf<double> stage_b, stage_x;    // single-process mode: device copies of the caller's host b / x slices
     // local system
     bool built = false;
     int64_t row0 = 0, n_global = 0;
@@ -137,6 +186,115 @@ struct gsb_dist {
     bool has_peer(int p) const { return p == 0 ? rank > 0 : rank < world - 1; }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// setup-time communication: NCCL (one process per GPU) or the LocalGroup (single process)
+// ---------------------------------------------------------------------------------------------
+#define GSB_LOCAL(call)                                                                              \
+    do {                                                                                             \
+        if ((call) != GSB_OK) {                                                                      \
+            gsb_set_error("dist (single process): another rank failed, rank %d gives up", d->rank); \
+            return GSB_ERR_NCCL;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+// Device buffers to / from the two neighbours (p = 0: rank - 1, p = 1: rank + 1); zero-length sides are skipped.
+// NCCL: stream-ordered.  Local: on return the data has arrived and the send buffers may be reused.
+static int comm_exchange_neighbours(gsb_dist *d, const void *const send[2], const size_t sbytes[2], void *const recv[2],
+                                    const size_t rbytes[2], cudaStream_t st) {
+    if (d->lg) {
+        LocalGroup *g = d->lg;
+        GSB_CUDA(cudaStreamSynchronize(st)); // what is sent has been produced
+        for (int p = 0; p < 2; ++p) g->ptr[d->rank][p] = send[p];
+        GSB_LOCAL(g->barrier());
+        for (int p = 0; p < 2; ++p)
+            if (d->has_peer(p) && rbytes[p]) {
+                const int q = d->peer_rank(p);
+                GSB_CUDA(cudaMemcpyPeerAsync(recv[p], d->device, g->ptr[q][1 - p], g->dev[q], rbytes[p], st));
+            }
+        GSB_CUDA(cudaStreamSynchronize(st));
+        GSB_LOCAL(g->barrier());
+        return GSB_OK;
+    }
+    GSB_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < 2; ++p)
+        if (d->has_peer(p)) {
+            if (sbytes[p]) GSB_NCCL(g_nccl.Send(send[p], sbytes[p], ncclInt8, d->peer_rank(p), d->comm, st));
+            if (rbytes[p]) GSB_NCCL(g_nccl.Recv(recv[p], rbytes[p], ncclInt8, d->peer_rank(p), d->comm, st));
+        }
+    GSB_NCCL(g_nccl.GroupEnd());
+    return GSB_OK;
+}
+
+// all-gather of a small host struct (bytes <= 256): all[q * bytes ...] = rank q's `mine`
+static int comm_allgather_host(gsb_dist *d, const void *mine, void *all, size_t bytes, cudaStream_t st) {
+    if (d->lg) {
+        LocalGroup *g = d->lg;
+        if (bytes > sizeof(g->blob[0])) return GSB_ERR_ARG;
+        memcpy(g->blob[d->rank], mine, bytes);
+        GSB_LOCAL(g->barrier());
+        for (int q = 0; q < d->world; ++q) memcpy((unsigned char *)all + (size_t)q * bytes, g->blob[q], bytes);
+        GSB_LOCAL(g->barrier());
+        return GSB_OK;
+    }
+    DevBuf<unsigned char> dm, da;
+    GSB_TRY(dm.alloc((int64_t)bytes));
+    GSB_TRY(da.alloc((int64_t)bytes * d->world));
+    GSB_CUDA(cudaMemcpyAsync(dm.p, mine, bytes, cudaMemcpyHostToDevice, st));
+    GSB_NCCL(g_nccl.AllGather(dm.p, da.p, bytes, ncclInt8, d->comm, st));
+    GSB_CUDA(cudaMemcpyAsync(all, da.p, bytes * (size_t)d->world, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+// *v = min over the ranks of *v (the "can everybody do X" agreements)
+static int comm_allreduce_min(gsb_dist *d, int *v, cudaStream_t st) {
+    if (d->world == 1) return GSB_OK;
+    if (d->lg) {
+        int all[GSB_DIST_MAX_WORLD];
+        GSB_TRY(comm_allgather_host(d, v, all, sizeof(int), st));
+        for (int q = 0; q < d->world; ++q) *v = all[q] < *v ? all[q] : *v;
+        return GSB_OK;
+    }
+    DevBuf<int> agree;
+    GSB_TRY(agree.alloc(1));
+    GSB_CUDA(cudaMemcpyAsync(agree.p, v, sizeof(int), cudaMemcpyHostToDevice, st));
+    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
+    GSB_CUDA(cudaMemcpyAsync(v, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+// every rank's stream has reached this point before any rank's stream goes on
+static int comm_stream_barrier(gsb_dist *d, int *scratch_dev, cudaStream_t st) {
+    if (d->world == 1) return GSB_OK;
+    if (d->lg) {
+        GSB_CUDA(cudaStreamSynchronize(st));
+        GSB_LOCAL(d->lg->barrier());
+        return GSB_OK;
+    }
+    GSB_NCCL(g_nccl.AllReduce(scratch_dev, scratch_dev, 1, ncclInt32, ncclMax, d->comm, st));
+    return GSB_OK;
+}
+
+// in place sum of one device double over the ranks (rank order -> the same bits everywhere)
+static int comm_allreduce_sum_dev(gsb_dist *d, double *v_dev, cudaStream_t st) {
+    if (d->world == 1) return GSB_OK;
+    if (d->lg) {
+        double mine = 0.0, all[GSB_DIST_MAX_WORLD];
+        GSB_CUDA(cudaMemcpyAsync(&mine, v_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+        GSB_CUDA(cudaStreamSynchronize(st));
+        GSB_TRY(comm_allgather_host(d, &mine, all, sizeof(double), st));
+        double s = 0.0;
+        for (int q = 0; q < d->world; ++q) s += all[q];
+        GSB_CUDA(cudaMemcpyAsync(v_dev, &s, sizeof(double), cudaMemcpyHostToDevice, st));
+        GSB_CUDA(cudaStreamSynchronize(st));
+        return GSB_OK;
+    }
+    GSB_NCCL(g_nccl.AllReduce(v_dev, v_dev, 1, ncclFloat64, ncclSum, d->comm, st));
+    return GSB_OK;
+}
+
 extern "C" int gsb_dist_unique_id(unsigned char id[GSB_UNIQUE_ID_BYTES]) {
     if (!id) return GSB_ERR_ARG;
     GSB_TRY(nccl_load());
@@ -176,12 +334,14 @@ extern "C" int gsb_dist_finalize(gsb_dist *d) {
     if (!d) return GSB_OK;
     cudaSetDevice(d->device);
     cudaStreamSynchronize(gsb_cur_stream());
-    for (int p = 0; p < 2; ++p) {
-        if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
-        if (d->peer_flags[p]) cudaIpcCloseMemHandle(d->peer_flags[p]);
+    if (!d->lg) { // (single-process mode holds the neighbours' raw pointers: nothing to unmap)
+        for (int p = 0; p < 2; ++p) {
+            if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
+            if (d->peer_flags[p]) cudaIpcCloseMemHandle(d->peer_flags[p]);
+        }
+        for (int q = 0; q < d->world && q < GSB_DIST_MAX_WORLD; ++q)
+            if (q != d->rank && d->peer_box[q]) cudaIpcCloseMemHandle(d->peer_box[q]);
     }
-    for (int q = 0; q < d->world && q < GSB_DIST_MAX_WORLD; ++q)
-        if (q != d->rank && d->peer_box[q]) cudaIpcCloseMemHandle(d->peer_box[q]);
     if (d->comm) g_nccl.CommDestroy(d->comm);
     if (d->ctl_host) cudaFreeHost(d->ctl_host);
     delete d;
@@ -191,7 +351,14 @@ extern "C" int gsb_dist_finalize(gsb_dist *d) {
 // ---------------------------------------------------------------------------------------------
 // local build kernels
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int parity_of(int64_t g, int W) { return (int)(((g % W) + (g / W)) & 1); }
+// colour of GLOBAL row g: the caller's two-colouring when one was given (c8), else pixel parity on a W-wide grid
+struct ColorOf {
+    const unsigned char *c8;
+    int W;
+    __device__ __forceinline__ int operator()(int64_t g) const {
+        return c8 ? (int)c8[g] : (int)(((g % W) + (g / W)) & 1);
+    }
+};
 
 __global__ void __launch_bounds__(256) d_minmax_col(const int *__restrict__ cg, int64_t nnz, int *__restrict__ mm) {
     int lo = INT32_MAX, hi = -1;
@@ -214,33 +381,33 @@ __global__ void __launch_bounds__(256) d_minmax_col(const int *__restrict__ cg, 
 // flags of the ghost columns in the two windows [row0-halo_lo,row0) and [row1,row1+halo_hi), split by colour:
 // flag[(w*2+colour)][j]
 __global__ void __launch_bounds__(256) d_mark_ghosts(const int *__restrict__ cg, int64_t nnz, int64_t row0,
-                                                     int64_t row1, int halo_lo, int halo_hi, int W,
+                                                     int64_t row1, int halo_lo, int halo_hi, ColorOf col,
                                                      int *__restrict__ f_lo0, int *__restrict__ f_lo1,
                                                      int *__restrict__ f_hi0, int *__restrict__ f_hi1) {
     for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * 256) {
         int64_t c = cg[k];
         if (c < row0) {
             int j = (int)(c - (row0 - halo_lo));
-            (parity_of(c, W) ? f_lo1 : f_lo0)[j] = 1;
+            (col(c) ? f_lo1 : f_lo0)[j] = 1;
         } else if (c >= row1) {
             int j = (int)(c - row1);
-            (parity_of(c, W) ? f_hi1 : f_hi0)[j] = 1;
+            (col(c) ? f_hi1 : f_hi0)[j] = 1;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) d_owned_flag(int64_t row0, int n_local, int W, int *__restrict__ f) {
+__global__ void __launch_bounds__(256) d_owned_flag(int64_t row0, int n_local, ColorOf col, int *__restrict__ f) {
     int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < n_local) f[i] = parity_of(row0 + i, W) == 0 ? 1 : 0;
+    if (i < n_local) f[i] = col(row0 + i) == 0 ? 1 : 0;
     if (i == n_local) f[i] = 0;
 }
 
-__global__ void __launch_bounds__(256) d_owned_place(int64_t row0, int n_local, int W, const int *__restrict__ scan0,
+__global__ void __launch_bounds__(256) d_owned_place(int64_t row0, int n_local, ColorOf col, const int *__restrict__ scan0,
                                                      int n0, int *__restrict__ perm, int *__restrict__ iperm) {
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n_local) return;
     int s = scan0[i];
-    int p = parity_of(row0 + i, W) == 0 ? s : n0 + (i - s);
+    int p = col(row0 + i) == 0 ? s : n0 + (i - s);
     perm[p] = i;
     iperm[i] = p;
 }
@@ -275,7 +442,7 @@ __global__ void __launch_bounds__(256) d_perm_len(const int *__restrict__ perm, 
 __global__ void __launch_bounds__(128) d_fill_rows(const int *__restrict__ perm, const int *__restrict__ iperm,
                                                    const int *__restrict__ rp_nat, const int *__restrict__ cg_nat,
                                                    const double *__restrict__ va_nat, int n_local, int64_t row0,
-                                                   int64_t row1, int halo_lo, int W, const int *__restrict__ map_lo,
+                                                   int64_t row1, int halo_lo, ColorOf col, const int *__restrict__ map_lo,
                                                    const int *__restrict__ map_hi, const int *__restrict__ rp,
                                                    int *__restrict__ ci, double *__restrict__ va,
                                                    double *__restrict__ dg, int *__restrict__ bad) {
@@ -284,7 +451,7 @@ __global__ void __launch_bounds__(128) d_fill_rows(const int *__restrict__ perm,
     const int o = perm[p];
     const int src = rp_nat[o], len_all = rp_nat[o + 1] - src, dst = rp[p];
     const int len = rp[p + 1] - dst;
-    const int my_par = parity_of(row0 + o, W);
+    const int my_par = col(row0 + o);
     double d = 0.0;
     int w = 0;
     for (int k = 0; k < len_all; ++k) { // insertion sort on key (colour, global id); ci temporarily holds global ids
@@ -294,12 +461,12 @@ __global__ void __launch_bounds__(128) d_fill_rows(const int *__restrict__ perm,
             d = v;
             continue;
         }
-        int gp = parity_of(g, W);
+        int gp = col(g);
         if (gp == my_par) atomicOr(bad, 1); // parity colouring improper for this matrix
         int q = dst + w;
         while (q > dst) {
             int h = ci[q - 1];
-            int hp = parity_of(h, W);
+            int hp = col(h);
             if (hp < gp || (hp == gp && h <= g)) break;
             ci[q] = h;
             va[q] = va[q - 1];
@@ -386,6 +553,7 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     d->n_global = n_global;
     d->W = W < 1 ? 1 : W;
     W = d->W;
+    const ColorOf col = {d->colors8.n >= n_global ? d->colors8.p : nullptr, W};
     int nnz = 0;
     GSB_CUDA(cudaMemcpyAsync(&nnz, d->nat_rp.p + n_local, sizeof(int), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
@@ -426,17 +594,17 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     }
     if (nnz > 0 && (halo_lo || halo_hi)) {
         d_mark_ghosts<<<gsb_blocks_for(nnz, 256 * 8, gsb_sm_count() * 8), 256, 0, st>>>(
-            d->nat_cg.p, nnz, row0, row1, halo_lo, halo_hi, W, f[0].p, f[1].p, f[2].p, f[3].p);
+            d->nat_cg.p, nnz, row0, row1, halo_lo, halo_hi, col, f[0].p, f[1].p, f[2].p, f[3].p);
         GSB_KERNEL_CHECK();
     }
     GSB_TRY(owned.alloc((int64_t)n_local + 1));
-    d_owned_flag<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(row0, n_local, W, owned.p);
+    d_owned_flag<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(row0, n_local, col, owned.p);
     GSB_KERNEL_CHECK();
     int n0 = 0;
     GSB_TRY(scan_count(owned, n_local, st, &n0));
     GSB_TRY(d->perm.alloc(n_local));
     GSB_TRY(d->iperm.alloc(n_local));
-    d_owned_place<<<(n_local + 255) / 256, 256, 0, st>>>(row0, n_local, W, owned.p, n0, d->perm.p, d->iperm.p);
+    d_owned_place<<<(n_local + 255) / 256, 256, 0, st>>>(row0, n_local, col, owned.p, n0, d->perm.p, d->iperm.p);
     GSB_KERNEL_CHECK();
     d->color_start[0] = 0;
     d->color_start[1] = n0;
@@ -479,14 +647,15 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     GSB_TRY(d->dg.alloc((int64_t)n_local + 8));
     GSB_CUDA(cudaMemsetAsync(mm.p + 2, 0, sizeof(int), st));
     d_fill_rows<<<(n_local + 127) / 128, 128, 0, st>>>(d->perm.p, d->iperm.p, d->nat_rp.p, d->nat_cg.p, d->nat_va.p,
-                                                      n_local, row0, row1, halo_lo, W, map_lo.p, map_hi.p, d->rp.p,
+                                                      n_local, row0, row1, halo_lo, col, map_lo.p, map_hi.p, d->rp.p,
                                                       d->ci.p, d->va.p, d->dg.p, mm.p + 2);
     GSB_KERNEL_CHECK();
     int h_bad = 0;
     GSB_CUDA(cudaMemcpyAsync(&h_bad, mm.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
     if (h_bad) {
-        gsb_set_error("dist: parity colouring with grid width %d is not proper for this matrix", W);
+        gsb_set_error(col.c8 ? "dist: the given two-colouring is not proper for this matrix (grid width %d unused)"
+                             : "dist: parity colouring with grid width %d is not proper for this matrix", W);
         return GSB_ERR_COLORING;
     }
 
@@ -497,13 +666,12 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
     int h_out[4] = {d->need_cnt[0][0], d->need_cnt[0][1], d->need_cnt[1][0], d->need_cnt[1][1]};
     GSB_CUDA(cudaMemcpyAsync(cnt_out.p, h_out, sizeof(h_out), cudaMemcpyHostToDevice, st));
     GSB_CUDA(cudaMemsetAsync(cnt_in.p, 0, 4 * sizeof(int), st));
-    GSB_NCCL(g_nccl.GroupStart());
-    for (int p = 0; p < 2; ++p)
-        if (d->has_peer(p)) {
-            GSB_NCCL(g_nccl.Send(cnt_out.p + 2 * p, 2, ncclInt32, d->peer_rank(p), d->comm, st));
-            GSB_NCCL(g_nccl.Recv(cnt_in.p + 2 * p, 2, ncclInt32, d->peer_rank(p), d->comm, st));
-        }
-    GSB_NCCL(g_nccl.GroupEnd());
+    {
+        const void *sp[2] = {cnt_out.p, cnt_out.p + 2};
+        void *rp2[2] = {cnt_in.p, cnt_in.p + 2};
+        const size_t nb[2] = {2 * sizeof(int), 2 * sizeof(int)};
+        GSB_TRY(comm_exchange_neighbours(d, sp, nb, rp2, nb, st));
+    }
     int h_in[4];
     GSB_CUDA(cudaMemcpyAsync(h_in, cnt_in.p, sizeof(h_in), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
@@ -515,16 +683,13 @@ static int dist_build(gsb_dist *d, int64_t row0, int n_local, int64_t n_global, 
             GSB_TRY(d->send_idx[p][c].alloc(d->send_cnt[p][c]));
             GSB_TRY(d->sendbuf[p][c].alloc((int64_t)d->send_cnt[p][c] * GSB_MAX_RHS));
         }
-    GSB_NCCL(g_nccl.GroupStart());
-    for (int p = 0; p < 2; ++p)
-        if (d->has_peer(p))
-            for (int c = 0; c < 2; ++c) {
-                if (d->need_cnt[p][c])
-                    GSB_NCCL(g_nccl.Send(need_ids[p][c].p, d->need_cnt[p][c], ncclInt32, d->peer_rank(p), d->comm, st));
-                if (d->send_cnt[p][c])
-                    GSB_NCCL(g_nccl.Recv(req_ids[p][c].p, d->send_cnt[p][c], ncclInt32, d->peer_rank(p), d->comm, st));
-            }
-    GSB_NCCL(g_nccl.GroupEnd());
+    for (int c = 0; c < 2; ++c) { // id lists, one colour at a time: what this rank reads <-> what it has to provide
+        const void *sp[2] = {need_ids[0][c].p, need_ids[1][c].p};
+        void *rp2[2] = {req_ids[0][c].p, req_ids[1][c].p};
+        const size_t sb[2] = {sizeof(int) * (size_t)d->need_cnt[0][c], sizeof(int) * (size_t)d->need_cnt[1][c]};
+        const size_t rb[2] = {sizeof(int) * (size_t)d->send_cnt[0][c], sizeof(int) * (size_t)d->send_cnt[1][c]};
+        GSB_TRY(comm_exchange_neighbours(d, sp, sb, rp2, rb, st));
+    }
     GSB_CUDA(cudaMemsetAsync(mm.p + 3, 0, sizeof(int), st));
     for (int p = 0; p < 2; ++p)
         for (int c = 0; c < 2; ++c)
@@ -574,6 +739,20 @@ extern "C" int gsb_dist_poisson_strip(gsb_dist *d, int W, int H, int y0, int y1)
     return dist_build(d, p0, n_local, n_global, W);
 }
 
+extern "C" int gsb_dist_set_colors(gsb_dist *d, const unsigned char *colors, int64_t n_global) {
+    if (!d || n_global < 0 || (n_global > 0 && !colors)) return GSB_ERR_ARG;
+    GSB_TRY(gsb_set_device(d->device));
+    cudaStream_t st = gsb_cur_stream();
+    if (n_global == 0) {
+        d->colors8.release();
+        return GSB_OK;
+    }
+    GSB_TRY(d->colors8.alloc(n_global));
+    GSB_CUDA(cudaMemcpyAsync(d->colors8.p, colors, (size_t)n_global, cudaMemcpyHostToDevice, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
 extern "C" int gsb_dist_matrix_rows(gsb_dist *d, const double *values, const int *row_off, const int *col_idx,
                                     int64_t row0, int n_local, int64_t n_global, int grid_width) {
     if (!d || !row_off || n_local <= 0 || row0 < 0 || row0 + n_local > n_global || grid_width < 1) {
@@ -605,6 +784,7 @@ extern "C" int gsb_dist_matrix_rows(gsb_dist *d, const double *values, const int
 // ---------------------------------------------------------------------------------------------
 struct PeerHello { // what a rank tells a neighbour so that it can write this rank's ghost slots
     cudaIpcMemHandle_t hx, hf;
+    void *raw_x, *raw_f; // single-process mode: the pointers themselves
     long long ld;
     int gs[2];
     int ok;
@@ -619,35 +799,35 @@ static int dist_box_setup(gsb_dist *d, cudaStream_t st) {
         d->box_failed = true;
         return GSB_OK;
     }
+    // one dedicated allocation, padded to the 2 MiB granule the driver sub-allocates from: the IPC handle then
+    // exports this box and nothing else
     const int64_t box_doubles = (int64_t)2 * d->world * GSB_MAX_RHS + d->world + 8; // flags: 2 * world ints
+    const int64_t alloc_doubles = ((box_doubles * 8 + (2 << 20) - 1) / (2 << 20)) * ((2 << 20) / 8);
     int ok = 1;
-    if (d->eps_box.alloc(box_doubles) != GSB_OK) ok = 0;
-    cudaIpcMemHandle_t mine;
-    memset(&mine, 0, sizeof(mine));
+    if (d->eps_box.alloc(alloc_doubles) != GSB_OK) ok = 0;
+    struct Hello { cudaIpcMemHandle_t h; void *raw; int ok; int pad; };
+    Hello hm;
+    memset(&hm, 0, sizeof(hm));
     if (ok) {
         GSB_CUDA(cudaMemsetAsync(d->eps_box.p, 0, sizeof(double) * (size_t)box_doubles, st));
-        if (cudaIpcGetMemHandle(&mine, d->eps_box.p) != cudaSuccess) {
+        GSB_CUDA(cudaStreamSynchronize(st));
+        hm.raw = d->eps_box.p;
+        if (!d->lg && cudaIpcGetMemHandle(&hm.h, d->eps_box.p) != cudaSuccess) {
             cudaGetLastError();
             ok = 0;
         }
     }
-    struct Hello { cudaIpcMemHandle_t h; int ok; int pad[3]; };
-    Hello hm;
-    memset(&hm, 0, sizeof(hm));
-    hm.h = mine;
     hm.ok = ok;
     std::vector<Hello> all((size_t)d->world);
-    DevBuf<unsigned char> dm, da;
-    GSB_TRY(dm.alloc(sizeof(Hello)));
-    GSB_TRY(da.alloc((int64_t)sizeof(Hello) * d->world));
-    GSB_CUDA(cudaMemcpyAsync(dm.p, &hm, sizeof(Hello), cudaMemcpyHostToDevice, st));
-    GSB_NCCL(g_nccl.AllGather(dm.p, da.p, sizeof(Hello), ncclInt8, d->comm, st));
-    GSB_CUDA(cudaMemcpyAsync(all.data(), da.p, sizeof(Hello) * (size_t)d->world, cudaMemcpyDeviceToHost, st));
-    GSB_CUDA(cudaStreamSynchronize(st));
+    GSB_TRY(comm_allgather_host(d, &hm, all.data(), sizeof(Hello), st));
     for (int q = 0; q < d->world; ++q) ok = ok && all[(size_t)q].ok;
     for (int q = 0; q < d->world && ok; ++q) {
         if (q == d->rank) {
             d->peer_box[q] = d->eps_box.p;
+            continue;
+        }
+        if (d->lg) { // same process: the other rank's pointer is valid here once peer access is on
+            d->peer_box[q] = (double *)all[(size_t)q].raw;
             continue;
         }
         void *pb = nullptr;
@@ -658,16 +838,13 @@ static int dist_box_setup(gsb_dist *d, cudaStream_t st) {
         }
         d->peer_box[q] = (double *)pb;
     }
-    DevBuf<int> agree;
-    GSB_TRY(agree.alloc(1));
-    GSB_CUDA(cudaMemcpyAsync(agree.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
-    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
-    GSB_CUDA(cudaMemcpyAsync(&ok, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    GSB_CUDA(cudaStreamSynchronize(st));
+    GSB_TRY(comm_allreduce_min(d, &ok, st));
     if (ok)
         d->box_ready = true;
-    else
+    else {
         d->box_failed = true;
+        fprintf(stderr, "libgsb200: rank %d: stop-rule exchange falls back to ncclAllReduce (peer mapping failed)\n", d->rank);
+    }
     return GSB_OK;
 }
 
@@ -675,25 +852,44 @@ static int dist_box_setup(gsb_dist *d, cudaStream_t st) {
 static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
     if (d->world == 1 || d->peer_failed) return GSB_OK;
     if (!d->flags.p) {
-        GSB_TRY(d->flags.alloc(8));
+        // a dedicated 2 MiB allocation: what the IPC handle exports is these flag words only
+        GSB_TRY(d->flags.alloc((2 << 20) / (int64_t)sizeof(int)));
         GSB_CUDA(cudaMemsetAsync(d->flags.p, 0, 8 * sizeof(int), st));
     }
-    for (int p = 0; p < 2; ++p) {
-        if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
-        d->peer_x[p] = nullptr;
-    }
+    if (!d->lg)
+        for (int p = 0; p < 2; ++p) {
+            if (d->peer_x[p]) cudaIpcCloseMemHandle(d->peer_x[p]);
+            d->peer_x[p] = nullptr;
+        }
     PeerHello mine[2], theirs[2];
     memset(mine, 0, sizeof(mine));
     memset(theirs, 0, sizeof(theirs));
     int ok = 1;
     cudaIpcMemHandle_t hx, hf;
-    if (cudaIpcGetMemHandle(&hx, d->xw.p) != cudaSuccess || cudaIpcGetMemHandle(&hf, d->flags.p) != cudaSuccess) {
+    memset(&hx, 0, sizeof(hx));
+    memset(&hf, 0, sizeof(hf));
+    if (d->lg) {
+        // same process: direct peer access between the devices replaces the IPC mappings
+        for (int p = 0; p < 2 && ok; ++p) {
+            if (!d->has_peer(p)) continue;
+            const int pd = d->lg->dev[d->peer_rank(p)];
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, d->device, pd) != cudaSuccess || !can) ok = 0;
+            if (ok) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+            }
+        }
+    } else if (cudaIpcGetMemHandle(&hx, d->xw.p) != cudaSuccess || cudaIpcGetMemHandle(&hf, d->flags.p) != cudaSuccess) {
         cudaGetLastError();
         ok = 0;
     }
     for (int p = 0; p < 2; ++p) {
         mine[p].hx = hx;
         mine[p].hf = hf;
+        mine[p].raw_x = d->xw.p;
+        mine[p].raw_f = d->flags.p;
         mine[p].ld = d->ld;
         mine[p].gs[0] = d->ghost_start[p][0];
         mine[p].gs[1] = d->ghost_start[p][1];
@@ -703,13 +899,12 @@ static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
     GSB_TRY(dm.alloc(2 * sizeof(PeerHello)));
     GSB_TRY(dt.alloc(2 * sizeof(PeerHello)));
     GSB_CUDA(cudaMemcpyAsync(dm.p, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
-    GSB_NCCL(g_nccl.GroupStart());
-    for (int p = 0; p < 2; ++p)
-        if (d->has_peer(p)) {
-            GSB_NCCL(g_nccl.Send(dm.p + p * sizeof(PeerHello), sizeof(PeerHello), ncclInt8, d->peer_rank(p), d->comm, st));
-            GSB_NCCL(g_nccl.Recv(dt.p + p * sizeof(PeerHello), sizeof(PeerHello), ncclInt8, d->peer_rank(p), d->comm, st));
-        }
-    GSB_NCCL(g_nccl.GroupEnd());
+    {
+        const void *sp[2] = {dm.p, dm.p + sizeof(PeerHello)};
+        void *rp2[2] = {dt.p, dt.p + sizeof(PeerHello)};
+        const size_t nb[2] = {sizeof(PeerHello), sizeof(PeerHello)};
+        GSB_TRY(comm_exchange_neighbours(d, sp, nb, rp2, nb, st));
+    }
     GSB_CUDA(cudaMemcpyAsync(theirs, dt.p, sizeof(theirs), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
     for (int p = 0; p < 2 && ok; ++p) {
@@ -718,20 +913,25 @@ static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
             ok = 0;
             break;
         }
-        void *px = nullptr, *pf = nullptr;
-        if (cudaIpcOpenMemHandle(&px, theirs[p].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            ok = 0;
-            break;
-        }
-        d->peer_x[p] = (double *)px;
-        if (!d->peer_flags[p]) {
-            if (cudaIpcOpenMemHandle(&pf, theirs[p].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        if (d->lg) {
+            d->peer_x[p] = (double *)theirs[p].raw_x;
+            d->peer_flags[p] = (int *)theirs[p].raw_f;
+        } else {
+            void *px = nullptr, *pf = nullptr;
+            if (cudaIpcOpenMemHandle(&px, theirs[p].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
                 ok = 0;
                 break;
             }
-            d->peer_flags[p] = (int *)pf;
+            d->peer_x[p] = (double *)px;
+            if (!d->peer_flags[p]) {
+                if (cudaIpcOpenMemHandle(&pf, theirs[p].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = 0;
+                    break;
+                }
+                d->peer_flags[p] = (int *)pf;
+            }
         }
         d->peer_ld[p] = theirs[p].ld;
         // this rank is the neighbour's other-side peer: it writes the ghost range the neighbour keeps for it
@@ -739,15 +939,11 @@ static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
         d->peer_gs[p][1] = theirs[p].gs[1];
     }
     // all ranks must agree on the transport: one failure anywhere keeps everybody on NCCL send/recv
-    DevBuf<int> agree;
-    GSB_TRY(agree.alloc(1));
-    GSB_CUDA(cudaMemcpyAsync(agree.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
-    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
-    GSB_CUDA(cudaMemcpyAsync(&ok, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    GSB_CUDA(cudaStreamSynchronize(st));
+    GSB_TRY(comm_allreduce_min(d, &ok, st));
     if (!ok) {
         d->peer_failed = true;
         d->peer_ready = false;
+        fprintf(stderr, "libgsb200: rank %d: halo exchange falls back to ncclSend/ncclRecv (peer mapping failed)\n", d->rank);
         return GSB_OK;
     }
     d->peer_ready = true;
@@ -849,6 +1045,21 @@ static int dist_exchange(gsb_dist *d, int c, int nrhs, cudaStream_t st, int64_t 
         }
         any = any || d->send_cnt[p][c] || d->need_cnt[p][c];
     }
+    if (d->lg) { // single-process mode (the residual only; solves always use the fused peer stores)
+        for (int r = 0; r < nrhs; ++r) {
+            const void *sp[2];
+            void *rp2[2];
+            size_t sb[2], rb[2];
+            for (int p = 0; p < 2; ++p) {
+                sp[p] = d->sendbuf[p][c].p + (size_t)r * d->send_cnt[p][c];
+                rp2[p] = d->xw.p + r * d->ld + d->ghost_start[p][c];
+                sb[p] = sizeof(double) * (size_t)d->send_cnt[p][c];
+                rb[p] = sizeof(double) * (size_t)d->need_cnt[p][c];
+            }
+            GSB_TRY(comm_exchange_neighbours(d, sp, sb, rp2, rb, st));
+        }
+        return GSB_OK;
+    }
     if (!any) return GSB_OK;
     GSB_NCCL(g_nccl.GroupStart());
     for (int p = 0; p < 2; ++p) {
@@ -936,7 +1147,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     {
         bool want = d->world > 1 && !d->peer_failed;
         const char *e = getenv("GSB_DIST_TRANSPORT");
-        if (e && strcmp(e, "nccl") == 0) want = false;
+        if (e && strcmp(e, "nccl") == 0 && !d->lg) want = false;
         use_peer = false;
         if (want) {
             if (!d->peer_ready) GSB_TRY(dist_peer_setup(d, st)); // collective; agrees on peer_failed itself
@@ -950,12 +1161,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
                         for (int c = 0; c < 2; ++c)
                             if (d->interior_base[c] < 0 || d->n_halo_tiles[c] > GSB_HALO_TILES_MAX) cap = 0;
                     }
-                    DevBuf<int> agree;
-                    GSB_TRY(agree.alloc(1));
-                    GSB_CUDA(cudaMemcpyAsync(agree.p, &cap, sizeof(int), cudaMemcpyHostToDevice, st));
-                    GSB_NCCL(g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, d->comm, st));
-                    GSB_CUDA(cudaMemcpyAsync(&cap, agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-                    GSB_CUDA(cudaStreamSynchronize(st));
+                    GSB_TRY(comm_allreduce_min(d, &cap, st));
                     d->halo_agreed = cap != 0;
                     d->halo_agreed_valid = true;
                 }
@@ -977,16 +1183,25 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             force_halo = d->halo_meta && d->interior_base[0] >= 0 && d->interior_base[1] >= 0;
         }
     }
+    if (d->lg && d->world > 1 && !use_peer) {
+        gsb_set_error("dist (single process): rank %d cannot reach its neighbours' memory (peer access) or the strips "
+                      "are too thin for the fused halo exchange; there is no NCCL transport in this mode", d->rank);
+        return GSB_ERR_NCCL;
+    }
     d->used_peer = use_peer ? 1 : 0;
     // stop-rule all-reduce: fused into the end-of-sweep kernel over peer memory, or fold + ncclAllReduce + decide
     bool fused_eps = use_peer;
     {
         const char *e = getenv("GSB_DIST_EPS");
-        if (e && strcmp(e, "nccl") == 0) fused_eps = false;
+        if (e && strcmp(e, "nccl") == 0 && !d->lg) fused_eps = false;
     }
     if (fused_eps) {
         GSB_TRY(dist_box_setup(d, st));
         fused_eps = d->box_ready;
+    }
+    if (d->lg && d->world > 1 && !fused_eps) {
+        gsb_set_error("dist (single process): the stop-rule boxes could not be set up on rank %d", d->rank);
+        return GSB_ERR_NCCL;
     }
     d->used_fused_eps = fused_eps ? 1 : 0;
     if (!d->ctl.p) GSB_TRY(d->ctl.alloc(sizeof(GsCtl)));
@@ -1015,7 +1230,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
     const long long epoch_base = d->epoch;
     if (use_peer) {
         // every rank has refilled its ghosts (stream order) before any neighbour starts pushing into them
-        GSB_NCCL(g_nccl.AllReduce(ctl, ctl, 1, ncclInt32, ncclMax, d->comm, st));
+        GSB_TRY(comm_stream_barrier(d, (int *)ctl, st));
     }
     cudaEvent_t ev0, ev1;
     GSB_CUDA(cudaEventCreate(&ev0));
@@ -1207,10 +1422,322 @@ extern "C" int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const 
     d_resid<<<gsb_blocks_for(n_local, 256, gsb_sm_count() * 8), 256, 0, st>>>(d->rp.p, d->ci.p, d->va.p, d->dg.p, d->bw.p,
                                                                              d->xw.p, n_local, acc.p);
     GSB_KERNEL_CHECK();
-    if (d->world > 1) GSB_NCCL(g_nccl.AllReduce(acc.p, acc.p, 1, ncclFloat64, ncclSum, d->comm, st));
+    GSB_TRY(comm_allreduce_sum_dev(d, acc.p, st));
     double h = 0.0;
     GSB_CUDA(cudaMemcpyAsync(&h, acc.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
     *out = sqrt(h);
     return GSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-process multi-device solve (gsb_dist_init_local): N devices of this box, one row strip and one worker
+// thread each, behind one blocking call -- the reference's call model (one host thread, synchronous solve,
+// project/src/PhotoMontage/main.cpp:581).  No NCCL, no torch, no IPC: setup talks through the LocalGroup, the data
+// path is peer stores inside the kernels.  Worker threads (rather than the calling thread enqueuing on N streams)
+// because a 4096^2 strip of an 8-GPU solve finishes a sweep in ~70 us, i.e. 24 launches per 70 us over 8 devices --
+// more than one thread can enqueue; a thread per device also reuses the per-rank code of the multi-process mode
+// unchanged, so both modes produce the same bits.
+// ---------------------------------------------------------------------------------------------
+struct gsb_dist_group {
+    int n = 0;
+    gsb_dist *rank[GSB_DIST_MAX_WORLD] = {nullptr};
+    LocalGroup lg;
+    int64_t n_global = 0;
+    int64_t row0[GSB_DIST_MAX_WORLD + 1] = {0}; // strip r owns global rows [row0[r], row0[r+1])
+    bool built = false;
+};
+
+// runs f(rank) on one thread per device; first failure wins (its message becomes the caller's last error)
+template <typename F>
+static int group_run(gsb_dist_group *g, F f) {
+    std::vector<int> rc((size_t)g->n, GSB_OK);
+    std::vector<std::string> msg((size_t)g->n);
+    g->lg.reset();
+    auto body = [&](int r) {
+        int s = gsb_set_device(g->rank[r]->device);
+        if (s == GSB_OK) s = f(r);
+        rc[(size_t)r] = s;
+        if (s != GSB_OK) {
+            msg[(size_t)r] = gsb_last_error();
+            g->lg.abort(); // the other ranks' barriers return instead of waiting for this one
+        }
+    };
+    if (g->n == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int r = 0; r < g->n; ++r) th.emplace_back(body, r);
+        for (auto &t : th) t.join();
+    }
+    // report the failure that caused the abort, not the "another rank failed" echoes of the others
+    int first = -1;
+    for (int r = 0; r < g->n; ++r)
+        if (rc[(size_t)r] != GSB_OK && (first < 0 || (msg[(size_t)first].find("another rank failed") != std::string::npos &&
+                                                     msg[(size_t)r].find("another rank failed") == std::string::npos)))
+            first = r;
+    if (first >= 0) {
+        gsb_set_error("rank %d (device %d): %s", first, g->rank[first]->device, msg[(size_t)first].c_str());
+        return rc[(size_t)first];
+    }
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_init_local(gsb_dist_group **out, const int *devices, int n) {
+    if (!out || !devices || n < 1 || n > GSB_DIST_MAX_WORLD) {
+        gsb_set_error("dist_init_local: need 1..%d devices", GSB_DIST_MAX_WORLD);
+        return GSB_ERR_ARG;
+    }
+    int count = 0;
+    gsb_device_count(&count);
+    if (count <= 0) {
+        gsb_set_error("no CUDA device visible: libgsb200 has no CPU fallback");
+        return GSB_ERR_NO_DEVICE;
+    }
+    for (int r = 0; r < n; ++r) {
+        if (devices[r] < 0 || devices[r] >= count) {
+            gsb_set_error("dist_init_local: device %d of %d visible", devices[r], count);
+            return GSB_ERR_ARG;
+        }
+        for (int q = 0; q < r; ++q)
+            if (devices[q] == devices[r]) {
+                gsb_set_error("dist_init_local: device %d listed twice", devices[r]);
+                return GSB_ERR_ARG;
+            }
+    }
+    gsb_dist_group *g = new (std::nothrow) gsb_dist_group();
+    if (!g) return GSB_ERR_ALLOC;
+    g->n = n;
+    g->lg.world = n;
+    for (int r = 0; r < n; ++r) {
+        gsb_dist *d = new (std::nothrow) gsb_dist();
+        if (!d) {
+            for (int q = 0; q < r; ++q) delete g->rank[q];
+            delete g;
+            return GSB_ERR_ALLOC;
+        }
+        d->rank = r;
+        d->world = n;
+        d->device = devices[r];
+        d->lg = &g->lg;
+        g->lg.dev[r] = devices[r];
+        g->rank[r] = d;
+    }
+    *out = g;
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_group_finalize(gsb_dist_group *g) {
+    if (!g) return GSB_OK;
+    const int keep = gsb_current_device();
+    for (int r = 0; r < g->n; ++r) gsb_dist_finalize(g->rank[r]);
+    gsb_set_device(keep);
+    delete g;
+    return GSB_OK;
+}
+
+extern "C" int gsb_dist_group_size(const gsb_dist_group *g) { return g ? g->n : 0; }
+
+// config C4: the reference-faithful full-grid Poisson system, every strip generated on its own device
+extern "C" int gsb_dist_group_poisson(gsb_dist_group *g, int W, int H) {
+    if (!g || W < 1 || H < g->n) {
+        gsb_set_error("dist_group_poisson: bad argument (need at least one image row per device)");
+        return GSB_ERR_ARG;
+    }
+    const int keep = gsb_current_device();
+    g->built = false;
+    g->n_global = (int64_t)W * H;
+    int y = 0;
+    std::vector<int> y0((size_t)g->n + 1);
+    for (int r = 0; r < g->n; ++r) { // as even as possible (workloads.strip_bounds)
+        y0[(size_t)r] = y;
+        y += H / g->n + (r < H % g->n ? 1 : 0);
+        g->row0[r] = (int64_t)y0[(size_t)r] * W;
+    }
+    y0[(size_t)g->n] = H;
+    g->row0[g->n] = g->n_global;
+    for (int r = 0; r < g->n; ++r) g->rank[r]->colors8.release(); // pixel parity
+    const int s = group_run(g, [&](int r) { return gsb_dist_poisson_strip(g->rank[r], W, H, y0[(size_t)r], y0[(size_t)r + 1]); });
+    gsb_set_device(keep);
+    g->built = s == GSB_OK;
+    return s;
+}
+
+// rows [r0, r0 + n_local) of a slack CSR -> compact CSR (local offsets)
+__global__ void __launch_bounds__(256) d_strip_row_len(const int *__restrict__ row_nnz, int64_t r0, int n_local,
+                                                       int *__restrict__ len) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n_local) len[i] = row_nnz[r0 + i];
+    if (i == n_local) len[i] = 0;
+}
+__global__ void __launch_bounds__(256) d_strip_copy_rows(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                         const int *__restrict__ row_begin, int64_t r0, int n_local,
+                                                         const int *__restrict__ rp, int *__restrict__ cg,
+                                                         double *__restrict__ va) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_local) return;
+    const int src = row_begin[r0 + i], dst = rp[i], len = rp[i + 1] - dst;
+    for (int k = 0; k < len; ++k) {
+        cg[dst + k] = cols[src + k];
+        va[dst + k] = vals[src + k];
+    }
+}
+__global__ void __launch_bounds__(256) d_colors_to_u8(const int *__restrict__ c, int64_t n, unsigned char *__restrict__ o) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) o[i] = (unsigned char)c[i];
+}
+
+// Shard an assembled matrix (any entry point: initializeFromVector / Triplets / EigenRowMajor) by rows over the
+// group's devices.  Needs the two-colouring of the analysis (red-black probe or the caller's colours); matrices that
+// take more colours do not shard this way (replicas only).
+extern "C" int gsb_dist_group_matrix(gsb_dist_group *g, gsb_matrix *m) {
+    if (!g || !m) return GSB_ERR_ARG;
+    if (!m->has_layout || m->n_rows != m->n_cols) {
+        gsb_set_error("dist_group_matrix: needs an assembled square matrix");
+        return GSB_ERR_STATE;
+    }
+    const int keep = gsb_current_device();
+    GSB_TRY(gsb_set_device(m->device));
+    if (!m->analyzed) GSB_TRY(gsb_matrix_analyze(m, GSB_ORDER_AUTO, nullptr));
+    if (m->n_colors > 2) {
+        gsb_set_error("dist_group_matrix: the ordering needs %d colours; row strips need a two-colouring (replicas only)",
+                      m->n_colors);
+        gsb_set_device(keep);
+        return GSB_ERR_COLORING;
+    }
+    const int64_t n = m->n_rows;
+    if (n < g->n) {
+        gsb_set_error("dist_group_matrix: %lld rows over %d devices", (long long)n, g->n);
+        gsb_set_device(keep);
+        return GSB_ERR_ARG;
+    }
+    g->built = false;
+    g->n_global = n;
+    // partition: whole image rows when the matrix is a W-wide grid, else equal row counts
+    const int W = m->grid_width > 1 && n % m->grid_width == 0 && n / m->grid_width >= g->n ? m->grid_width : 1;
+    const int64_t units = n / W;
+    int64_t u = 0;
+    for (int r = 0; r < g->n; ++r) {
+        g->row0[r] = u * W;
+        u += units / g->n + (r < units % g->n ? 1 : 0);
+    }
+    g->row0[g->n] = n;
+    cudaStream_t st = gsb_cur_stream();
+    // the colour of every global row as bytes, once on the matrix' device, then copied to every rank's device
+    DevBuf<unsigned char> c8;
+    GSB_TRY(c8.alloc(n));
+    d_colors_to_u8<<<gsb_blocks_for(n, 256), 256, 0, st>>>(m->colors.p, n, c8.p);
+    GSB_KERNEL_CHECK();
+    DevBuf<int> rp;
+    DevBuf<int> cg;
+    DevBuf<double> va;
+    int status = GSB_OK;
+    for (int r = 0; r < g->n && status == GSB_OK; ++r) {
+        gsb_dist *d = g->rank[r];
+        const int64_t r0 = g->row0[r];
+        const int n_local = (int)(g->row0[r + 1] - r0);
+        auto step = [&]() -> int {
+            GSB_TRY(gsb_set_device(m->device));
+            GSB_TRY(rp.alloc((int64_t)n_local + 1));
+            d_strip_row_len<<<(n_local + 1 + 255) / 256, 256, 0, st>>>(m->row_nnz.p, r0, n_local, rp.p);
+            GSB_KERNEL_CHECK();
+            GSB_TRY(gsb_exclusive_scan_i32(rp.p, rp.p, (int64_t)n_local + 1, nullptr, st));
+            int nnz = 0;
+            GSB_CUDA(cudaMemcpyAsync(&nnz, rp.p + n_local, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GSB_CUDA(cudaStreamSynchronize(st));
+            GSB_TRY(cg.alloc(nnz));
+            GSB_TRY(va.alloc(nnz));
+            d_strip_copy_rows<<<(n_local + 255) / 256, 256, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, r0, n_local,
+                                                                    rp.p, cg.p, va.p);
+            GSB_KERNEL_CHECK();
+            GSB_CUDA(cudaStreamSynchronize(st));
+            GSB_TRY(gsb_set_device(d->device));
+            GSB_TRY(d->nat_rp.alloc((int64_t)n_local + 1));
+            GSB_TRY(d->nat_cg.alloc(nnz));
+            GSB_TRY(d->nat_va.alloc(nnz));
+            GSB_TRY(d->colors8.alloc(n));
+            GSB_CUDA(cudaMemcpyPeer(d->nat_rp.p, d->device, rp.p, m->device, sizeof(int) * (size_t)(n_local + 1)));
+            if (nnz > 0) {
+                GSB_CUDA(cudaMemcpyPeer(d->nat_cg.p, d->device, cg.p, m->device, sizeof(int) * (size_t)nnz));
+                GSB_CUDA(cudaMemcpyPeer(d->nat_va.p, d->device, va.p, m->device, sizeof(double) * (size_t)nnz));
+            }
+            GSB_CUDA(cudaMemcpyPeer(d->colors8.p, d->device, c8.p, m->device, (size_t)n));
+            return GSB_OK;
+        };
+        status = step();
+    }
+    gsb_set_device(m->device);
+    rp.release();
+    cg.release();
+    va.release();
+    c8.release();
+    if (status == GSB_OK)
+        status = group_run(g, [&](int r) {
+            return dist_build(g->rank[r], g->row0[r], (int)(g->row0[r + 1] - g->row0[r]), n, W);
+        });
+    gsb_set_device(keep);
+    g->built = status == GSB_OK;
+    return status;
+}
+
+// b / x: HOST vectors, nrhs x n_global doubles (one vector after another), as gsb_gauss_seidel takes them
+extern "C" int gsb_dist_group_gauss_seidel(gsb_dist_group *g, const double *b, int nrhs, double epsilon,
+                                           int max_iteration, const gsb_gs_options *opts, double *x_out,
+                                           gsb_gs_stats *stats) {
+    if (!g || !b || !x_out || nrhs < 1 || nrhs > GSB_MAX_RHS) return GSB_ERR_ARG;
+    if (!g->built) {
+        gsb_set_error("dist_group_gauss_seidel: no matrix on the group yet");
+        return GSB_ERR_STATE;
+    }
+    const int keep = gsb_current_device();
+    std::vector<gsb_gs_stats> st_r((size_t)g->n);
+    const int64_t n = g->n_global;
+    const int s = group_run(g, [&](int r) -> int {
+        gsb_dist *d = g->rank[r];
+        cudaStream_t st = gsb_cur_stream();
+        const int64_t r0 = g->row0[r];
+        const int n_local = d->n_local;
+        GSB_TRY(d->stage_b.alloc((int64_t)n_local * nrhs));
+        GSB_TRY(d->stage_x.alloc((int64_t)n_local * nrhs));
+        for (int c = 0; c < nrhs; ++c)
+            GSB_CUDA(cudaMemcpyAsync(d->stage_b.p + (size_t)c * n_local, b + (size_t)c * n + r0, sizeof(double) * (size_t)n_local,
+                                     cudaMemcpyHostToDevice, st));
+        GSB_TRY(gsb_dist_gauss_seidel_dev(d, d->stage_b.p, nrhs, epsilon, max_iteration, opts, d->stage_x.p, &st_r[(size_t)r]));
+        for (int c = 0; c < nrhs; ++c)
+            GSB_CUDA(cudaMemcpyAsync(x_out + (size_t)c * n + r0, d->stage_x.p + (size_t)c * n_local,
+                                     sizeof(double) * (size_t)n_local, cudaMemcpyDeviceToHost, st));
+        GSB_CUDA(cudaStreamSynchronize(st));
+        return GSB_OK;
+    });
+    gsb_set_device(keep);
+    if (s != GSB_OK) return s;
+    if (stats) {
+        *stats = st_r[0];
+        for (int r = 1; r < g->n; ++r) { // slowest rank's device time, all ranks' launches
+            if (st_r[(size_t)r].solve_ms > stats->solve_ms) stats->solve_ms = st_r[(size_t)r].solve_ms;
+            stats->kernel_launches += st_r[(size_t)r].kernel_launches;
+        }
+    }
+    return GSB_OK;
+}
+
+// ||b - A x||_2 over all strips (host vectors of n_global doubles)
+extern "C" int gsb_dist_group_residual_l2(gsb_dist_group *g, const double *b, const double *x, double *out) {
+    if (!g || !b || !x || !out) return GSB_ERR_ARG;
+    if (!g->built) return GSB_ERR_STATE;
+    const int keep = gsb_current_device();
+    std::vector<double> res((size_t)g->n, 0.0);
+    const int s = group_run(g, [&](int r) -> int {
+        gsb_dist *d = g->rank[r];
+        cudaStream_t st = gsb_cur_stream();
+        const int n_local = d->n_local;
+        GSB_TRY(d->stage_b.alloc(n_local));
+        GSB_TRY(d->stage_x.alloc(n_local));
+        GSB_CUDA(cudaMemcpyAsync(d->stage_b.p, b + g->row0[r], sizeof(double) * (size_t)n_local, cudaMemcpyHostToDevice, st));
+        GSB_CUDA(cudaMemcpyAsync(d->stage_x.p, x + g->row0[r], sizeof(double) * (size_t)n_local, cudaMemcpyHostToDevice, st));
+        return gsb_dist_residual_l2_dev(d, d->stage_b.p, d->stage_x.p, &res[(size_t)r]);
+    });
+    gsb_set_device(keep);
+    if (s == GSB_OK) *out = res[0];
+    return s;
 }

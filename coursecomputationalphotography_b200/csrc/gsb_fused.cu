@@ -58,12 +58,12 @@ __device__ __forceinline__ void fused_item(const GsbFusedArgs &fa, int p, int &c
     }
 }
 
-// First warp of a colour-1 tile: every colour-0 tile in [lo, hi] has published `epoch`.  Bounded: a flag that never
-// comes (it cannot, short of a device fault) raises ctl->error instead of hanging the GPU.  Out of line so that the
-// spin loop does not weigh on the tile loop's register allocation / uniform datapath (as the halo helpers).
+// Control thread, before a colour-1 tile is released to the compute warps: every colour-0 tile in [lo, hi] has
+// published `epoch`.  Bounded: a flag that never comes (it cannot, short of a device fault) raises ctl->error instead
+// of hanging the GPU, and once one tile has given up nobody waits any more.
 __device__ __noinline__ void fused_wait_tiles(const int *flags, int lo, int hi, int epoch, GsCtl *ctl) {
-    if (*(volatile int *)&ctl->error) return; // some tile already gave up: the sweep's result is void, just finish
-    for (int i = lo + (int)(threadIdx.x & 31); i <= hi; i += 32) {
+    if (*(volatile int *)&ctl->error) return; // the sweep's result is void already, just finish
+    for (int i = lo; i <= hi; ++i) {
         int v, spins = 0;
         for (;;) {
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
@@ -76,64 +76,46 @@ __device__ __noinline__ void fused_wait_tiles(const int *flags, int lo, int hi, 
         }
     }
 }
-__device__ __noinline__ void fused_publish_tile(int *flag, int epoch) {
-    __threadfence();
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t bytes) { // tx-count up, no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// Warp-specialised: GS_THREADS compute threads (one row of the tile each) + one control warp.  The control thread
+// is the only one that talks to the rest of the GPU: it issues the bulk copies of a tile's inputs (up to STAGES tiles
+// ahead), polls the dependency flags of a colour-1 tile and only then arrives on the stage's `full` mbarrier (the
+// copies complete its transaction count), and -- once all compute warps have arrived on the stage's `empty` mbarrier,
+// i.e. the tile's rows are stored -- publishes a colour-0 tile's flag and refills the stage.  The compute warps never
+// meet a CTA-wide barrier inside the loop; a warp moves on to the next tile as soon as that tile's stage is full.
+//   (v1 of this kernel had thread 0 of the compute warps do the control work between two __syncthreads per tile:
+//    ncu showed 18 of 27 issue-stall cycles on those barriers and 54 % of the DRAM throughput,
+//    profiles/r02_sweep_fused_v1_rhs3.txt.)
+#define GS_FUSED_THREADS (GS_THREADS + 32)
+#define GS_FUSED_WARPS (GS_THREADS / 32)
+
 template <int NRHS, bool CHECK, int STAGES>
-__global__ void __launch_bounds__(GS_THREADS, 4)
+__global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
     gs_sweep_fused(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                    const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int cap, GsCtl *ctl,
                    double *__restrict__ partials, const GsbFusedArgs fa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RingLayout L = ring_layout(cap, NRHS, CHECK, 0);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + STAGES;
     unsigned char *stage0 = smem_raw + 64;
     const int tid = threadIdx.x, bid = blockIdx.x, gsz = gridDim.x;
     const int total = fa.nt0 + fa.nt1;
-
-    struct Desc {
-        int c, t, k0, k1;
-    };
-    auto load_desc = [&](int p) -> Desc { // thread 0; fetched one iteration early (hides the L2 latency of tile_k)
-        Desc d;
-        fused_item(fa, p, d.c, d.t);
-        const int *tk = d.c ? fa.tile_k1 : fa.tile_k0;
-        d.k0 = tk[d.t];
-        d.k1 = tk[d.t + 1];
-        return d;
-    };
-    auto issue = [&](const Desc &d, int s) { // thread 0: every per-tile input is one contiguous span
-        unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
-        const int r_begin = (d.c ? fa.row0_1 : fa.row0_0) + d.t * GS_THREADS;
-        const int rows = min(GS_THREADS, (d.c ? fa.row1_1 : fa.row1_0) - r_begin);
-        const int k0 = d.k0, k1 = d.k1;
-        const int kv0 = k0 & ~1, kc0 = k0 & ~3;
-        const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
-        const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
-        const int ra = r_begin & ~3;
-        const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
-        const int ea = r_begin & ~1; // the leading dimension is even: the same alignment for every plane
-        const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
-        const uint32_t tx = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
-        reinterpret_cast<int *>(st + L.hdr_off)[0] = k0;
-        mbar_expect_tx(&full[s], tx);
-        if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
-        if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
-        bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
-        bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
-            // x_old: this tile's own rows, which nobody but this tile writes during the sweep
-            if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
-        }
-    };
+    __shared__ double red_ws[NRHS][GS_FUSED_WARPS];
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], GS_FUSED_WARPS);
+        }
     }
     __syncthreads();
     // the previous sweep (and its end-of-sweep kernel) is complete and visible from here on
@@ -141,66 +123,132 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
     pdl_launch_dependents();
     if (*(volatile const int *)&ctl->done) return;
     const int epoch = *(volatile const int *)&ctl->sweeps + 1;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            const int p = bid + s * gsz;
-            if (p < total) issue(load_desc(p), s);
-        }
-    }
+    const int my_items = bid < total ? (total - bid + gsz - 1) / gsz : 0;
 
-    double acc[NRHS];
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
-    int k = 0;
-    for (int p = bid; p < total; p += gsz, ++k) {
-        const int s = k % STAGES;
-        const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
-        unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
-        int c, t;
-        fused_item(fa, p, c, t);
-        const int pn = p + STAGES * gsz; // the item that will reuse this stage
-        Desc next_desc;
-        if (tid == 0 && pn < total) next_desc = load_desc(pn);
-        if (c == 1) { // uniform over the CTA
-            if (tid < 32) {
-                const int2 d = fa.dep[t];
-                fused_wait_tiles(fa.flags, d.x, d.y, epoch, ctl);
-            }
-            __syncthreads();
-        }
-        const int r_begin = (c ? fa.row0_1 : fa.row0_0) + t * GS_THREADS;
-        const int rows = min(GS_THREADS, (c ? fa.row1_1 : fa.row1_0) - r_begin);
-        mbar_wait(&full[s], parity);
-
-        const int k0 = reinterpret_cast<const int *>(st + L.hdr_off)[0];
-        const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
-        const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
-        const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
-        const int i = r_begin + tid;
-        if (tid < rows) {
-            const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
-            const int po = (r_begin & 1) + tid;
-            const double d = reinterpret_cast<const double *>(st + L.dg_off)[po];
-            double sig[NRHS];
-            gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int col, int r) { return x[r * n + col]; }, sig);
-            if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+    if (tid >= GS_THREADS) {
+        // ------------------------------- control warp (one thread) -------------------------------
+        if (tid == GS_THREADS) {
+            struct Desc {
+                int c, t, k0, k1;
+            };
+            auto load_desc = [&](int p) -> Desc {
+                Desc d;
+                fused_item(fa, p, d.c, d.t);
+                const int *tk = d.c ? fa.tile_k1 : fa.tile_k0;
+                d.k0 = tk[d.t];
+                d.k1 = tk[d.t + 1];
+                return d;
+            };
+            auto issue = [&](const Desc &d, int s) { // every per-tile input is one contiguous span
+                unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+                const int r_begin = (d.c ? fa.row0_1 : fa.row0_0) + d.t * GS_THREADS;
+                const int rows = min(GS_THREADS, (d.c ? fa.row1_1 : fa.row1_0) - r_begin);
+                const int k0 = d.k0, k1 = d.k1;
+                const int kv0 = k0 & ~1, kc0 = k0 & ~3;
+                const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+                const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+                const int ra = r_begin & ~3;
+                const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
+                const int ea = r_begin & ~1; // the leading dimension is even: the same alignment for every plane
+                const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
+                const uint32_t tx = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
+                int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
+                hdr[0] = k0;
+                hdr[1] = r_begin;
+                hdr[2] = rows;
+                mbar_expect_tx_only(&full[s], tx);
+                if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
+                if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
+                bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
+                bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
 #pragma unroll
                 for (int r = 0; r < NRHS; ++r) {
-                    const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
-                    const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
-                    if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
-                    x[r * n + i] = xn;
+                    bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
+                    // x_old: this tile's own rows, which nobody but this tile writes during the sweep
+                    if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
                 }
+            };
+            // release tile j to the compute warps: its dependencies are met (the copies were issued earlier)
+            auto make_runnable = [&](int j) {
+                int c, t;
+                fused_item(fa, bid + j * gsz, c, t);
+                if (c == 1) {
+                    const int2 d = fa.dep[t];
+                    fused_wait_tiles(fa.flags, d.x, d.y, epoch, ctl);
+                }
+                mbar_arrive(&full[j % STAGES]);
+            };
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                if (s < my_items) issue(load_desc(bid + s * gsz), s);
+            if (my_items > 0) make_runnable(0);
+            for (int j = 0; j < my_items; ++j) {
+                const int s = j % STAGES;
+                Desc next_desc;
+                const bool refill = j + STAGES < my_items;
+                if (refill) next_desc = load_desc(bid + (j + STAGES) * gsz); // L2 latency hidden behind the waits below
+                if (j + 1 < my_items) make_runnable(j + 1);
+                mbar_wait(&empty[s], (uint32_t)(j / STAGES) & 1u); // all compute warps have stored tile j's rows
+                int c, t;
+                fused_item(fa, bid + j * gsz, c, t);
+                if (c == 0) // (release: cumulative over the compute warps' stores observed through `empty`)
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fa.flags + t), "r"(epoch) : "memory");
+                if (refill) issue(next_desc, s);
             }
         }
-        __syncthreads(); // every thread is done with stage s, and with its stores of this tile
-        if (tid == 0) {
-            if (c == 0) fused_publish_tile(fa.flags + t, epoch);
-            if (pn < total) issue(next_desc, s);
+    } else {
+        // ------------------------------------ compute warps ------------------------------------
+        double acc[NRHS];
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
+        for (int j = 0; j < my_items; ++j) {
+            const int s = j % STAGES;
+            unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+            mbar_wait(&full[s], (uint32_t)(j / STAGES) & 1u);
+            const int *hdr = reinterpret_cast<const int *>(st + L.hdr_off);
+            const int k0 = hdr[0], r_begin = hdr[1], rows = hdr[2];
+            const double *va_s = reinterpret_cast<const double *>(st + L.va_off) - (k0 & ~1);
+            const int *ci_s = reinterpret_cast<const int *>(st + L.ci_off) - (k0 & ~3);
+            const int *rp_s = reinterpret_cast<const int *>(st + L.rp_off) + (r_begin & 3);
+            const int i = r_begin + tid;
+            if (tid < rows) {
+                const int rs = rp_s[tid], len = rp_s[tid + 1] - rs;
+                const int po = (r_begin & 1) + tid;
+                const double d = reinterpret_cast<const double *>(st + L.dg_off)[po];
+                double sig[NRHS];
+                gs_row_sigma<NRHS>(ci_s + rs, va_s + rs, len, [&](int col, int r) { return x[r * n + col]; }, sig);
+                if (d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) {
+                        const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
+                        const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
+                        if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
+                        x[r * n + i] = xn;
+                    }
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]); // this warp is done with stage s and has stored its rows
+        }
+        if (CHECK) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                double t = acc[r];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+                if ((tid & 31) == 0) red_ws[r][tid >> 5] = t;
+            }
         }
     }
-    if (CHECK) gsb_block_reduce_store<NRHS, GS_THREADS>(acc, partials + (size_t)blockIdx.x * NRHS);
+    if (CHECK) { // fixed-order fold of the CTA's stop-rule partial -> slot blockIdx.x
+        __syncthreads();
+        if (tid < NRHS) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < GS_FUSED_WARPS; ++w) sum += red_ws[tid][w];
+            partials[(size_t)blockIdx.x * NRHS + tid] = sum;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,25 +382,8 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     fused_fn kern = check ? (fused_fn)gs_sweep_fused<NRHS, true, GS_RING_STAGES_DEFAULT>
                           : (fused_fn)gs_sweep_fused<NRHS, false, GS_RING_STAGES_DEFAULT>;
     const int smem = 64 + GS_RING_STAGES_DEFAULT * ring_layout(p->cap, NRHS, check, 0).stage_bytes;
-    // opt-in shared-memory size and resident CTAs per SM: per (function, size, device)
-    struct Cfg { const void *fn; int smem, occ, dev; };
-    static Cfg cfgs[64];
-    static int ncfg = 0;
-    const int dev_now = gsb_current_device();
-    Cfg *cf = nullptr;
-    for (int q = 0; q < ncfg; ++q)
-        if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem && cfgs[q].dev == dev_now) cf = &cfgs[q];
-    if (!cf) {
-        GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        int o = 0;
-        GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
-        if (ncfg == 64) ncfg = 0;
-        cf = &cfgs[ncfg++];
-        cf->fn = (const void *)kern;
-        cf->smem = smem;
-        cf->dev = dev_now;
-        cf->occ = o < 1 ? 1 : o;
-    }
+    int per_sm = 1;
+    GSB_TRY(gsb_kernel_occupancy((const void *)kern, smem, &per_sm, GS_FUSED_THREADS));
     static int env_ctas = -1, env_lead = -1;
     if (env_ctas < 0) {
         const char *e = getenv("GSB_RING_CTAS");
@@ -360,7 +391,6 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
         e = getenv("GSB_FUSED_LEAD"); // extra lead in tiles on top of the dependency distance; default = the grid size
         env_lead = e ? atoi(e) : 0;
     }
-    int per_sm = cf->occ;
     if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
     const int nt0 = p->blocks[0], nt1 = p->blocks[1];
     int grid = gsb_sm_count() * per_sm; // every CTA must be resident: the walk waits on other CTAs' tiles
@@ -385,7 +415,7 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     fa.nalt = nt1 < nt0 - lead ? nt1 : nt0 - lead;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GS_THREADS);
+    cfg.blockDim = dim3(GS_FUSED_THREADS);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -102,6 +102,11 @@ static inline int gsb_blocks_for(int64_t n, int threads, int max_blocks = 1 << 3
     return (int)b;
 }
 
+#define GSB_DIST_MAX_WORLD_DECL 16
+struct gsb_dist_group;
+// process-wide device list of the host entry points (gsb_set_devices / GSB_DEVICES); returns the count
+int gsb_devices(int *out, int cap);
+
 // ---- the matrix handle -------------------------------------------------------------------
 struct gsb_matrix {
     int vtype = GSB_F64;
@@ -153,6 +158,10 @@ struct gsb_matrix {
     void *graph_exec = nullptr;
     int graph_key[6] = {0, 0, 0, 0, 0, 0};
     struct GsbPlan *plan = nullptr; // colour-phase launch plan (gsb_phase.cu)
+    // multi-device solve through the host entry points (gsb_set_devices): the group and whether it holds this matrix
+    struct gsb_dist_group *group = nullptr;
+    bool group_built = false;
+    int group_key[GSB_DIST_MAX_WORLD_DECL + 1] = {0}; // device list the group was made for ([0] = count)
 
     void drop_analysis();
     ~gsb_matrix();
@@ -225,6 +234,7 @@ int gsb_plan_launch_fused(const GsbPlan *p, const int *rp, const int *ci, const 
 int gsb_plan_partial_slots(const GsbPlan *p, int c, int nrhs); // stop-rule partial slots of colour phase c
 // programmatic dependent launch of the ring kernels / gs_end_sweep (GSB_PDL=0 disables; suppressed during graph capture)
 bool gsb_pdl_enabled();
+int gsb_kernel_occupancy(const void *kern, int smem, int *occ, int threads = 256); // resident CTAs per SM (cached, thread-safe)
 int gsb_pdl_mode(int64_t phase_rows); // decision for the launch about to be made (remembered for gs_end_sweep)
 int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t st); // gsb_fused.cu
 void gsb_pdl_suppress(int on);

@@ -29,6 +29,7 @@ void gsb_matrix::drop_analysis() {
     }
     memset(graph_key, 0, sizeof(graph_key));
     if (plan) plan->valid = false; // (its tile tables are rebuilt, into the same allocations, by gsb_plan_build)
+    group_built = false;           // the strips of a multi-device solve belong to the previous matrix
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,6 +24,8 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 // ---------------------------------------------------------------------------------------------
 // kernel 1: row per thread, direct global loads
 // ---------------------------------------------------------------------------------------------
@@ -1103,6 +1105,39 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
     return GSB_OK;
 }
 
+
+// Resident CTAs per SM of a persistent kernel at `smem` bytes of dynamic shared memory, with the opt-in to the
+// planner's upper bound made once per (function, device).  One small table for all ring / fused variants, guarded:
+// the worker threads of the single-process multi-device solver launch concurrently.
+int gsb_kernel_occupancy(const void *kern, int smem, int *occ, int threads) {
+    struct Cfg { const void *fn; int smem, occ, dev; };
+    static Cfg cfgs[256];
+    static int ncfg = 0;
+    static std::mutex mu;
+    const int dev_now = gsb_current_device(); // function attributes and occupancy are per device
+    std::lock_guard<std::mutex> lk(mu);
+    for (int q = 0; q < ncfg; ++q)
+        if (cfgs[q].fn == kern && cfgs[q].smem == smem && cfgs[q].dev == dev_now) {
+            *occ = cfgs[q].occ;
+            return GSB_OK;
+        }
+    // the attribute is per function, not per launch: setting it to this matrix' size would break a later launch for
+    // a matrix with larger tiles, so every variant opts in to the upper bound once
+    bool seen = false;
+    for (int q = 0; q < ncfg; ++q) seen = seen || (cfgs[q].fn == kern && cfgs[q].dev == dev_now);
+    if (!seen) GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int o = 0;
+    GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem));
+    if (ncfg == 256) ncfg = 0; // (entries overwritten after a wrap-around just get their attribute set again)
+    Cfg *cf = &cfgs[ncfg++];
+    cf->fn = kern;
+    cf->smem = smem;
+    cf->dev = dev_now;
+    cf->occ = o < 1 ? 1 : o;
+    *occ = cf->occ;
+    return GSB_OK;
+}
+
 template <int NRHS>
 static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
                          const double *b, double *x, int64_t ld, bool check, const GsCtl *ctl, double *partials,
@@ -1169,31 +1204,8 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
 #undef GSB_RING_PICK_FE
 #undef GSB_RING_PICK_ST
 #undef GSB_RING_PICK
-        // per (variant) cache of the opt-in shared-memory size and the resident CTAs per SM
-        struct Cfg { const void *fn; int smem, occ, dev; };
-        const int dev_now = gsb_current_device(); // function attributes and occupancy are per device
-        static Cfg cfgs[256];
-        static int ncfg = 0;
-        Cfg *cf = nullptr;
-        for (int q = 0; q < ncfg; ++q)
-            if (cfgs[q].fn == (const void *)kern && cfgs[q].smem == smem && cfgs[q].dev == dev_now) cf = &cfgs[q];
-        if (!cf) {
-            // opt in to the planner's upper bound once per variant (the attribute is per function, not per launch:
-            // setting it to this matrix' size would break a later launch for a matrix with larger tiles)
-            bool seen = false;
-            for (int q = 0; q < ncfg; ++q) seen = seen || (cfgs[q].fn == (const void *)kern && cfgs[q].dev == dev_now);
-            if (!seen)
-                GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            int o = 0;
-            GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)kern, GS_THREADS, smem));
-            if (ncfg == 256) ncfg = 0; // (entries overwritten after a wrap-around just get their attribute set again)
-            cf = &cfgs[ncfg++];
-            cf->fn = (const void *)kern;
-            cf->smem = smem;
-            cf->dev = dev_now;
-            cf->occ = o < 1 ? 1 : o;
-        }
-        int per_sm = cf->occ;
+        int per_sm = 1;
+        GSB_TRY(gsb_kernel_occupancy((const void *)kern, smem, &per_sm));
         if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
         // halo variant: n_halo_tiles one-tile CTAs first, then the persistent ring over the interior tiles
         // (the halo CTAs start first and occupy resident slots: the ring gets the remaining slots, so that every

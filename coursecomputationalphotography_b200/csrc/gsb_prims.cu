@@ -3,6 +3,8 @@
 // deterministic two-pass reductions, and the reference's free vector helpers (A8).
 #include "gsb_internal.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 // ---------------------------------------------------------------------------------------------
@@ -20,7 +22,9 @@ void gsb_set_error(const char *fmt, ...) {
 extern "C" const char *gsb_last_error(void) { return g_err; }
 extern "C" int gsb_version(void) { return 100; }
 
-static int g_device = 0;
+// the current device is per host thread (as CUDA's own): the single-process multi-device solver runs one worker
+// thread per device; streams, SM counts and reduction scratch are per device and shared
+static thread_local int g_device = 0;
 static cudaStream_t g_streams[64] = {nullptr};
 static int g_sm_count[64] = {0};
 static double *g_scratch[64] = {nullptr};
@@ -71,6 +75,59 @@ extern "C" int gsb_set_device(int device) {
 }
 
 int gsb_current_device() { return g_device; }
+
+// ---- device list of the host entry points (multi-device solve behind SparseMatrix::gaussSeidel) ----------------
+static int g_devlist[GSB_DIST_MAX_WORLD_DECL];
+static int g_devlist_n = -1; // -1: not set yet -> GSB_DEVICES is consulted once
+
+extern "C" int gsb_set_devices(const int *devices, int n) {
+    if (n < 0 || n > GSB_DIST_MAX_WORLD_DECL || (n > 0 && !devices)) {
+        gsb_set_error("gsb_set_devices: 0..%d devices", GSB_DIST_MAX_WORLD_DECL);
+        return GSB_ERR_ARG;
+    }
+    int c = 0;
+    gsb_device_count(&c);
+    for (int i = 0; i < n; ++i) {
+        if (devices[i] < 0 || devices[i] >= c) {
+            gsb_set_error("gsb_set_devices: device %d, %d visible", devices[i], c);
+            return c <= 0 ? GSB_ERR_NO_DEVICE : GSB_ERR_ARG;
+        }
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) {
+                gsb_set_error("gsb_set_devices: device %d listed twice", devices[i]);
+                return GSB_ERR_ARG;
+            }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < n; ++i) g_devlist[i] = devices[i];
+    g_devlist_n = n;
+    return GSB_OK;
+}
+
+int gsb_devices(int *out, int cap) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_devlist_n < 0) { // GSB_DEVICES=0,1,2,3 (unset: single device, the one gsb_set_device selected)
+        g_devlist_n = 0;
+        const char *e = getenv("GSB_DEVICES");
+        int c = 0;
+        cudaError_t ce = cudaGetDeviceCount(&c);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            c = 0;
+        }
+        while (e && *e && g_devlist_n < GSB_DIST_MAX_WORLD_DECL) {
+            char *end = nullptr;
+            long v = strtol(e, &end, 10);
+            if (end == e) break;
+            if (v >= 0 && v < c) g_devlist[g_devlist_n++] = (int)v;
+            e = *end == ',' ? end + 1 : end;
+        }
+    }
+    for (int i = 0; i < g_devlist_n && i < cap; ++i) out[i] = g_devlist[i];
+    return g_devlist_n;
+}
+
+extern "C" int gsb_get_devices(int *devices, int cap) { return gsb_devices(devices, devices ? cap : 0); }
 
 cudaStream_t gsb_cur_stream() {
     std::lock_guard<std::mutex> lk(g_mu);

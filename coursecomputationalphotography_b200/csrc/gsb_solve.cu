@@ -330,9 +330,77 @@ int gsb_gs_solve_device_x0(gsb_matrix *m, const double *b_dev, const double *x0_
     return gs_solve_device(m, b_dev, x0_dev, nrhs, epsilon, max_iteration, opts, x_dev, stats);
 }
 
+// Multi-device path of the host entry point: when the process has a device list of two or more
+// (gsb_set_devices / GSB_DEVICES) and the matrix takes a two-colouring, the solve runs on row strips, one per
+// device, from this one blocking call (gsb_dist_init_local: worker thread per device, peer-memory halo).  *took = 0
+// when the matrix does not shard that way (more than two colours, fewer rows than GS_MGPU_MIN_ROWS per device): the
+// caller then runs the single-device path.
+#define GS_MGPU_MIN_ROWS 65536
+static int gs_host_multi(gsb_matrix *m, const double *b, int nrhs, double epsilon, int max_iteration,
+                         const gsb_gs_options *opts_in, double *x_out, gsb_gs_stats *stats, int *took) {
+    *took = 0;
+    int devs[GSB_DIST_MAX_WORLD_DECL];
+    const int nd = gsb_devices(devs, GSB_DIST_MAX_WORLD_DECL);
+    if (nd < 2 || (int64_t)m->n_rows < (int64_t)GS_MGPU_MIN_ROWS * nd) return GSB_OK;
+    gsb_gs_options opts;
+    gsb_gs_default_options(&opts);
+    if (opts_in) opts = *opts_in;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double setup_ms = 0.0;
+    if (!m->group_built) {
+        GSB_CUDA(cudaEventCreate(&e0));
+        GSB_CUDA(cudaEventCreate(&e1));
+        GSB_CUDA(cudaEventRecord(e0, gsb_cur_stream()));
+    }
+    if (!m->analyzed) GSB_TRY(gsb_matrix_analyze(m, opts.ordering, nullptr));
+    if (m->n_colors > 2) { // replicas only: stays on one device
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        return GSB_OK;
+    }
+    bool same = m->group && m->group_key[0] == nd;
+    for (int i = 0; same && i < nd; ++i) same = m->group_key[1 + i] == devs[i];
+    if (!same) {
+        if (m->group) gsb_dist_group_finalize(m->group);
+        m->group = nullptr;
+        m->group_built = false;
+        GSB_TRY(gsb_dist_init_local(&m->group, devs, nd));
+        m->group_key[0] = nd;
+        for (int i = 0; i < nd; ++i) m->group_key[1 + i] = devs[i];
+    }
+    if (!m->group_built) {
+        GSB_TRY(gsb_dist_group_matrix(m->group, m));
+        m->group_built = true;
+        GSB_CUDA(cudaEventRecord(e1, gsb_cur_stream()));
+        GSB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        setup_ms = ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    GSB_TRY(gsb_dist_group_gauss_seidel(m->group, b, nrhs, epsilon, max_iteration, &opts, x_out, stats));
+    if (stats) {
+        stats->setup_ms = setup_ms;
+        stats->n_colors = m->n_colors;
+        stats->ordering_used = m->ordering_used;
+        if (opts.compute_residual)
+            for (int r = 0; r < nrhs; ++r)
+                GSB_TRY(gsb_dist_group_residual_l2(m->group, b + (size_t)r * m->n_rows, x_out + (size_t)r * m->n_rows,
+                                                   &stats->residual_l2[r]));
+    }
+    *took = 1;
+    return GSB_OK;
+}
+
 static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, double epsilon, int max_iteration,
                    const gsb_gs_options *opts, double *x_out, gsb_gs_stats *stats) {
     GSB_TRY(gs_check_args(m, b, nrhs, x_out));
+    if (!x0) { // (the initial-guess extension stays single-device)
+        int took = 0;
+        GSB_TRY(gs_host_multi(m, b, nrhs, epsilon, max_iteration, opts, x_out, stats, &took));
+        if (took) return GSB_OK;
+    }
     cudaStream_t st = gsb_cur_stream();
     const int64_t n = m->n_rows;
     // device staging of the caller's host vectors: kept with the handle (repeated solves reuse it)

@@ -9,7 +9,7 @@ import numpy as np
 def run(args, pkg, wl, dist, rank, world, local):
     import torch
     from . import strips
-    from bench import ClockSampler, algorithmic_bytes_per_sweep, peaks
+    from bench import ClockSampler, algorithmic_bytes_per_sweep, peaks, workload_config
 
     L = pkg.load()
     dev = torch.device("cuda", local)
@@ -89,6 +89,8 @@ def run(args, pkg, wl, dist, rank, world, local):
                "ms_per_step": float(tt[0]) / steps_e2e * 1e3, "steps": steps_e2e,
                "includes": "strip matrix generation + ordering + halo setup + b H2D + sweeps + x D2H (all ranks)"}
 
+    parity = parity_vs_one_gpu(args, pkg, wl, dist, torch, solver, b_dev, rank, world, dev, W, H, ch, n_local, opts)
+
     if rank == 0:
         assert sweeps_done == args.sweeps * args.steps
         value = nnz * ch * sweeps_done / (total_ms * 1e-3) / 1e9
@@ -100,22 +102,73 @@ def run(args, pkg, wl, dist, rank, world, local):
             "metric": "gauss_seidel_throughput", "value": value, "unit": "Gnnz/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "poisson_%dx%d_x%dch_full_grid (BASELINE configs[2]), %d row strips" % (W, H, ch, world),
-                       "n": n, "nnz": int(nnz), "sweeps_per_step": args.sweeps, "ordering": "red-black (global parity)",
+            "config": workload_config(W, H, ch, n, nnz),
+            "run": {"partition": "%d row strips, one rank per GPU" % world,
+                       "sweeps_per_step": args.sweeps, "ordering": "red-black (global parity)",
                        "check_every": args.check_every,
                        "halo": "1 image row per neighbour per colour phase, " +
                                ("stored into the neighbour's ghost slots by the phase kernel (NVLink peer memory)"
                                 if st.kernel_used >= 10 else "packed ncclSend/ncclRecv"),
                        "stop_rule_allreduce": ("fused into the end-of-sweep kernel (peer memory)" if st.kernel_used >= 30
                                                else "ncclAllReduce"),
-                       "l2": "per-GPU working set %.2f GB per sweep" % (abytes / 1e9),
+                       "per_gpu_working_set_gb_per_sweep": abytes / 1e9,
                        "sweeps_per_s": sweeps_done / (total_ms * 1e-3), "residual_l2": resid},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "gs_phase per GPU incl. halo exchange gaps", "peak_source": peak_src,
                          "avg_launch_ms": per_launch_ms},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sm[2]), "clocks": clocks,
         }
-        print(json.dumps(line))
+        line.update(parity)
+        print(json.dumps(line), flush=True)
     solver.close()
     dist.barrier()
     dist.destroy_process_group()
+    if rank == 0 and parity.get("parity_bitwise_vs_1gpu") is False:
+        raise SystemExit("dist_bench: the %d-strip solution differs from the 1-GPU solution" % world)
+
+
+PARITY_SWEEPS = 10
+
+
+def parity_vs_one_gpu(args, pkg, wl, dist, torch, solver, b_dev, rank, world, dev, W, H, ch, n_local, opts):
+    """A fixed PARITY_SWEEPS-sweep solve from x0 = 1 on the strips, gathered on rank 0 and compared BIT FOR BIT with
+    the single-GPU solver (SparseMatrix::gaussSeidel on the whole system, which fits one B200) on the same b.
+    Returns the keys rank 0 adds to its line; a mismatch makes the bench exit non-zero."""
+    import hashlib
+    x_dev = torch.empty_like(b_dev)
+    st = solver.gauss_seidel_dev(b_dev.data_ptr(), x_dev.data_ptr(), ch, 0.0, PARITY_SWEEPS, opts)
+    assert st.sweeps == PARITY_SWEEPS
+    bounds = [y1 - y0 for y0, y1 in wl.strip_bounds(H, world)]
+    nmax = max(bounds) * W
+
+    def padded(t):
+        out = torch.zeros(ch, nmax, device=dev, dtype=torch.float64)
+        out[:, :n_local] = t
+        return out
+
+    got_x = [torch.empty(ch, nmax, device=dev, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+    got_b = [torch.empty(ch, nmax, device=dev, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded(x_dev), got_x, dst=0)
+    dist.gather(padded(b_dev), got_b, dst=0)
+    if rank != 0:
+        return {}
+    x_full = torch.cat([got_x[r][:, :bounds[r] * W] for r in range(world)], dim=1).contiguous()
+    b_full = torch.cat([got_b[r][:, :bounds[r] * W] for r in range(world)], dim=1).contiguous()
+    del got_x, got_b
+    sp = pkg.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    x_one = torch.empty_like(x_full)
+    st1 = sp.gaussSeidel_dev(b_full.data_ptr(), x_one.data_ptr(), ch, 0.0, PARITY_SWEEPS,
+                             pkg.SparseMatrix.options(check_every=args.check_every))
+    torch.cuda.synchronize()
+    same = bool(torch.equal(x_full, x_one))
+    out = {"parity_bitwise_vs_1gpu": same, "parity": {
+        "what": "%d sweeps from x0 = 1: %d strips gathered on rank 0 vs SparseMatrix::gaussSeidel on one GPU, same b"
+                % (PARITY_SWEEPS, world),
+        "x_sha256": hashlib.sha256(x_full.cpu().numpy().tobytes()).hexdigest(),
+        "x_sha256_1gpu": hashlib.sha256(x_one.cpu().numpy().tobytes()).hexdigest(),
+        "max_abs_diff": float((x_full - x_one).abs().max()), "kernel_1gpu": int(st1.kernel_used),
+        "kernel_strips": int(st.kernel_used), "last_eps_strips": [float(v) for v in list(st.last_eps)[:ch]],
+        "last_eps_1gpu": [float(v) for v in list(st1.last_eps)[:ch]]}}
+    del sp
+    return out

@@ -311,6 +311,37 @@ int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int nrhs, double
                               gsb_gs_stats *stats);
 int gsb_dist_residual_l2_dev(gsb_dist *d, const double *b_dev, const double *x_dev, double *out);
 
+/* ---------------------------------------------------------------------------------------
+ * Single-process multi-device solve: N devices of one box behind ONE blocking call, the call
+ * model of the reference (one host thread, synchronous solve: project/src/PhotoMontage/
+ * main.cpp:581).  No NCCL, no torch, no IPC -- the devices reach each other through peer access.
+ * ------------------------------------------------------------------------------------- */
+/* Process-wide device list of the HOST entry points (gsb_gauss_seidel, i.e. SparseMatrix::
+ * gaussSeidel of the drop-in header): with two or more devices a solve of a matrix that takes
+ * a two-colouring (red-black grids, the caller's two colours) is split into row strips, one per
+ * device; x is bit-identical to the single-device solve.  Matrices with more colours, tiny
+ * systems and the x0 extension stay on one device (stats.kernel_used < 10 says so).
+ * n = 0 or 1: single device.  Default: the environment variable GSB_DEVICES ("0,1,2,3"). */
+int gsb_set_devices(const int *devices, int n);
+int gsb_get_devices(int *devices, int cap); /* returns the count */
+/* The same machinery as an explicit object (bench.py, tests): */
+typedef struct gsb_dist_group gsb_dist_group;
+int gsb_dist_init_local(gsb_dist_group **out, const int *devices, int n);
+int gsb_dist_group_finalize(gsb_dist_group *g);
+int gsb_dist_group_size(const gsb_dist_group *g);
+/* shard an assembled matrix (any assembly entry point) by rows; analyses it if necessary */
+int gsb_dist_group_matrix(gsb_dist_group *g, gsb_matrix *m);
+/* or generate the reference-faithful W x H Poisson system strip by strip on the devices (C4) */
+int gsb_dist_group_poisson(gsb_dist_group *g, int W, int H);
+/* b / x_out: HOST vectors, nrhs * n doubles, as gsb_gauss_seidel takes them */
+int gsb_dist_group_gauss_seidel(gsb_dist_group *g, const double *b, int nrhs, double epsilon,
+                                int max_iteration, const gsb_gs_options *opts, double *x_out,
+                                gsb_gs_stats *stats);
+int gsb_dist_group_residual_l2(gsb_dist_group *g, const double *b, const double *x, double *out);
+/* one-process-per-GPU mode: the caller's two-colouring of ALL n_global rows (bytes 0/1) for
+ * gsb_dist_matrix_rows, instead of pixel parity (compact / masked systems); n_global = 0 clears */
+int gsb_dist_set_colors(gsb_dist *d, const unsigned char *colors, int64_t n_global);
+
 /* Pinned host memory for callers that want full-rate PCIe copies (bench.py e2e leg). */
 int gsb_host_alloc(void **ptr, int64_t bytes);
 int gsb_host_free(void *ptr);

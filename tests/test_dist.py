@@ -42,12 +42,15 @@ def test_single_rank_strip_equals_single_gpu(gsb):
 
 
 @pytest.mark.gpu
-def test_two_strips_equal_single_gpu(gsb):
-    if gsb._lib.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    r = _launch("gpu", 2)
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_n_strips_equal_single_gpu(gsb, world):
+    """world row strips (one process per GPU, fused peer-memory halo and NCCL halo) == the 1-GPU solve, bit for bit,
+    and every rank stops on the same sweep (tests/dist_worker.py, mode gpu)."""
+    if gsb._lib.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
+    r = _launch("gpu", world, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("gpu strips ok") == 3
+    assert r.stdout.count("gpu strips ok") == 3 and "gpu strips stop rule ok" in r.stdout
 
 
 @pytest.mark.gpu

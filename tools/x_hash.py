@@ -18,6 +18,7 @@ gx, gy = wl.seamless_gradients(img)
 b = pkg.poisson_rhs(W, H, gx, gy, img[:, 0, 0].astype(np.float64))
 sp = pkg.SparseMatrix(np.float64)
 sp.poisson(W, H)
+b = np.asarray(b).reshape(ch, -1)
 x = sp.gaussSeidel(b if ch > 1 else b[0], epsilon=0.0, max_iteration=sweeps,
                    options=pkg.SparseMatrix.options(kernel=kernel, use_graph=0))
 print(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest(), sp.last_stats.kernel_used, sp.last_stats.sweeps,
