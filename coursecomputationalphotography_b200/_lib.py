@@ -104,6 +104,7 @@ SIGNATURES = {
     "gsb_gdf_release": [],
     "gsb_pano_mask_image": [_vp, _vp, _i, _i, _vp],
     "gsb_pano_gradients": [_vp, _i, _i, _vp, _vp],
+    "gsb_pano_gradients_masked": [_vp, _vp, _i, _i, _vp, _vp],
     "gsb_pano_merge2_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i],
     "gsb_pano_merge_u8": [_vp, _vp, _vp, _vp, _i, _d, _i, _i],
     "gsb_pano_enforce_gradient_bound": [_vp, _vp, _vp, _vp, _i, _i],

@@ -58,23 +58,31 @@ __device__ __forceinline__ void fused_item(const GsbFusedArgs &fa, int p, int &c
     }
 }
 
-// Control thread, before a colour-1 tile is released to the compute warps: every colour-0 tile in [lo, hi] has
-// published `epoch`.  Bounded: a flag that never comes (it cannot, short of a device fault) raises ctl->error instead
-// of hanging the GPU, and once one tile has given up nobody waits any more.
-__device__ __noinline__ void fused_wait_tiles(const int *flags, int lo, int hi, int epoch, GsCtl *ctl) {
-    if (*(volatile int *)&ctl->error) return; // the sweep's result is void already, just finish
-    for (int i = lo; i <= hi; ++i) {
-        int v, spins = 0;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-            if (v >= epoch) break;
-            if (++spins > (1 << 22) || ((spins & 1023) == 0 && *(volatile int *)&ctl->error)) { // ~1 s
-                ctl->error = 2;
-                return;
-            }
-            __nanosleep(spins < 32 ? 32 : 256);
-        }
+// One record per work item of the sweep, in sequence order, built once per (matrix, lead) by plan_fused_items: what
+// the control warp needs to stage, release and retire a tile without computing or chasing anything at run time.
+struct __align__(16) FusedItem {
+    int k0, k1, r_begin, rows; // CSR span of the tile, its first row and row count
+    int c, t, dep_lo, dep_hi;  // colour, tile, colour-0 tiles to wait for (dep_lo > dep_hi: none)
+};
+
+__global__ void __launch_bounds__(256) plan_fused_items(const GsbFusedArgs fa, FusedItem *__restrict__ items) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= fa.nt0 + fa.nt1) return;
+    FusedItem it;
+    fused_item(fa, p, it.c, it.t);
+    const int *tk = it.c ? fa.tile_k1 : fa.tile_k0;
+    it.k0 = tk[it.t];
+    it.k1 = tk[it.t + 1];
+    it.r_begin = (it.c ? fa.row0_1 : fa.row0_0) + it.t * GS_THREADS;
+    it.rows = min(GS_THREADS, (it.c ? fa.row1_1 : fa.row1_0) - it.r_begin);
+    it.dep_lo = 0;
+    it.dep_hi = -1;
+    if (it.c == 1) {
+        const int2 d = fa.dep[it.t];
+        it.dep_lo = d.x;
+        it.dep_hi = d.y;
     }
+    items[p] = it;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -84,15 +92,43 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t byte
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// Warp-specialised: GS_THREADS compute threads (one row of the tile each) + one control warp.  The control thread
-// is the only one that talks to the rest of the GPU: it issues the bulk copies of a tile's inputs (up to STAGES tiles
-// ahead), polls the dependency flags of a colour-1 tile and only then arrives on the stage's `full` mbarrier (the
-// copies complete its transaction count), and -- once all compute warps have arrived on the stage's `empty` mbarrier,
-// i.e. the tile's rows are stored -- publishes a colour-0 tile's flag and refills the stage.  The compute warps never
-// meet a CTA-wide barrier inside the loop; a warp moves on to the next tile as soon as that tile's stage is full.
-//   (v1 of this kernel had thread 0 of the compute warps do the control work between two __syncthreads per tile:
-//    ncu showed 18 of 27 issue-stall cycles on those barriers and 54 % of the DRAM throughput,
-//    profiles/r02_sweep_fused_v1_rhs3.txt.)
+// Control warp, all 32 lanes: every colour-0 tile in [lo, hi] has published `epoch`.  The lanes poll one flag each
+// (one coalesced L2 round trip for the usual ~20-tile range) with relaxed loads and fence once they have all seen it;
+// the warp barrier then orders lane 0's arrive on the stage's `full` mbarrier after every lane's observation, so the
+// compute warps' gathers are ordered after the colour-0 tiles' stores (release / acquire at GPU scope, cumulative
+// through the warp and mbarrier synchronisation).  Bounded: a flag that never comes (it cannot, short of a device
+// fault) raises ctl->error instead of hanging the GPU, and once one tile has given up nobody waits any more.
+__device__ __forceinline__ void fused_wait_tiles(const int *flags, int lo, int hi, int epoch, GsCtl *ctl) {
+    const int lane = threadIdx.x & 31;
+    for (int base = lo; base <= hi; base += 32) {
+        const int i = base + lane;
+        int spins = 0;
+        for (;;) {
+            int v = epoch;
+            if (i <= hi) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            if (__all_sync(0xffffffffu, v >= epoch)) break;
+            if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)&ctl->error)) { // ~1 s
+                if (lane == 0) ctl->error = 2;
+                return;
+            }
+            __nanosleep(spins < 16 ? 20 : 200);
+        }
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    __syncwarp();
+}
+
+// Warp-specialised: GS_THREADS compute threads (one row of the tile each) + one control warp.  The control warp is
+// the only one that talks to the rest of the GPU: lane 0 issues the bulk copies of a tile's inputs (up to STAGES
+// tiles ahead); the warp polls the dependency flags of a colour-1 tile and only then lane 0 arrives on the stage's
+// `full` mbarrier (the copies complete its transaction count); once all compute warps have arrived on the stage's
+// `empty` mbarrier -- the tile's rows are stored -- lane 0 refills the stage and publishes a colour-0 tile's flag.
+// The compute warps never meet a CTA-wide barrier inside the loop; a warp moves on to the next tile as soon as that
+// tile's stage is full.
+//   v1 (thread 0 of the compute warps did the control work between two __syncthreads per tile): 18 of 27 issue-stall
+//      cycles on those barriers, 54 % of the DRAM throughput (profiles/r02_sweep_fused_v1_rhs3.txt).
+//   v2 (one control THREAD, polling its ~20 flags one after another and computing every descriptor on the fly): the
+//      compute warps starved on `full`, 43 % (profiles/r02_sweep_fused_v2_rhs3.txt).
 #define GS_FUSED_THREADS (GS_THREADS + 32)
 #define GS_FUSED_WARPS (GS_THREADS / 32)
 
@@ -100,14 +136,13 @@ template <int NRHS, bool CHECK, int STAGES>
 __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
     gs_sweep_fused(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                    const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int cap, GsCtl *ctl,
-                   double *__restrict__ partials, const GsbFusedArgs fa) {
+                   double *__restrict__ partials, const FusedItem *__restrict__ items, int total, int *flags, int debug) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RingLayout L = ring_layout(cap, NRHS, CHECK, 0);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + STAGES;
     unsigned char *stage0 = smem_raw + 64;
     const int tid = threadIdx.x, bid = blockIdx.x, gsz = gridDim.x;
-    const int total = fa.nt0 + fa.nt1;
     __shared__ double red_ws[NRHS][GS_FUSED_WARPS];
 
     if (tid == 0) {
@@ -126,74 +161,78 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
     const int my_items = bid < total ? (total - bid + gsz - 1) / gsz : 0;
 
     if (tid >= GS_THREADS) {
-        // ------------------------------- control warp (one thread) -------------------------------
-        if (tid == GS_THREADS) {
-            struct Desc {
-                int c, t, k0, k1;
-            };
-            auto load_desc = [&](int p) -> Desc {
-                Desc d;
-                fused_item(fa, p, d.c, d.t);
-                const int *tk = d.c ? fa.tile_k1 : fa.tile_k0;
-                d.k0 = tk[d.t];
-                d.k1 = tk[d.t + 1];
-                return d;
-            };
-            auto issue = [&](const Desc &d, int s) { // every per-tile input is one contiguous span
-                unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
-                const int r_begin = (d.c ? fa.row0_1 : fa.row0_0) + d.t * GS_THREADS;
-                const int rows = min(GS_THREADS, (d.c ? fa.row1_1 : fa.row1_0) - r_begin);
-                const int k0 = d.k0, k1 = d.k1;
-                const int kv0 = k0 & ~1, kc0 = k0 & ~3;
-                const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
-                const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
-                const int ra = r_begin & ~3;
-                const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
-                const int ea = r_begin & ~1; // the leading dimension is even: the same alignment for every plane
-                const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
-                const uint32_t tx = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
-                int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
-                hdr[0] = k0;
-                hdr[1] = r_begin;
-                hdr[2] = rows;
-                mbar_expect_tx_only(&full[s], tx);
-                if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
-                if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
-                bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
-                bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
+        // ------------------------------------ control warp -------------------------------------
+        const int lane = tid - GS_THREADS;
+        auto load_item = [&](int j) -> FusedItem { // all lanes read the same 32 bytes (one broadcast transaction)
+            const int4 *src = reinterpret_cast<const int4 *>(items + (bid + j * gsz));
+            const int4 a = __ldg(src), c4 = __ldg(src + 1);
+            FusedItem it;
+            it.k0 = a.x; it.k1 = a.y; it.r_begin = a.z; it.rows = a.w;
+            it.c = c4.x; it.t = c4.y; it.dep_lo = c4.z; it.dep_hi = c4.w;
+            return it;
+        };
+        auto issue = [&](const FusedItem &d, int s) { // lane 0: every per-tile input is one contiguous span
+            unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
+            const int r_begin = d.r_begin, rows = d.rows, k0 = d.k0, k1 = d.k1;
+            const int kv0 = k0 & ~1, kc0 = k0 & ~3;
+            const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+            const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+            const int ra = r_begin & ~3;
+            const uint32_t bytes_r = (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u;
+            const int ea = r_begin & ~1; // the leading dimension is even: the same alignment for every plane
+            const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
+            const uint32_t tx = bytes_v + bytes_c + bytes_r + bytes_p + (uint32_t)NRHS * bytes_p * (CHECK ? 2u : 1u);
+            int *hdr = reinterpret_cast<int *>(st + L.hdr_off);
+            hdr[0] = k0;
+            hdr[1] = r_begin;
+            hdr[2] = rows;
+            mbar_expect_tx_only(&full[s], tx);
+            if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
+            if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
+            bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
+            bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
 #pragma unroll
-                for (int r = 0; r < NRHS; ++r) {
-                    bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
-                    // x_old: this tile's own rows, which nobody but this tile writes during the sweep
-                    if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
-                }
-            };
-            // release tile j to the compute warps: its dependencies are met (the copies were issued earlier)
-            auto make_runnable = [&](int j) {
-                int c, t;
-                fused_item(fa, bid + j * gsz, c, t);
-                if (c == 1) {
-                    const int2 d = fa.dep[t];
-                    fused_wait_tiles(fa.flags, d.x, d.y, epoch, ctl);
-                }
-                mbar_arrive(&full[j % STAGES]);
-            };
+            for (int r = 0; r < NRHS; ++r) {
+                bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
+                // x_old: this tile's own rows, which nobody but this tile writes during the sweep
+                if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
+            }
+        };
+        // release an item to the compute warps: its dependencies are met (its copies were issued earlier)
+        auto make_runnable = [&](const FusedItem &d, int j) {
+            if (d.dep_hi >= d.dep_lo && !(debug & 1)) fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl);
+            if (lane == 0) mbar_arrive(&full[j % STAGES]);
+        };
+        // items in flight: cur = item j (being computed), nxt = item j+1 (staged, about to be released); the record of
+        // item j+STAGES is fetched one iteration before it is issued
+        FusedItem cur, nxt, far;
+        if (my_items > 0) cur = load_item(0);
+        if (my_items > 1) nxt = load_item(1);
+        if (lane == 0) {
+            if (my_items > 0) issue(cur, 0);
+            if (STAGES >= 2 && my_items > 1) issue(nxt, 1);
 #pragma unroll
-            for (int s = 0; s < STAGES; ++s)
-                if (s < my_items) issue(load_desc(bid + s * gsz), s);
-            if (my_items > 0) make_runnable(0);
-            for (int j = 0; j < my_items; ++j) {
-                const int s = j % STAGES;
-                Desc next_desc;
-                const bool refill = j + STAGES < my_items;
-                if (refill) next_desc = load_desc(bid + (j + STAGES) * gsz); // L2 latency hidden behind the waits below
-                if (j + 1 < my_items) make_runnable(j + 1);
-                mbar_wait(&empty[s], (uint32_t)(j / STAGES) & 1u); // all compute warps have stored tile j's rows
-                int c, t;
-                fused_item(fa, bid + j * gsz, c, t);
-                if (c == 0) // (release: cumulative over the compute warps' stores observed through `empty`)
-                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fa.flags + t), "r"(epoch) : "memory");
-                if (refill) issue(next_desc, s);
+            for (int s = 2; s < STAGES; ++s)
+                if (s < my_items) issue(load_item(s), s);
+        }
+        if (my_items > 0) make_runnable(cur, 0);
+        for (int j = 0; j < my_items; ++j) {
+            const int s = j % STAGES;
+            const bool refill = j + STAGES < my_items;
+            if (refill) far = load_item(j + STAGES); // (L2 latency hidden behind the waits below)
+            if (j + 1 < my_items) make_runnable(nxt, j + 1);
+            mbar_wait(&empty[s], (uint32_t)(j / STAGES) & 1u); // every compute warp has stored item j's rows
+            if (lane == 0) {
+                if (refill) issue(far, s); // first the refill (the copies are what the pipeline waits for) ...
+                if (cur.c == 0 && !(debug & 2)) // ... then the flag (release: cumulative over the compute warps'
+                                                // stores observed through `empty`)
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + cur.t), "r"(epoch) : "memory");
+            }
+            cur = nxt;
+            if (STAGES == 2) {
+                nxt = far; // item j+2 is item (j+1)+1
+            } else if (j + 2 < my_items) {
+                nxt = load_item(j + 2);
             }
         }
     } else {
@@ -335,6 +374,7 @@ __global__ void __launch_bounds__(256) plan_fused_init(int *__restrict__ dep, in
 // Called by gsb_plan_build once the ring kernel (3/4) is available: decides p->fused_ok.
 int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t st) {
     p->fused_ok = false;
+    p->fused_items_lead = -1; // the item table belongs to the previous matrix
     if (!p->fused_allowed || p->n_colors != 2 || p->tile_rows != GS_THREADS) return GSB_OK;
     const int nt0 = p->blocks[0], nt1 = p->blocks[1];
     if (nt0 <= 0 || nt1 <= 0) return GSB_OK;
@@ -378,14 +418,16 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
                           const double *b, double *x, int64_t ld, bool check, GsCtl *ctl, double *partials,
                           cudaStream_t st, int *slots) {
     typedef void (*fused_fn)(const int *, const int *, const double *, const double *, const double *, double *, int64_t,
-                             int, GsCtl *, double *, const GsbFusedArgs);
+                             int, GsCtl *, double *, const FusedItem *, int, int *, int);
     fused_fn kern = check ? (fused_fn)gs_sweep_fused<NRHS, true, GS_RING_STAGES_DEFAULT>
                           : (fused_fn)gs_sweep_fused<NRHS, false, GS_RING_STAGES_DEFAULT>;
     const int smem = 64 + GS_RING_STAGES_DEFAULT * ring_layout(p->cap, NRHS, check, 0).stage_bytes;
     int per_sm = 1;
     GSB_TRY(gsb_kernel_occupancy((const void *)kern, smem, &per_sm, GS_FUSED_THREADS));
-    static int env_ctas = -1, env_lead = -1;
+    static int env_ctas = -1, env_lead = -1, env_debug = 0;
     if (env_ctas < 0) {
+        const char *dbg = getenv("GSB_FUSED_DEBUG"); // measurement aid, WRONG RESULTS: 1 = no dependency waits, 2 = no flags
+        env_debug = dbg ? atoi(dbg) : 0;
         const char *e = getenv("GSB_RING_CTAS");
         env_ctas = e ? atoi(e) : 0;
         e = getenv("GSB_FUSED_LEAD"); // extra lead in tiles on top of the dependency distance; default = the grid size
@@ -413,6 +455,14 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     if (lead > nt0) lead = nt0;
     fa.lead = lead;
     fa.nalt = nt1 < nt0 - lead ? nt1 : nt0 - lead;
+    // the item table belongs to (matrix, lead): rebuilt when the lead changes (stream-ordered before the launch)
+    GsbPlan *pm = const_cast<GsbPlan *>(p);
+    if (!pm->fused_items.p || pm->fused_items_lead != lead) {
+        GSB_TRY(pm->fused_items.alloc((int64_t)(nt0 + nt1) * (int64_t)(sizeof(FusedItem) / sizeof(int4))));
+        plan_fused_items<<<(nt0 + nt1 + 255) / 256, 256, 0, st>>>(fa, reinterpret_cast<FusedItem *>(pm->fused_items.p));
+        GSB_KERNEL_CHECK();
+        pm->fused_items_lead = lead;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(GS_FUSED_THREADS);
@@ -423,7 +473,8 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = gsb_pdl_mode((int64_t)p->color_start[2] - p->color_start[0]) ? 1 : 0;
-    GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, ci, va, dg, b, x, ld, p->cap, ctl, partials, (const GsbFusedArgs)fa));
+    GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, ci, va, dg, b, x, ld, p->cap, ctl, partials,
+                                (const FusedItem *)pm->fused_items.p, nt0 + nt1, p->fused_flags.p, env_debug));
     if (slots) *slots = grid;
     return GSB_OK;
 }

@@ -151,6 +151,44 @@ extern "C" int gsb_pano_gradients(const unsigned char *img, int W, int H, float 
     return GSB_OK;
 }
 
+// struct Gradients, second (mask-driven) constructor: first mask pixel per row, then one pass over the pixels
+__global__ void __launch_bounds__(128) pano_first_nonzero_kernel(const unsigned char *__restrict__ mask, int W, int H,
+                                                                 int *__restrict__ first) {
+    const int y = blockIdx.x * 128 + threadIdx.x;
+    if (y < H) first[y] = pano_first_nonzero(mask + (size_t)y * W, W);
+}
+__global__ void __launch_bounds__(256) pano_gradients_masked_kernel(const unsigned char *__restrict__ img,
+                                                                    const int *__restrict__ first, int W, int H,
+                                                                    float *__restrict__ gx, float *__restrict__ gy) {
+    const int64_t n = (int64_t)W * H;
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (int64_t)gridDim.x * 256)
+        pano_gradients_masked_at(img, first, W, H, p, gx, gy);
+}
+
+extern "C" int gsb_pano_gradients_masked(const unsigned char *img, const unsigned char *mask, int W, int H, float *gx,
+                                         float *gy) {
+    if (!img || !mask || !gx || !gy) return GSB_ERR_ARG;
+    GSB_TRY(pano_check("pano_gradients_masked", W, H));
+    cudaStream_t st = gsb_cur_stream();
+    const int64_t n = (int64_t)W * H;
+    DevBuf<unsigned char> di, dm;
+    DevBuf<float> dgx, dgy;
+    DevBuf<int> first;
+    GSB_TRY(up(di, img, 3 * n, st));
+    GSB_TRY(up(dm, mask, n, st));
+    GSB_TRY(dgx.alloc(3 * n));
+    GSB_TRY(dgy.alloc(3 * n));
+    GSB_TRY(first.alloc(H));
+    pano_first_nonzero_kernel<<<(H + 127) / 128, 128, 0, st>>>(dm.p, W, H, first.p);
+    GSB_KERNEL_CHECK();
+    pano_gradients_masked_kernel<<<pix_blocks(n), 256, 0, st>>>(di.p, first.p, W, H, dgx.p, dgy.p);
+    GSB_KERNEL_CHECK();
+    GSB_TRY(down(gx, dgx, 3 * n, st));
+    GSB_TRY(down(gy, dgy, 3 * n, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
 extern "C" int gsb_pano_merge2_f32(float *target, const float *src, const unsigned char *target_mask,
                                    const unsigned char *src_outer_mask, const unsigned char *src_inner_mask, int W,
                                    int H) {

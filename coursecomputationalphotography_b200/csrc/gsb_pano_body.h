@@ -94,18 +94,67 @@ GSB_HD void pano_gradients_at(const unsigned char *img, int W, int H, int64_t p,
     }
 }
 
+// struct Gradients, second constructor (hw8_pa.cc:638-676), mask-driven.  Per image row y < H-1 the reference finds
+// the first non-zero mask pixel x0 (its walk does not stop at the row end, but then x >= W and nothing else happens),
+// writes ZeroGradientAt (:325-334: grad_x = pixel (y, x0), grad_y = pixel (y+1, x0-1), NOT differences) at column
+// x0 - 1 when x0 < W-2, and GradientAt at every x in [x0, W-2] -- the loop tests the mask pointer it stopped at, so it
+// runs to the row end whatever the mask holds after x0.  Everything else stays 0.  Mat::at(y, -1) is the previous
+// row's last pixel on a continuous image, so x0 == 0 writes entry (y-1, W-1); for y == 0 that lies outside the image
+// and is dropped (zero guard rows, see pano_enforce_bound_at).  first[y] = x0, or W when the row has no mask pixel.
+// Bounded per-pixel form: every entry is written by at most one of the three cases.
+GSB_HD int pano_first_nonzero(const unsigned char *mask_row, int W) {
+    int x = 0;
+    while (x < W && mask_row[x] == 0) ++x;
+    return x;
+}
+GSB_HD void pano_gradients_masked_at(const unsigned char *img, const int *first, int W, int H, int64_t p, float *gx,
+                                     float *gy) {
+    const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    float ox[3] = {0.f, 0.f, 0.f}, oy[3] = {0.f, 0.f, 0.f};
+    const int x0 = y < H - 1 ? first[y] : W;
+    if (x0 < W && x >= x0 && x <= W - 2) { // GradientAt
+        for (int c = 0; c < 3; ++c) {
+            const int color1 = img[p * 3 + c], color2 = img[(p + 1) * 3 + c], color3 = img[(p + W) * 3 + c];
+            ox[c] = (float)(color2 - color1);
+            oy[c] = (float)(color3 - color1);
+        }
+    } else if (x0 < W - 2 && x0 >= 1 && x == x0 - 1) { // ZeroGradientAt(m, x0 - 1, y)
+        for (int c = 0; c < 3; ++c) {
+            ox[c] = (float)img[(p + 1) * 3 + c];
+            oy[c] = (float)img[(p + W) * 3 + c];
+        }
+    } else if (x == W - 1 && y + 1 < H - 1 && first[y + 1] == 0 && 0 < W - 2) { // row y+1's ZeroGradientAt at column -1
+        for (int c = 0; c < 3; ++c) {
+            ox[c] = (float)img[(p + 1) * 3 + c];
+            oy[c] = (float)img[(p + W) * 3 + c];
+        }
+    }
+    for (int c = 0; c < 3; ++c) {
+        gx[p * 3 + c] = ox[c];
+        gy[p * 3 + c] = oy[c];
+    }
+}
+
 // EnforceGradientBound (hw8_pa.cc:468-498) for mask pixel p = i*W + j: GradientAt(src) into rows i, i-1, i+1 of
-// dx / dy (Mat::at on a continuous Mat: column W-1 reads the next row's first pixel).  Rows outside [0, H-2]
-// would touch memory outside the buffers (undefined upstream) and are skipped.  Concurrent pixels may write the
-// same entry; they write the same value.
+// dx / dy (Mat::at on a continuous Mat: column W-1 reads the next row's first pixel).  The walk leaves the images at
+// the first and last row (rows -1 and H are written, row H is read) -- undefined upstream.  Semantics here, pinned to
+// the compiled reference running over images with zero guard rows (oracle/ref_pano_shim.cc): pixels outside the
+// image read as 0, writes outside it are dropped.  Concurrent pixels may write the same entry; they write the same
+// value.
 GSB_HD void pano_enforce_bound_at(const unsigned char *src, const unsigned char *mask, int W, int H, int64_t p,
                                   float *dx, float *dy) {
     if (!mask[p]) return;
     const int i = (int)(p / W);
-    const int64_t j = p - (int64_t)i * W;
+    const int64_t j = p - (int64_t)i * W, n = (int64_t)W * H;
     for (int t = 0; t < 3; ++t) {
         const int r = t == 0 ? i : (t == 1 ? i - 1 : i + 1);
-        if (r < 0 || r > H - 2) continue;
-        pano_gradient_write(src, W, (int64_t)r * W + j, dx, dy);
+        if (r < 0 || r > H - 1) continue;
+        const int64_t q = (int64_t)r * W + j;
+        for (int c = 0; c < 3; ++c) {
+            const int color1 = src[q * 3 + c];
+            const int color2 = q + 1 < n ? src[(q + 1) * 3 + c] : 0, color3 = q + W < n ? src[(q + W) * 3 + c] : 0;
+            dx[q * 3 + c] = (float)(color2 - color1);
+            dy[q * 3 + c] = (float)(color3 - color1);
+        }
     }
 }

@@ -33,12 +33,16 @@ def MaskImage(src, mask):
     return out
 
 
-def Gradients(img):
-    """struct Gradients(m), hw8_pa.cc:604-636 -> (x, y), each (H, W, 3) float32"""
+def Gradients(img, mask=None):
+    """struct Gradients, hw8_pa.cc:604-636 (m) and :638-676 (m, mask) -> (x, y), each (H, W, 3) float32"""
     img = _img(img)
     H, W, _ = img.shape
     gx, gy = np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32)
-    check(load().gsb_pano_gradients(ptr(img), W, H, ptr(gx), ptr(gy)), "gsb_pano_gradients")
+    if mask is None:
+        check(load().gsb_pano_gradients(ptr(img), W, H, ptr(gx), ptr(gy)), "gsb_pano_gradients")
+    else:
+        mask = _mask(mask, (H, W))
+        check(load().gsb_pano_gradients_masked(ptr(img), ptr(mask), W, H, ptr(gx), ptr(gy)), "gsb_pano_gradients_masked")
     return gx, gy
 
 

@@ -271,6 +271,10 @@ int gsb_gdf_release(void);
 int gsb_pano_mask_image(const unsigned char *src, const unsigned char *mask, int W, int H, unsigned char *out);
 /* struct Gradients(m) :604-636 -- GradientAt :314-323 for y < H-1, x < W-1 (0 elsewhere) */
 int gsb_pano_gradients(const unsigned char *img, int W, int H, float *gx, float *gy);
+/* struct Gradients, second constructor (mask-driven)            hw8_pa.cc:638-676, ZeroGradientAt :325-334
+ * per row: ZeroGradientAt left of the first mask pixel, GradientAt from there to the row end, 0 elsewhere */
+int gsb_pano_gradients_masked(const unsigned char *img, const unsigned char *mask, int W, int H, float *gx,
+                              float *gy);
 /* MergeImage2<float>(target, src, target_mask, src_outer_mask, src_inner_mask) :338-385; target in place */
 int gsb_pano_merge2_f32(float *target, const float *src, const unsigned char *target_mask,
                         const unsigned char *src_outer_mask, const unsigned char *src_inner_mask, int W, int H);

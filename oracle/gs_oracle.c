@@ -547,6 +547,41 @@ void orc_pano_gradients(const unsigned char *img, int W, int H, float *gx, float
         }
 }
 
+/* struct Gradients, second constructor (:638-676), literal: per row the pointer walk to the first non-zero mask byte
+ * (not bounded by the row: it reads on into the following rows; `end` guards the buffer, where the reference's
+ * stand-in images carry a terminating sentinel), ZeroGradientAt (:325-334) at column x-1 when x < W-2, then
+ * GradientAt while x < W-1 and the byte the walk stopped at is non-zero (the loop never advances the pointer).
+ * Mat::at(y, -1) addresses the previous row's last pixel on a continuous image; outside the image: dropped. */
+void orc_pano_gradients_masked(const unsigned char *img, const unsigned char *mask, int W, int H, float *gx, float *gy) {
+    const int64_t n = (int64_t)W * H;
+    for (int64_t i = 0; i < 3 * n; ++i) gx[i] = gy[i] = 0.0f;
+    for (int y = 0; y < H - 1; ++y) {
+        int64_t q = (int64_t)y * W; /* ptr */
+        int64_t x = 0;
+        while (q < n && mask[q] == 0) {
+            ++q;
+            ++x;
+        }
+        const int stopped_on = q < n ? mask[q] : 1; /* the sentinel */
+        if (x < W - 2) { /* ZeroGradientAt(m, x-1, y) */
+            const int64_t p = (int64_t)y * W + (x - 1);
+            if (p >= 0)
+                for (int c = 0; c < 3; ++c) {
+                    gx[p * 3 + c] = (float)img[(p + 1) * 3 + c];
+                    gy[p * 3 + c] = (float)img[(p + W) * 3 + c];
+                }
+        }
+        for (; x < W - 1 && stopped_on; ++x) {
+            const int64_t p = (int64_t)y * W + x;
+            for (int c = 0; c < 3; ++c) {
+                const int color1 = img[p * 3 + c], color2 = img[(p + 1) * 3 + c], color3 = img[(p + W) * 3 + c];
+                gx[p * 3 + c] = (float)(color2 - color1);
+                gy[p * 3 + c] = (float)(color3 - color1);
+            }
+        }
+    }
+}
+
 /* MergeImage2<float> (:338-385): per row, skip to the source's outer mask, skip on while the source's inner mask
  * is 0 and the target is already covered, then copy the rest of the outer-mask run.  `end` = H*W guards the
  * reads the reference makes past the buffer. */
@@ -608,20 +643,24 @@ void orc_pano_merge_u8(unsigned char *target, const unsigned char *src, const un
 }
 
 /* EnforceGradientBound (:468-498): where the mask is set, GradientAt(src) into rows i, i-1, i+1 of dx / dy.
- * Flat indexing as Mat::at on a continuous Mat (x + 1 == W reads the next row's first pixel); rows outside
- * [0, H-2] would touch memory outside the buffers and are skipped. */
+ * Flat indexing as Mat::at on a continuous Mat (x + 1 == W reads the next row's first pixel).  At the first / last
+ * row the reference walks out of the images (undefined upstream); pinned here to the compiled reference running over
+ * images with zero guard rows (ref_pano_shim.cc): outside pixels read as 0, outside writes are dropped. */
 void orc_pano_enforce_gradient_bound(float *dx, float *dy, const unsigned char *src, const unsigned char *mask, int W,
                                      int H) {
+    const int64_t n = (int64_t)W * H;
     for (int i = 0; i < H; ++i)
         for (int j = 0; j < W; ++j) {
             if (!mask[(int64_t)i * W + j]) continue;
             const int rows[3] = {i, i - 1, i + 1};
             for (int t = 0; t < 3; ++t) {
                 const int r = rows[t];
-                if (r < 0 || r > H - 2) continue;
+                if (r < 0 || r > H - 1) continue;
                 const int64_t p = (int64_t)r * W + j;
                 for (int c = 0; c < 3; ++c) {
-                    const int color1 = src[p * 3 + c], color2 = src[(p + 1) * 3 + c], color3 = src[(p + W) * 3 + c];
+                    const int color1 = src[p * 3 + c];
+                    const int color2 = p + 1 < n ? src[(p + 1) * 3 + c] : 0;
+                    const int color3 = p + W < n ? src[(p + W) * 3 + c] : 0;
                     dx[p * 3 + c] = (float)(color2 - color1);
                     dy[p * 3 + c] = (float)(color3 - color1);
                 }

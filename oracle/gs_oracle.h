@@ -85,6 +85,7 @@ void orc_gdf_writeback(const double *x, int64_t n, unsigned char *out);
 /* lab8 panorama right-hand-side producers (hw8_pa.cc:338-498, :604-636) */
 void orc_pano_mask_image(const unsigned char *src, const unsigned char *mask, int W, int H, unsigned char *out);
 void orc_pano_gradients(const unsigned char *img, int W, int H, float *gx, float *gy);
+void orc_pano_gradients_masked(const unsigned char *img, const unsigned char *mask, int W, int H, float *gx, float *gy);
 void orc_pano_merge2_f32(float *target, const float *src, const unsigned char *target_mask,
                          const unsigned char *src_outer_mask, const unsigned char *src_inner_mask, int W, int H);
 void orc_pano_merge_u8(unsigned char *target, const unsigned char *src, const unsigned char *target_mask,

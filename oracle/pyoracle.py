@@ -79,6 +79,8 @@ def _oracle():
         L.orc_gdf_writeback.argtypes = [_f64p, C.c_int64, _u8p]
         L.orc_pano_mask_image.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _u8p]
         L.orc_pano_gradients.argtypes = [_u8p, C.c_int, C.c_int, _f32p, _f32p]
+        L.orc_pano_gradients_masked.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _f32p, _f32p]
+        L.orc_pano_gradients_masked.restype = None
         L.orc_pano_merge2_f32.argtypes = [_f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int]
         L.orc_pano_merge_u8.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_double, C.c_int, C.c_int]
         L.orc_pano_enforce_gradient_bound.argtypes = [_f32p, _f32p, _u8p, _u8p, C.c_int, C.c_int]
@@ -293,6 +295,15 @@ def pano_gradients(img):
     return gx, gy
 
 
+def pano_gradients_masked(img, mask):
+    """struct Gradients, second constructor (hw8_pa.cc:638-676)"""
+    img, mask = _a(img, np.uint8), _a(mask, np.uint8)
+    H, W, _ = img.shape
+    gx, gy = np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32)
+    _oracle().orc_pano_gradients_masked(img.reshape(-1), mask.reshape(-1), W, H, gx.reshape(-1), gy.reshape(-1))
+    return gx, gy
+
+
 def pano_merge2_f32(target, src, target_mask, src_outer_mask, src_inner_mask):
     """MergeImage2<float>: returns the updated copy of `target` (H, W, 3) float32."""
     out = _a(target, np.float32).copy()
@@ -328,6 +339,82 @@ def pano_enforce_gradient_bound(dx, dy, src, mask):
     H, W, _ = dx.shape
     _oracle().orc_pano_enforce_gradient_bound(dx.reshape(-1), dy.reshape(-1), _a(src, np.uint8).reshape(-1),
                                               _a(mask, np.uint8).reshape(-1), W, H)
+    return dx, dy
+
+
+# --------------------------------------------------------------------------------------
+# The compiled reference's lab8 producers (oracle/_ref/libpanoref.so: hw8_pa.cc:316-498 and :602-676, unmodified,
+# over a stand-in for cv::Mat whose images carry zero guard rows -- see ref_pano_shim.cc)
+# --------------------------------------------------------------------------------------
+PANO_REF_SO = os.path.join(_HERE, "_ref", "libpanoref.so")
+_pref = None
+
+
+def pano_ref_available():
+    return os.path.exists(PANO_REF_SO)
+
+
+def _panoref():
+    global _pref
+    if _pref is None:
+        if not os.path.exists(PANO_REF_SO):
+            raise RuntimeError("oracle/_ref/libpanoref.so missing: run `make -C oracle` where /root/reference exists")
+        R = C.CDLL(PANO_REF_SO)
+        R.ref_pano_mask_image.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _u8p]
+        R.ref_pano_gradients.argtypes = [_u8p, C.c_void_p, C.c_int, C.c_int, _f32p, _f32p]
+        R.ref_pano_merge2_f32.argtypes = [_f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int]
+        R.ref_pano_merge_u8.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_double, C.c_int, C.c_int]
+        R.ref_pano_enforce_gradient_bound.argtypes = [_f32p, _f32p, _u8p, _u8p, C.c_int, C.c_int]
+        for fn in (R.ref_pano_mask_image, R.ref_pano_gradients, R.ref_pano_merge2_f32, R.ref_pano_merge_u8,
+                   R.ref_pano_enforce_gradient_bound):
+            fn.restype = None
+        _pref = R
+    return _pref
+
+
+def ref_pano_mask_image(src, mask):
+    src, mask = _a(src, np.uint8), _a(mask, np.uint8)
+    H, W = mask.shape
+    out = np.empty_like(src)
+    _panoref().ref_pano_mask_image(src.reshape(-1), mask.reshape(-1), W, H, out.reshape(-1))
+    return out
+
+
+def ref_pano_gradients(img, mask=None):
+    """struct Gradients: first constructor, or (mask given) the mask-driven second one (hw8_pa.cc:638-676)."""
+    img = _a(img, np.uint8)
+    H, W, _ = img.shape
+    gx, gy = np.empty((H, W, 3), np.float32), np.empty((H, W, 3), np.float32)
+    mp = None
+    if mask is not None:
+        mask = _a(mask, np.uint8)
+        mp = mask.ctypes.data
+    _panoref().ref_pano_gradients(img.reshape(-1), mp, W, H, gx.reshape(-1), gy.reshape(-1))
+    return gx, gy
+
+
+def ref_pano_merge2_f32(target, src, target_mask, src_outer_mask, src_inner_mask):
+    out = _a(target, np.float32).copy()
+    H, W, _ = out.shape
+    _panoref().ref_pano_merge2_f32(out.reshape(-1), _a(src, np.float32).reshape(-1), _a(target_mask, np.uint8).reshape(-1),
+                                   _a(src_outer_mask, np.uint8).reshape(-1), _a(src_inner_mask, np.uint8).reshape(-1), W, H)
+    return out
+
+
+def ref_pano_merge_u8(target, src, target_mask, src_mask, skip_how_many):
+    out = _a(target, np.uint8).copy()
+    H, W = out.shape[:2]
+    ch = 3 if out.ndim == 3 else 1
+    _panoref().ref_pano_merge_u8(out.reshape(-1), _a(src, np.uint8).reshape(-1), _a(target_mask, np.uint8).reshape(-1),
+                                 _a(src_mask, np.uint8).reshape(-1), ch, float(skip_how_many), W, H)
+    return out
+
+
+def ref_pano_enforce_gradient_bound(dx, dy, src, mask):
+    dx, dy = _a(dx, np.float32).copy(), _a(dy, np.float32).copy()
+    H, W, _ = dx.shape
+    _panoref().ref_pano_enforce_gradient_bound(dx.reshape(-1), dy.reshape(-1), _a(src, np.uint8).reshape(-1),
+                                               _a(mask, np.uint8).reshape(-1), W, H)
     return dx, dy
 
 

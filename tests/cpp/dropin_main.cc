@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -27,7 +28,68 @@ static bool CheckEqual(const SparseMatrix<T> &mat, const std::vector<std::vector
         }                                                        \
     } while (0)
 
-int main() {
+// A Dirichlet-masked 5-point blend system on a W x H frame (SURVEY 8d C3 in miniature): unknowns = masked pixels in
+// raster order, row 4 v_p - sum of masked neighbours = rhs; colours = pixel parity.  Solved through the drop-in
+// class on one device and on `ndev` devices (SparseMatrix<>::setDevices): same bits.
+static int multi_device_check(int ndev) {
+    const int W = 1024, H = 1024;
+    std::vector<int> id((size_t)W * H, -1), px;
+    for (int y = 1; y < H - 1; ++y)
+        for (int x = 1; x < W - 1; ++x) {
+            const int cx = x % 97 - 48, cy = y % 89 - 44; // a lattice of blobs, ~55 % of the frame
+            if (cx * cx + cy * cy < 36 * 36) {
+                id[(size_t)y * W + x] = (int)px.size();
+                px.push_back(y * W + x);
+            }
+        }
+    const int n = (int)px.size();
+    std::vector<double> va, b((size_t)3 * n);
+    std::vector<int> ro, ci, colors((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const int x = px[i] % W, y = px[i] / W;
+        colors[i] = (x + y) & 1;
+        ro.push_back((int)va.size());
+        const int nb[4] = {px[i] - W, px[i] - 1, px[i] + 1, px[i] + W};
+        double rhs = 0;
+        bool diag_done = false;
+        for (int k = 0; k < 4; ++k) {
+            const int j = id[(size_t)nb[k]];
+            if (k == 2 && !diag_done) { ci.push_back(i); va.push_back(4.0); diag_done = true; }
+            if (j >= 0) { ci.push_back(j); va.push_back(-1.0); }
+            else rhs += 100.0 + 50.0 * std::sin(0.01 * (nb[k] % W)) * std::cos(0.013 * (nb[k] / W));
+        }
+        for (int r = 0; r < 3; ++r) b[(size_t)r * n + i] = rhs * (1.0 + 0.1 * r) + ((x * 7 + y * 3) % 5 - 2);
+    }
+    SparseMatrix<double> sp;
+    sp.initializeFromEigenRowMajor(va.data(), (int)va.size(), ro.data(), n, ci.data(), n, nullptr, 0);
+    REQUIRE(SparseMatrix<double>::lastStatus() == GSB_OK, "import of the masked system");
+    REQUIRE(gsb_matrix_analyze(sp.device_handle(), GSB_ORDER_USER, colors.data()) == GSB_OK, "parity colouring");
+    REQUIRE(SparseMatrix<double>::setDevices({}), "setDevices({})");
+    auto x1 = sp.gaussSeidelMulti(b, 3, 1e-3, 400);
+    const int sweeps1 = sp.last_stats.sweeps, kernel1 = sp.last_stats.kernel_used;
+    REQUIRE(kernel1 < 10 && sweeps1 > 10 && sweeps1 < 400, "single-device solve of the masked system");
+    std::vector<int> devs;
+    for (int d = 0; d < ndev; ++d) devs.push_back(d);
+    REQUIRE(gsb_set_devices(devs.data(), ndev) == GSB_OK, "gsb_set_devices");
+    auto xn = sp.gaussSeidelMulti(b, 3, 1e-3, 400);
+    REQUIRE(SparseMatrix<double>::lastStatus() == GSB_OK, "multi-device solve");
+    REQUIRE(sp.last_stats.kernel_used >= 30, "the solve ran on row strips (fused halo + stop-rule exchange)");
+    REQUIRE(sp.last_stats.sweeps == sweeps1, "same stop sweep on 1 and N devices");
+    REQUIRE(std::memcmp(x1.data(), xn.data(), sizeof(double) * x1.size()) == 0, "N-device solution == 1-device solution, bit for bit");
+    // the reference signature (one right-hand side, defaults) takes the same path
+    std::vector<double> b0(b.begin(), b.begin() + n);
+    auto xa = sp.gaussSeidel(b0, 1e-3, 400);
+    REQUIRE(sp.last_stats.kernel_used >= 30, "gaussSeidel(b) on row strips");
+    SparseMatrix<double>::setDevices({});
+    auto xb = sp.gaussSeidel(b0, 1e-3, 400);
+    REQUIRE(std::memcmp(xa.data(), xb.data(), sizeof(double) * xa.size()) == 0, "gaussSeidel(b): N devices == 1 device");
+    std::printf("dropin multi-device ok: masked %dx%d (n = %d), %d devices == 1 device bit for bit, %d sweeps\n", W, H, n,
+                ndev, sweeps1);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc >= 3 && std::string(argv[1]) == "mgpu") return multi_device_check(std::atoi(argv[2]));
     try {
         SparseMatrix<int> spi;
         std::vector<std::vector<int>> mat = {{1, 0, 0, 1, 0}, {0, 0, 0, 0, 0}, {8, 0, 1, 0, 0}};
@@ -99,6 +161,16 @@ int main() {
         for (size_t i = 0; i < x3.size(); ++i) err = std::max(err, std::fabs(x3[i] - xs[i]));
         REQUIRE(err < 1e-8, "3-RHS Gauss-Seidel on an imported CSR");
         REQUIRE(sp3.last_stats.n_colors == 2, "1-D chain is red-black");
+        // errors do not throw (the reference's release build never does): status + message are kept instead
+        SparseMatrix<double> rect;
+        std::vector<int> rr = {0, 1}, rc = {0, 3};
+        std::vector<double> rv = {1.0, 2.0};
+        rect.initializeFromVector(rr, std::move(rc), std::move(rv)); // 2 x 4
+        REQUIRE(SparseMatrix<double>::lastStatus() == GSB_OK, "rectangular matrix assembles");
+        auto xr = rect.gaussSeidel(std::vector<double>(4, 1.0));
+        REQUIRE(SparseMatrix<double>::lastStatus() == GSB_ERR_SHAPE && xr.size() == 4 && xr[0] == 1.0,
+                "gaussSeidel on a rectangular matrix: status kept, start vector returned, nothing thrown");
+        REQUIRE(std::string(SparseMatrix<double>::lastError()).find("square") != std::string::npos, "lastError()");
         std::printf("dropin ok: fixtures T1-T5, 4x4 GS/CG/PCG, triplets, import + 3-RHS GS (%d sweeps, max err %.2e)\n",
                     sp3.last_stats.sweeps, err);
         return 0;

@@ -1,6 +1,7 @@
 // Host build of the per-row / per-pixel bodies of the lab8 panorama kernels
 // (coursecomputationalphotography_b200/csrc/gsb_pano_body.h) for tests/test_pano_host.py.  Test infrastructure only.
 // Each function applies the body exactly as the corresponding kernel does (run finder per row, then the copy).
+#include <vector>
 #include "../../coursecomputationalphotography_b200/csrc/gsb_pano_body.h"
 
 extern "C" void host_pano_mask_image(const unsigned char *src, const unsigned char *mask, int W, int H,
@@ -8,6 +9,12 @@ extern "C" void host_pano_mask_image(const unsigned char *src, const unsigned ch
     for (int64_t p = 0; p < (int64_t)W * H; ++p) pano_mask_image_at(src, mask, p, out);
 }
 
+extern "C" void host_pano_gradients_masked(const unsigned char *img, const unsigned char *mask, int W, int H, float *gx,
+                                           float *gy) {
+    std::vector<int> first((size_t)H);
+    for (int y = 0; y < H; ++y) first[(size_t)y] = pano_first_nonzero(mask + (size_t)y * W, W);
+    for (int64_t p = 0; p < (int64_t)W * H; ++p) pano_gradients_masked_at(img, first.data(), W, H, p, gx, gy);
+}
 extern "C" void host_pano_gradients(const unsigned char *img, int W, int H, float *gx, float *gy) {
     for (int64_t p = 0; p < (int64_t)W * H; ++p) pano_gradients_at(img, W, H, p, gx, gy);
 }

@@ -23,6 +23,8 @@ def host(tmp_path_factory):
     f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
     L.host_pano_mask_image.argtypes = [u8, u8, C.c_int, C.c_int, u8]
     L.host_pano_gradients.argtypes = [u8, C.c_int, C.c_int, f32, f32]
+    L.host_pano_gradients_masked.argtypes = [u8, u8, C.c_int, C.c_int, f32, f32]
+    L.host_pano_gradients_masked.restype = None
     L.host_pano_merge2_f32.argtypes = [f32, f32, u8, u8, u8, C.c_int, C.c_int]
     L.host_pano_merge_u8.argtypes = [u8, u8, u8, u8, C.c_int, C.c_double, C.c_int, C.c_int]
     L.host_pano_enforce_gradient_bound.argtypes = [f32, f32, u8, u8, C.c_int, C.c_int]

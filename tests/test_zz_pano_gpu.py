@@ -51,6 +51,19 @@ def test_primitives_bitexact(gsb, oracle_mod, H, W):
     dx, dy = pano.EnforceGradientBound(gx, gy, src, bound)
     wx, wy = oracle_mod.pano_enforce_gradient_bound(ox, oy, src, bound)
     assert np.array_equal(dx, wx) and np.array_equal(dy, wy)
+    # struct Gradients, second (mask-driven) constructor, hw8_pa.cc:638-676
+    for mk in (tmask, outer, bound, np.zeros_like(bound), np.full_like(bound, 255)):
+        mx, my = pano.Gradients(img, mk)
+        qx, qy = oracle_mod.pano_gradients_masked(img, mk)
+        assert np.array_equal(mx, qx) and np.array_equal(my, qy)
+        if oracle_mod.pano_ref_available():  # ... and the compiled reference itself
+            rx, ry = oracle_mod.ref_pano_gradients(img, mk)
+            assert np.array_equal(mx, rx) and np.array_equal(my, ry)
+    if oracle_mod.pano_ref_available():
+        rx, ry = oracle_mod.ref_pano_enforce_gradient_bound(ox, oy, src, bound)
+        assert np.array_equal(dx, rx) and np.array_equal(dy, ry)
+        assert np.array_equal(pano.MergeImage2(tgt, gx, tmask, outer, inner),
+                              oracle_mod.ref_pano_merge2_f32(tgt, ox, tmask, outer, inner))
 
 
 def _erode_cross(m):
