@@ -138,7 +138,7 @@ GSB_HD void pano_gradients_masked_at(const unsigned char *img, const int *first,
 // EnforceGradientBound (hw8_pa.cc:468-498) for mask pixel p = i*W + j: GradientAt(src) into rows i, i-1, i+1 of
 // dx / dy (Mat::at on a continuous Mat: column W-1 reads the next row's first pixel).  The walk leaves the images at
 // the first and last row (rows -1 and H are written, row H is read) -- undefined upstream.  Semantics here, pinned to
-// the compiled reference running over images with zero guard rows (oracle/ref_pano_shim.cc): pixels outside the
+// the compiled reference running over images with zero guard rows (see tests/test_pano_vs_reference.py): pixels outside the
 // image read as 0, writes outside it are dropped.  Concurrent pixels may write the same entry; they write the same
 // value.
 GSB_HD void pano_enforce_bound_at(const unsigned char *src, const unsigned char *mask, int W, int H, int64_t p,
