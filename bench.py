@@ -48,6 +48,11 @@ def parse():
     p.add_argument("--no-time-to-tol", action="store_true", help="skip the time-to-tolerance leg (masked blend)")
     p.add_argument("--time-to-tol-only", action="store_true", help=argparse.SUPPRESS)
     p.add_argument("--no-default-eps", action="store_true", help="time-to-tol: skip the epsilon = 1e-6 run")
+    p.add_argument("--no-other-configs", action="store_true", help="skip the legs for BASELINE configs[0], [1], [4]")
+    p.add_argument("--other-config-only", default=None, help=argparse.SUPPRESS)
+    p.add_argument("--no-c4", action="store_true", help="N >= 2: skip the 16384^2 strip leg (BASELINE configs[3])")
+    p.add_argument("--c4-size", type=int, default=16384)
+    p.add_argument("--c5-n", type=int, default=10_000_000, help="rows of the random SPD system (configs[4])")
     return p.parse_args()
 
 
@@ -384,6 +389,10 @@ def run_ours(args):
             line["time_to_tol"] = time_to_tol_child(args)
         except Exception as e:
             line["time_to_tol"] = {"error": repr(e)[:300]}
+    if not args.no_other_configs:
+        line["other_configs"] = {"c1_lab3_n1e4": other_config_child(args, "c1", 120),
+                                 "c2_poisson_1024": other_config_child(args, "c2", 120),
+                                 "c5_random_spd": other_config_child(args, "c5", 420)}
     print(json.dumps(line))
 
 
@@ -480,6 +489,115 @@ def run_time_to_tol(args):
     print(json.dumps(out))
 
 
+# --------------------------------------------------------------------------------------------------
+# The other BASELINE configurations, as extra keys on the N = 1 line (each in a child process, bounded):
+#   configs[0] C1  lab3 diagonally dominant system, n = 1e4: microseconds per solve (reference defaults) next to the
+#                  compiled reference on this host, no roofline claim (launch-latency bound)
+#   configs[1] C2  1024^2 single channel: throughput; the 92 MB working set is L2-resident, so the bytes/s figure is
+#                  an EFFECTIVE one (stated), not an HBM claim
+#   configs[4] C5  random sparse SPD, n = 1e7, ~27 entries per row: unsorted triplets -> device radix sort
+#                  (initializeFromTriplets) -> Jones-Plassmann multicolour -> sweeps; Gnnz/s, algorithmic GB/s
+#   (configs[3] C4, 16384^2 row strips, is reported by the N >= 2 arm: dist_bench.py)
+# --------------------------------------------------------------------------------------------------
+def run_other_config(args):
+    import coursecomputationalphotography_b200 as pkg
+    from coursecomputationalphotography_b200 import workloads as wl
+    which = args.other_config_only
+    peak, _ = peaks()
+    if which == "c1":
+        r, c, v, b, xstar = wl.diag_dominant_system(10_000, 4, seed=42)
+        sp = pkg.SparseMatrix(np.float64)
+        sp.initializeFromVector(r, c, v)
+        sp.gaussSeidel(b)  # analysis, plan, graph capture
+        reps, t = 20, []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            x = sp.gaussSeidel(b)
+            t.append((time.perf_counter() - t0) * 1e6)
+        st = sp.last_stats
+        out = {"workload": "lab3 diag-dominant, n = 10000, 4 off-diagonals per row (BASELINE configs[0])",
+               "sweeps": int(st.sweeps), "n_colors": int(st.n_colors), "last_eps": float(st.last_eps[0]),
+               "us_per_solve_wall_median": float(np.median(t)), "us_per_solve_wall_min": float(min(t)),
+               "us_device_sweep_loop": float(st.solve_ms) * 1e3, "includes": "b H2D, sweeps (CUDA-graph batches), x D2H",
+               "max_abs_vs_xstar": float(np.abs(x - xstar).max()), "roofline": "none claimed: launch-latency bound"}
+        try:
+            from oracle import pyoracle
+            if pyoracle.ref_available():
+                ref = pyoracle.Ref(2, "f64").init_from_vector(r, c, v)
+                tr = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    xr = ref.gauss_seidel(b)
+                    tr.append((time.perf_counter() - t0) * 1e6)
+                out["reference_cpu_us_per_solve"] = float(np.median(tr))
+                out["max_abs_vs_reference"] = float(np.abs(x - xr).max())
+        except Exception as e:  # the CPU arm is a courtesy here
+            out["reference_cpu_error"] = repr(e)[:200]
+    elif which == "c2":
+        W = H = 1024
+        sp = pkg.SparseMatrix(np.float64)
+        sp.poisson(W, H)
+        b = synth_rhs(pkg, wl, W, H, 1)[0]
+        sweeps = 2000
+        sp.gaussSeidel(b, epsilon=0.0, max_iteration=50)
+        sp.gaussSeidel(b, epsilon=0.0, max_iteration=sweeps)
+        st = sp.last_stats
+        ab = algorithmic_bytes_per_sweep(sp._nnz, W * H, 1)
+        gbs = ab * st.sweeps / (st.solve_ms * 1e-3) / 1e9
+        out = {"workload": "poisson_1024x1024_x1ch_full_grid (BASELINE configs[1])", "n": W * H, "nnz": int(sp._nnz),
+               "sweeps": int(st.sweeps), "ms": float(st.solve_ms), "kernel": int(st.kernel_used),
+               "Gnnz_per_s": sp._nnz * st.sweeps / (st.solve_ms * 1e-3) / 1e9, "sweeps_per_s": st.sweeps / (st.solve_ms * 1e-3),
+               "effective_GBps": gbs, "effective_frac_of_hbm_peak": gbs / peak,
+               "note": "working set %.0f MB per sweep is L2-resident (126 MB): effective bytes/s, not an HBM figure" % (ab / 1e6)}
+    elif which == "c5":
+        n = args.c5_n
+        t0 = time.perf_counter()
+        rows, cols, vals = wl.random_spd_coo(n, 13, seed=5)
+        t_gen = time.perf_counter() - t0
+        sp = pkg.SparseMatrix(np.float64)
+        sp.initialize(n, n)
+        t0 = time.perf_counter()
+        sp.initializeFromTriplets(rows, cols, vals)
+        t_asm = time.perf_counter() - t0
+        del rows, cols, vals
+        nnz = int(sp._nnz)
+        rng = np.random.default_rng(1)
+        xstar = rng.uniform(-1.0, 1.0, n)
+        b = sp.applyToVector(xstar)
+        t0 = time.perf_counter()
+        info = sp.analyze()
+        t_ana = time.perf_counter() - t0
+        sweeps = 20
+        sp.gaussSeidel(b, epsilon=0.0, max_iteration=3)
+        x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=sweeps)
+        st = sp.last_stats
+        ab = algorithmic_bytes_per_sweep(nnz, n, 1)
+        gbs = ab * st.sweeps / (st.solve_ms * 1e-3) / 1e9
+        out = {"workload": "random sparse SPD, n = %d, ~27 entries per row, unsorted triplets (BASELINE configs[4])" % n,
+               "n": n, "nnz": nnz, "nnz_per_row": nnz / n, "n_colors": int(info["n_colors"]), "kernel": int(st.kernel_used),
+               "sweeps": int(st.sweeps), "ms": float(st.solve_ms), "Gnnz_per_s": nnz * st.sweeps / (st.solve_ms * 1e-3) / 1e9,
+               "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+               "note": "x gathers hit random 32-byte sectors: DRAM traffic exceeds the algorithmic bytes (profiles/)",
+               "max_abs_vs_xstar_after_%d_sweeps" % sweeps: float(np.abs(x - xstar).max()),
+               "residual_l2": float(sp.residual(b, x)), "residual_l2_x0": float(sp.residual(b, np.ones(n))),
+               "host_generation_s": t_gen, "assembly_s_triplets_to_slack_csr": t_asm, "analysis_s_colouring_and_permute": t_ana}
+    else:
+        raise SystemExit("unknown config " + str(which))
+    print(json.dumps(out))
+
+
+def other_config_child(args, which, timeout):
+    cmd = [sys.executable, os.path.abspath(__file__), "--other-config-only", which, "--c5-n", str(args.c5_n)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
+    except Exception as e:
+        return {"error": repr(e)[:400]}
+
+
 def time_to_tol_child(args):
     """Run the leg in a child process; returns its dict or {"error": ...}."""
     cmd = [sys.executable, os.path.abspath(__file__), "--time-to-tol-only", "--size", str(args.size), "--channels",
@@ -498,6 +616,8 @@ def main():
     args = parse()
     if args.time_to_tol_only:
         return run_time_to_tol(args)
+    if args.other_config_only:
+        return run_other_config(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -88,6 +88,7 @@ SIGNATURES = {
     "gsb_axpy": [_vp, _vp, _d, _i64, _vp],
     "gsb_vecmul": [_vp, _vp, _i64, _vp],
     "gsb_conjugate_gradient": [_vp, _vp, _d, _i, _vp, _vp, _ip],
+    "gsb_conjugate_gradient_multi": [_vp, _vp, _i, _d, _i, _vp, _vp, _vp],
     "gsb_conjugate_gradient_jacobi": [_vp, _vp, _d, _i, _vp, _ip],
     "gsb_poisson_matrix": [_vp, _i, _i],
     "gsb_poisson_rhs": [_i, _i, _i, _vp, _vp, _vp, _vp],

@@ -18,6 +18,8 @@ gsb_matrix::~gsb_matrix() {
     plan = nullptr;
     if (ctl_host) cudaFreeHost(ctl_host);
     ctl_host = nullptr;
+    if (cg_state_host) cudaFreeHost(cg_state_host);
+    cg_state_host = nullptr;
 }
 
 extern "C" int gsb_matrix_create(gsb_matrix **out, int vtype) {

@@ -1,30 +1,285 @@
-// gsb_cg.cu -- "next" row N1: the conjugate-gradient solvers the reference's Poisson drivers
-// actually call (hw8_pa.cc:972, PhotoMontage.cpp:613), on the device.
+// gsb_cg.cu -- row N1: the conjugate-gradient solvers the reference's Poisson drivers actually call
+// (hw8_pa.cc:972, PhotoMontage.cpp:613), as a DEVICE loop.
 //   conjugateGradient(b, eps, max_iter, initialize)   v2 :396-434
 //   conjugateGradientEigen(b, eps, max_iter)          v2 :472-535  (Jacobi-preconditioned)
-// Same recurrences, same unfused a + s*b vector updates, same SpMV (storage order).  Dot products
-// are tree reductions (the reference's transform_reduce leaves the order unspecified), so the
-// iterates agree with the reference to rounding, not bit for bit.
+// Same recurrences, same unfused a + s*b vector updates, same SpMV (storage order, bit-exact with applyToVector).
+//
+// One iteration = three launches and no host round trip:
+//   cg_spmv_dot   Ap = A p for up to 4 right-hand sides in ONE pass over the CSR (the colour channels share the
+//                 matrix, PhotoMontage.cpp:428-433), fused with the partial sums of p.Ap; the last CTA to retire folds
+//                 the partials in a fixed order and leaves alpha = (r.r) / (p.Ap) in device memory
+//   cg_update_xr  x += alpha p, r -= alpha Ap (and z = M^-1 r for the Jacobi variant), fused with the partial sums of
+//                 r.r (and z.r); the last CTA folds, takes the stop decision sqrt(r.r) < eps (v2 :425 / :524: the
+//                 loop breaks BEFORE p is updated and before the counter is bumped) and leaves beta
+//   cg_update_p   p = z + beta p
+// alpha, beta, the norms, the per-RHS iteration counters and `done` flags live in a CgState block on the device; a
+// right-hand side that has stopped is frozen while the others go on.  The host enqueues a batch of iterations and
+// reads the block once per batch (kernels launched after the last RHS stopped return at their first instruction).
+// Dot products are fixed-order tree reductions (the reference's transform_reduce leaves the order unspecified), so
+// iterates agree with the reference to rounding, not bit for bit; run to run they are identical.
+// Workspaces stay with the matrix handle: repeated solves (three channels, every frame) allocate nothing.
 #include "gsb_internal.cuh"
 
 #include <math.h>
 
-__global__ void __launch_bounds__(256) cg_axpy(const double *a, const double *b, double s,
-                                               int64_t n, double *out) {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
-        out[i] = __dadd_rn(a[i], __dmul_rn(s, b[i]));
+#define CG_THREADS 256
+#define CG_SPAN_CAP 2048 // CSR entries of a 256-row tile staged in shared memory (24 KB): rows up to 8 entries on average
+
+struct CgState {
+    double rho[GSB_MAX_RHS];   // r.r (CG) / z.r (Jacobi) of the current residual: numerator of alpha, denominator of beta
+    double alpha[GSB_MAX_RHS], beta[GSB_MAX_RHS];
+    double err[GSB_MAX_RHS];   // r.r after the last update
+    int done[GSB_MAX_RHS];     // 1 = stopped (converged, or max_iteration reached)
+    int cnt[GSB_MAX_RHS];      // the reference's `cnt` at exit
+    int all_done;
+    int max_iter;
+    double epsilon;
+    unsigned ticket[2];        // "last CTA folds" counters of the two reducing kernels
+};
+
+// fixed-order fold of `np` per-CTA partials (NV values each) by the calling CTA -> sum[0..NV) in shared memory
+template <int NV>
+__device__ __forceinline__ void cg_fold(const double *partials, int np, double (&sum)[NV], double (*ws)[CG_THREADS / 32]) {
+    double s[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = 0.0;
+    for (int i = threadIdx.x; i < np; i += CG_THREADS) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[v] += __ldcg(partials + (size_t)i * NV + v);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double t = s[v];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+        if (lane == 0) ws[v][wid] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double t = 0.0;
+        for (int w = 0; w < CG_THREADS / 32; ++w) t += ws[v][w];
+        sum[v] = t;
+    }
 }
 
-__global__ void __launch_bounds__(256) cg_sub(const double *a, const double *b, int64_t n,
-                                              double *out) {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
-        out[i] = __dsub_rn(a[i], b[i]);
+// per-CTA partial (NV values per thread) -> partials[blockIdx.x]; returns true in the last CTA to retire
+template <int NV>
+__device__ __forceinline__ bool cg_block_partial(double (&v)[NV], double *partials, unsigned *ticket,
+                                                 double (*ws)[CG_THREADS / 32]) {
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double t = v[q];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+        if (lane == 0) ws[q][wid] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (int w = 0; w < CG_THREADS / 32; ++w) t += ws[threadIdx.x][w];
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) *ticket = 0;
+    return s_last != 0;
 }
 
-__global__ void __launch_bounds__(256) cg_mul(const double *a, const double *b, int64_t n,
-                                              double *out) {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
-        out[i] = __dmul_rn(a[i], b[i]);
+// out_r = A * in_r (storage order, product and sum rounded separately: bit-exact with applyToVector, v2 :382-393) for
+// NRHS vectors in one pass over the CSR.  A tile of 256 rows is one contiguous span of the slack CSR; it is staged
+// through shared memory with coalesced loads when it fits, else read row per thread.  DOT: also sum in_r . out_r.
+template <int NRHS, bool DOT>
+__global__ void __launch_bounds__(CG_THREADS) cg_spmv_dot(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                          const int *__restrict__ row_begin,
+                                                          const int *__restrict__ row_nnz, int n_rows, int64_t store,
+                                                          const double *__restrict__ in, double *__restrict__ out,
+                                                          int64_t ld, CgState *st, double *__restrict__ partials) {
+    __shared__ double v_s[CG_SPAN_CAP];
+    __shared__ int c_s[CG_SPAN_CAP];
+    __shared__ double ws[NRHS][CG_THREADS / 32];
+    if (DOT && *(volatile int *)&st->all_done) return;
+    bool live[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) live[r] = !DOT || !st->done[r];
+    double dot[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) dot[r] = 0.0;
+    const int ntiles = (n_rows + CG_THREADS - 1) / CG_THREADS;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int r0 = t * CG_THREADS, r1 = min(r0 + CG_THREADS, n_rows);
+        const int64_t k0 = row_begin[r0], k1 = r1 < n_rows ? (int64_t)row_begin[r1] : store;
+        const bool staged = k1 - k0 <= CG_SPAN_CAP;
+        __syncthreads(); // the previous tile's rows are done with the stage
+        if (staged) {
+            for (int k = threadIdx.x; k < (int)(k1 - k0); k += CG_THREADS) {
+                v_s[k] = vals[k0 + k];
+                c_s[k] = cols[k0 + k];
+            }
+        }
+        __syncthreads();
+        const int i = r0 + threadIdx.x;
+        if (i < r1) {
+            const int64_t kb = row_begin[i];
+            const int len = row_nnz[i];
+            double s[NRHS];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+            for (int j = 0; j < len; ++j) {
+                const double v = staged ? v_s[kb - k0 + j] : vals[kb + j];
+                const int c = staged ? c_s[kb - k0 + j] : cols[kb + j];
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r)
+                    if (live[r]) s[r] = __dadd_rn(s[r], __dmul_rn(v, in[r * ld + c]));
+            }
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+                if (live[r]) {
+                    out[r * ld + i] = s[r];
+                    if (DOT) dot[r] += in[r * ld + i] * s[r];
+                }
+        }
+    }
+    if (DOT) {
+        if (cg_block_partial<NRHS>(dot, partials, &st->ticket[0], ws)) {
+            double sum[NRHS];
+            cg_fold<NRHS>(partials, gridDim.x, sum, ws);
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r)
+                    if (!st->done[r]) st->alpha[r] = st->rho[r] / sum[r]; // v2 :420-421 / :517-518
+            }
+        }
+    }
+}
+
+// start-up: r = b - A x0 (Ax0 in `ax`, or absent: r = b), z = M^-1 r (inv != null), p = z, rho = z.r
+template <int NRHS>
+__global__ void __launch_bounds__(CG_THREADS) cg_start(const double *__restrict__ b, const double *__restrict__ ax,
+                                                       const double *__restrict__ inv, int64_t n, int64_t ld,
+                                                       double *__restrict__ r, double *__restrict__ p, CgState *st,
+                                                       double *__restrict__ partials) {
+    __shared__ double ws[NRHS][CG_THREADS / 32];
+    double dot[NRHS];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) dot[q] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * CG_THREADS) {
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) {
+            const double rv = ax ? __dsub_rn(b[q * ld + i], ax[q * ld + i]) : b[q * ld + i]; // v2 :405-407
+            const double zv = inv ? __dmul_rn(rv, inv[i]) : rv;                            // v2 :505
+            r[q * ld + i] = rv;
+            p[q * ld + i] = zv;
+            dot[q] += zv * rv;
+        }
+    }
+    if (cg_block_partial<NRHS>(dot, partials, &st->ticket[1], ws)) {
+        double sum[NRHS];
+        cg_fold<NRHS>(partials, gridDim.x, sum, ws);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) st->rho[q] = sum[q];
+        }
+    }
+}
+
+// x += alpha p; r -= alpha Ap; (z = M^-1 r;) err = r.r, rho' = z.r; stop decision and beta by the last CTA
+template <int NRHS, bool JACOBI>
+__global__ void __launch_bounds__(CG_THREADS) cg_update_xr(double *__restrict__ x, double *__restrict__ r,
+                                                           const double *__restrict__ p, const double *__restrict__ ap,
+                                                           const double *__restrict__ inv, double *__restrict__ z,
+                                                           int64_t n, int64_t ld, CgState *st,
+                                                           double *__restrict__ partials) {
+    constexpr int NV = JACOBI ? 2 * NRHS : NRHS;
+    __shared__ double ws[NV][CG_THREADS / 32];
+    if (*(volatile int *)&st->all_done) return;
+    double alpha[NRHS];
+    bool live[NRHS];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) {
+        live[q] = !st->done[q];
+        alpha[q] = st->alpha[q];
+    }
+    double dot[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) dot[q] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * CG_THREADS) {
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q)
+            if (live[q]) {
+                x[q * ld + i] = __dadd_rn(x[q * ld + i], __dmul_rn(alpha[q], p[q * ld + i]));          // v2 :422 / :519
+                const double rv = __dadd_rn(r[q * ld + i], __dmul_rn(-alpha[q], ap[q * ld + i]));     // v2 :423 / :520
+                r[q * ld + i] = rv;
+                dot[q] += rv * rv;
+                if (JACOBI) {
+                    const double zv = __dmul_rn(rv, inv[i]); // v2 :526
+                    z[q * ld + i] = zv;
+                    dot[NRHS + q] += zv * rv;
+                }
+            }
+    }
+    if (cg_block_partial<NV>(dot, partials, &st->ticket[1], ws)) {
+        double sum[NV];
+        cg_fold<NV>(partials, gridDim.x, sum, ws);
+        if (threadIdx.x == 0) {
+            int all = 1;
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) {
+                if (!st->done[q]) {
+                    st->err[q] = sum[q];
+                    if (sqrt(sum[q]) < st->epsilon) {
+                        st->done[q] = 1; // break: p is not updated, cnt is not bumped (v2 :425 / :524)
+                    } else {
+                        const double rho_new = JACOBI ? sum[NRHS + q] : sum[q];
+                        st->beta[q] = rho_new / st->rho[q]; // v2 :426 / :528
+                        st->rho[q] = rho_new;
+                        st->cnt[q] += 1;
+                        // (the p update below still runs for this right-hand side: the reference updates p, bumps
+                        // cnt and only then tests cnt < max_iteration)
+                    }
+                }
+                all = all && st->done[q];
+            }
+            st->all_done = all;
+        }
+    }
+}
+
+// p = z + beta p (z = r for plain CG); then the loop condition cnt < max_iteration
+template <int NRHS>
+__global__ void __launch_bounds__(CG_THREADS) cg_update_p(double *__restrict__ p, const double *__restrict__ z, int64_t n,
+                                                          int64_t ld, CgState *st) {
+    if (*(volatile int *)&st->all_done) return;
+    double beta[NRHS];
+    bool live[NRHS];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) {
+        live[q] = !st->done[q];
+        beta[q] = st->beta[q];
+    }
+    for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * CG_THREADS) {
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q)
+            if (live[q]) p[q * ld + i] = __dadd_rn(z[q * ld + i], __dmul_rn(beta[q], p[q * ld + i])); // v2 :427 / :530
+    }
+}
+// after cg_update_p of every iteration (one thread): a right-hand side whose counter reached max_iteration stops
+__global__ void cg_check_max(CgState *st) {
+    if (st->all_done) return;
+    int all = 1;
+    for (int q = 0; q < GSB_MAX_RHS; ++q) {
+        if (!st->done[q] && st->cnt[q] >= st->max_iter) st->done[q] = 1;
+        all = all && st->done[q];
+    }
+    st->all_done = all;
 }
 
 // extractDiagnolColInv (v2 :472-491): 1/a_ii where the diagonal is stored and nonzero, else 1
@@ -47,26 +302,8 @@ __global__ void __launch_bounds__(256) cg_inv_diag(const double *__restrict__ va
     inv[i] = r;
 }
 
-struct CgWork {
-    cudaStream_t st;
-    int64_t n;
-    int nb;
-    DevBuf<double> scal;
-    int dot(const double *a, const double *b, double *out) {
-        GSB_TRY(gsb_dot_dev(a, b, n, scal.p, st));
-        GSB_CUDA(cudaMemcpyAsync(out, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-        GSB_CUDA(cudaStreamSynchronize(st));
-        return GSB_OK;
-    }
-    int axpy(const double *a, const double *b, double s, double *out) {
-        cg_axpy<<<nb, 256, 0, st>>>(a, b, s, n, out);
-        GSB_KERNEL_CHECK();
-        return GSB_OK;
-    }
-};
-
-static int cg_common_check(gsb_matrix *m, const double *b, double *x) {
-    if (!m || !b || !x) return GSB_ERR_ARG;
+static int cg_common_check(gsb_matrix *m, const double *b, double *x, int nrhs) {
+    if (!m || !b || !x || nrhs < 1 || nrhs > GSB_MAX_RHS) return GSB_ERR_ARG;
     if (!m->has_layout) {
         gsb_set_error("conjugate_gradient: matrix holds no layout yet");
         return GSB_ERR_STATE;
@@ -78,119 +315,125 @@ static int cg_common_check(gsb_matrix *m, const double *b, double *x) {
     return gsb_set_device(m->device);
 }
 
-// device-pointer core of conjugateGradient (v2 :396-434): b_dev, x_dev natural order; x0_dev may be null (zero start)
-int gsb_cg_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_dev, double epsilon, int max_iteration,
-                        double *x_dev, int *iters) {
-    CgWork w;
-    w.st = gsb_cur_stream();
-    w.n = m->n_rows;
-    w.nb = gsb_blocks_for(w.n, 256 * 4, gsb_sm_count() * 16);
-    GSB_TRY(w.scal.alloc(1));
-    const int64_t n = w.n;
-    const size_t bytes = sizeof(double) * (size_t)n;
-    DevBuf<double> x, r, r1, p, Ap;
-    GSB_TRY(x.alloc(n));
-    GSB_TRY(r.alloc(n));
-    GSB_TRY(r1.alloc(n));
-    GSB_TRY(p.alloc(n));
-    GSB_TRY(Ap.alloc(n));
-    if (x0_dev)
-        GSB_CUDA(cudaMemcpyAsync(x.p, x0_dev, bytes, cudaMemcpyDeviceToDevice, w.st));
-    else
-        GSB_CUDA(cudaMemsetAsync(x.p, 0, bytes, w.st));
-    GSB_TRY(gsb_spmv_dev(m, x.p, r.p)); // r0 = b - A x   (:405-407)
-    cg_sub<<<w.nb, 256, 0, w.st>>>(b_dev, r.p, n, r.p);
-    GSB_KERNEL_CHECK();
-    GSB_CUDA(cudaMemcpyAsync(p.p, r.p, bytes, cudaMemcpyDeviceToDevice, w.st));
-    int cnt = 0;
-    while (cnt < max_iteration) {
-        double rlen, pAp, r1len;
-        GSB_TRY(w.dot(r.p, r.p, &rlen));
-        GSB_TRY(gsb_spmv_dev(m, p.p, Ap.p));
-        GSB_TRY(w.dot(p.p, Ap.p, &pAp));
-        double alpha = rlen / pAp;
-        GSB_TRY(w.axpy(x.p, p.p, alpha, x.p));
-        GSB_TRY(w.axpy(r.p, Ap.p, -alpha, r1.p));
-        GSB_TRY(w.dot(r1.p, r1.p, &r1len));
-        if (sqrt(r1len) < epsilon) break; // :425 (cnt is not incremented on the break)
-        double beta = r1len / rlen;
-        GSB_TRY(w.axpy(r1.p, p.p, beta, p.p));
-        r.swap(r1);
-        ++cnt;
+template <int NRHS>
+static int cg_run(gsb_matrix *m, const double *b_dev, const double *x0_dev, bool jacobi, double epsilon,
+                  int max_iteration, double *x_dev, int *iters) {
+    cudaStream_t st = gsb_cur_stream();
+    const int64_t n = m->n_rows;
+    const int64_t ld = n; // callers hand over nrhs vectors of n doubles, one after another
+    const int grid_v = gsb_blocks_for(n, CG_THREADS * 4, gsb_sm_count() * 8);
+    const int ntiles = (int)((n + CG_THREADS - 1) / CG_THREADS);
+    const int grid_s = ntiles < gsb_sm_count() * 8 ? ntiles : gsb_sm_count() * 8;
+    // workspace with the handle: r, p, Ap (, z, inv) + partials + state
+    const int nvec = jacobi ? 4 : 3;
+    GSB_TRY(m->cg_ws.alloc((int64_t)nvec * NRHS * n + (jacobi ? n : 0)));
+    GSB_TRY(m->cg_partials.alloc((int64_t)(grid_v > grid_s ? grid_v : grid_s) * 2 * NRHS + 64));
+    GSB_TRY(m->cg_state.alloc(sizeof(CgState)));
+    if (!m->cg_state_host) GSB_CUDA(cudaHostAlloc(&m->cg_state_host, sizeof(CgState), cudaHostAllocDefault));
+    double *r = m->cg_ws.p, *p = r + NRHS * n, *ap = p + NRHS * n, *z = jacobi ? ap + NRHS * n : r;
+    double *inv = jacobi ? z + NRHS * n : nullptr;
+    CgState *ds = (CgState *)m->cg_state.p, *hs = (CgState *)m->cg_state_host;
+    memset(hs, 0, sizeof(CgState));
+    hs->max_iter = max_iteration;
+    hs->epsilon = epsilon;
+    for (int q = NRHS; q < GSB_MAX_RHS; ++q) hs->done[q] = 1;
+    if (max_iteration <= 0) { // while (cnt < max_iteration) never runs: x = x0
+        for (int q = 0; q < NRHS; ++q) hs->done[q] = 1;
+        hs->all_done = 1;
     }
-    if (iters) *iters = cnt;
-    GSB_CUDA(cudaMemcpyAsync(x_dev, x.p, bytes, cudaMemcpyDeviceToDevice, w.st));
-    GSB_CUDA(cudaStreamSynchronize(w.st));
+    GSB_CUDA(cudaMemcpyAsync(ds, hs, sizeof(CgState), cudaMemcpyHostToDevice, st));
+    const size_t bytes = sizeof(double) * (size_t)(NRHS * n);
+    if (x0_dev) {
+        if (x0_dev != x_dev) GSB_CUDA(cudaMemcpyAsync(x_dev, x0_dev, bytes, cudaMemcpyDeviceToDevice, st));
+        cg_spmv_dot<NRHS, false><<<grid_s, CG_THREADS, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, m->n_rows,
+                                                               m->store, x_dev, ap, ld, ds, m->cg_partials.p);
+        GSB_KERNEL_CHECK();
+    } else {
+        GSB_CUDA(cudaMemsetAsync(x_dev, 0, bytes, st)); // v2 :398-403: zero start
+    }
+    if (jacobi) {
+        cg_inv_diag<<<(int)((n + 255) / 256), 256, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, m->n_rows,
+                                                           m->n_cols, inv);
+        GSB_KERNEL_CHECK();
+    }
+    cg_start<NRHS><<<grid_v, CG_THREADS, 0, st>>>(b_dev, x0_dev ? ap : nullptr, inv, n, ld, r, p, ds, m->cg_partials.p);
+    GSB_KERNEL_CHECK();
+    int issued = 0;
+    const int batch = 16;
+    while (!hs->all_done) {
+        for (int k = 0; k < batch; ++k) {
+            cg_spmv_dot<NRHS, true><<<grid_s, CG_THREADS, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p,
+                                                                  m->n_rows, m->store, p, ap, ld, ds, m->cg_partials.p);
+            if (jacobi)
+                cg_update_xr<NRHS, true><<<grid_v, CG_THREADS, 0, st>>>(x_dev, r, p, ap, inv, z, n, ld, ds, m->cg_partials.p);
+            else
+                cg_update_xr<NRHS, false><<<grid_v, CG_THREADS, 0, st>>>(x_dev, r, p, ap, nullptr, nullptr, n, ld, ds,
+                                                                        m->cg_partials.p);
+            cg_update_p<NRHS><<<grid_v, CG_THREADS, 0, st>>>(p, z, n, ld, ds);
+            cg_check_max<<<1, 1, 0, st>>>(ds);
+        }
+        GSB_KERNEL_CHECK();
+        issued += batch;
+        GSB_CUDA(cudaMemcpyAsync(hs, ds, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+        GSB_CUDA(cudaStreamSynchronize(st));
+        if (issued > max_iteration + batch) break; // cannot happen (cg_check_max stops at max_iteration)
+    }
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (iters)
+        for (int q = 0; q < NRHS; ++q) iters[q] = hs->cnt[q];
     return GSB_OK;
 }
 
-extern "C" int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
-                                      const double *x0, double *x_out, int *iters) {
-    GSB_TRY(cg_common_check(m, b, x_out));
+static int cg_dispatch(gsb_matrix *m, const double *b_dev, const double *x0_dev, int nrhs, bool jacobi, double epsilon,
+                       int max_iteration, double *x_dev, int *iters) {
+    switch (nrhs) {
+        case 1: return cg_run<1>(m, b_dev, x0_dev, jacobi, epsilon, max_iteration, x_dev, iters);
+        case 2: return cg_run<2>(m, b_dev, x0_dev, jacobi, epsilon, max_iteration, x_dev, iters);
+        case 3: return cg_run<3>(m, b_dev, x0_dev, jacobi, epsilon, max_iteration, x_dev, iters);
+        case 4: return cg_run<4>(m, b_dev, x0_dev, jacobi, epsilon, max_iteration, x_dev, iters);
+    }
+    return GSB_ERR_ARG;
+}
+
+// device-pointer core of conjugateGradient (v2 :396-434): b_dev, x_dev natural order; x0_dev may be null (zero start)
+int gsb_cg_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_dev, double epsilon, int max_iteration,
+                        double *x_dev, int *iters) {
+    return cg_dispatch(m, b_dev, x0_dev, 1, false, epsilon, max_iteration, x_dev, iters);
+}
+int gsb_cg_solve_device_multi(gsb_matrix *m, const double *b_dev, const double *x0_dev, int nrhs, double epsilon,
+                              int max_iteration, double *x_dev, int *iters) {
+    return cg_dispatch(m, b_dev, x0_dev, nrhs, false, epsilon, max_iteration, x_dev, iters);
+}
+
+static int cg_host(gsb_matrix *m, const double *b, int nrhs, bool jacobi, double epsilon, int max_iteration,
+                   const double *x0, double *x_out, int *iters) {
+    GSB_TRY(cg_common_check(m, b, x_out, nrhs));
     cudaStream_t st = gsb_cur_stream();
     const int64_t n = m->n_rows;
-    const size_t bytes = sizeof(double) * (size_t)n;
-    DevBuf<double> db, dx;
-    GSB_TRY(db.alloc(n));
-    GSB_TRY(dx.alloc(n));
+    const size_t bytes = sizeof(double) * (size_t)(n * nrhs);
+    DevBuf<double> &db = m->stage_b, &dx = m->stage_x; // device staging of the caller's host vectors, kept with the handle
+    GSB_TRY(db.alloc(n * nrhs));
+    GSB_TRY(dx.alloc(n * nrhs));
     GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
     if (x0) GSB_CUDA(cudaMemcpyAsync(dx.p, x0, bytes, cudaMemcpyHostToDevice, st));
-    GSB_TRY(gsb_cg_solve_device(m, db.p, x0 ? dx.p : nullptr, epsilon, max_iteration, dx.p, iters));
+    GSB_TRY(cg_dispatch(m, db.p, x0 ? dx.p : nullptr, nrhs, jacobi, epsilon, max_iteration, dx.p, iters));
     GSB_CUDA(cudaMemcpyAsync(x_out, dx.p, bytes, cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
     return GSB_OK;
 }
 
+extern "C" int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
+                                      const double *x0, double *x_out, int *iters) {
+    return cg_host(m, b, 1, false, epsilon, max_iteration, x0, x_out, iters);
+}
+
+// EXTENSION: up to 4 right-hand sides (the colour channels) in one call; every SpMV reads the CSR once for all of them
+extern "C" int gsb_conjugate_gradient_multi(gsb_matrix *m, const double *b, int nrhs, double epsilon, int max_iteration,
+                                            const double *x0, double *x_out, int *iters) {
+    return cg_host(m, b, nrhs, false, epsilon, max_iteration, x0, x_out, iters);
+}
+
 extern "C" int gsb_conjugate_gradient_jacobi(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
                                              double *x_out, int *iters) {
-    GSB_TRY(cg_common_check(m, b, x_out));
-    CgWork w;
-    w.st = gsb_cur_stream();
-    w.n = m->n_rows;
-    w.nb = gsb_blocks_for(w.n, 256 * 4, gsb_sm_count() * 16);
-    GSB_TRY(w.scal.alloc(1));
-    const int64_t n = w.n;
-    const size_t bytes = sizeof(double) * (size_t)n;
-    DevBuf<double> db, x, r, z, p, Ap, inv;
-    GSB_TRY(db.alloc(n));
-    GSB_TRY(x.alloc(n));
-    GSB_TRY(r.alloc(n));
-    GSB_TRY(z.alloc(n));
-    GSB_TRY(p.alloc(n));
-    GSB_TRY(Ap.alloc(n));
-    GSB_TRY(inv.alloc(n));
-    GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, w.st));
-    GSB_CUDA(cudaMemsetAsync(x.p, 0, bytes, w.st));
-    cg_inv_diag<<<(int)((n + 255) / 256), 256, 0, w.st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p,
-                                                         m->n_rows, m->n_cols, inv.p);
-    GSB_KERNEL_CHECK();
-    GSB_TRY(gsb_spmv_dev(m, x.p, r.p));
-    cg_sub<<<w.nb, 256, 0, w.st>>>(db.p, r.p, n, r.p);
-    GSB_KERNEL_CHECK();
-    cg_mul<<<w.nb, 256, 0, w.st>>>(r.p, inv.p, n, p.p); // p0 = M^-1 r0   (:505)
-    GSB_KERNEL_CHECK();
-    double olddist;
-    GSB_TRY(w.dot(p.p, r.p, &olddist));
-    int cnt = 0;
-    while (cnt < max_iteration) {
-        double pAp, err, newdist;
-        GSB_TRY(gsb_spmv_dev(m, p.p, Ap.p));
-        GSB_TRY(w.dot(p.p, Ap.p, &pAp));
-        double alpha = olddist / pAp;
-        GSB_TRY(w.axpy(x.p, p.p, alpha, x.p));
-        GSB_TRY(w.axpy(r.p, Ap.p, -alpha, r.p));
-        GSB_TRY(w.dot(r.p, r.p, &err));
-        if (sqrt(err) < epsilon) break; // :524
-        cg_mul<<<w.nb, 256, 0, w.st>>>(r.p, inv.p, n, z.p);
-        GSB_KERNEL_CHECK();
-        GSB_TRY(w.dot(z.p, r.p, &newdist));
-        double beta = newdist / olddist;
-        olddist = newdist;
-        GSB_TRY(w.axpy(z.p, p.p, beta, p.p));
-        ++cnt;
-    }
-    if (iters) *iters = cnt;
-    GSB_CUDA(cudaMemcpyAsync(x_out, x.p, bytes, cudaMemcpyDeviceToHost, w.st));
-    GSB_CUDA(cudaStreamSynchronize(w.st));
-    return GSB_OK;
+    return cg_host(m, b, 1, true, epsilon, max_iteration, nullptr, x_out, iters);
 }

@@ -229,10 +229,8 @@ static int gdf_core(int W, int H, const float *gx_dev, const float *gy_dev, cons
         GSB_CUDA(cudaEventCreate(&e0));
         GSB_CUDA(cudaEventCreate(&e1));
         GSB_CUDA(cudaEventRecord(e0, st));
-        int status = GSB_OK;
-        for (int c = 0; c < 3 && status == GSB_OK; ++c)
-            status = gsb_cg_solve_device(m, b.p + c * n, init_dev ? init_dev + c * n : nullptr, opts.epsilon,
-                                         opts.max_iteration, x.p + c * n, &s.iterations[c]);
+        // the three channels share every pass over the matrix (one SpMV for all of them); each stops on its own
+        int status = gsb_cg_solve_device_multi(m, b.p, init_dev, 3, opts.epsilon, opts.max_iteration, x.p, s.iterations);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;

@@ -158,6 +158,10 @@ struct gsb_matrix {
     void *graph_exec = nullptr;
     int graph_key[6] = {0, 0, 0, 0, 0, 0};
     struct GsbPlan *plan = nullptr; // colour-phase launch plan (gsb_phase.cu)
+    // conjugate-gradient workspaces (gsb_cg.cu): vectors, per-CTA partials, the device-resident scalar block
+    DevBuf<double> cg_ws, cg_partials;
+    DevBuf<unsigned char> cg_state;
+    void *cg_state_host = nullptr;
     // multi-device solve through the host entry points (gsb_set_devices): the group and whether it holds this matrix
     struct gsb_dist_group *group = nullptr;
     bool group_built = false;
@@ -313,6 +317,8 @@ int gsb_gs_solve_device_x0(gsb_matrix *m, const double *b_dev, const double *x0_
                            int max_iteration, const gsb_gs_options *opts, double *x_dev, gsb_gs_stats *stats);
 int gsb_cg_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_dev, double epsilon, int max_iteration,
                         double *x_dev, int *iters);
+int gsb_cg_solve_device_multi(gsb_matrix *m, const double *b_dev, const double *x0_dev, int nrhs, double epsilon,
+                              int max_iteration, double *x_dev, int *iters);
 
 // gsb_poisson.cu: rows [p0,p1) of the reference's Poisson matrix (global columns)
 int gsb_poisson_launch_row_len(int W, int H, int64_t p0, int64_t p1, int *len, cudaStream_t st);

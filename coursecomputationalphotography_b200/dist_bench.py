@@ -110,6 +110,14 @@ def run(args, pkg, wl, dist, rank, world, local):
 
     parity = parity_vs_one_gpu(args, pkg, wl, dist, torch, solver, b_dev, rank, world, dev, W, H, ch, n_local, opts)
 
+    c4 = None
+    if not getattr(args, "no_c4", False):
+        try:
+            c4 = config4_strips(args, pkg, wl, dist, torch, solver, rank, world, dev)
+        except Exception as e:  # nothing in this leg may cost the main line
+            c4 = {"error": repr(e)[:300]}
+    solver.poisson_strip(W, H, y0, y1)  # (the handle is finalised below; leave it on the headline system)
+
     if rank == 0:
         assert sweeps_done == args.sweeps * args.steps
         value = nnz * ch * sweeps_done / (total_ms * 1e-3) / 1e9
@@ -138,12 +146,85 @@ def run(args, pkg, wl, dist, rank, world, local):
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(sm[2]), "clocks": clocks,
         }
         line.update(parity)
+        if c4 is not None:
+            line["config4_16384_strips"] = c4
         print(json.dumps(line), flush=True)
     solver.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and parity.get("parity_bitwise_vs_1gpu") is False:
         raise SystemExit("dist_bench: the %d-strip solution differs from the 1-GPU solution" % world)
+    if rank == 0 and c4 and c4.get("parity_bitwise_vs_1gpu") is False:
+        raise SystemExit("dist_bench: the %d-strip 16384^2 solution differs from the 1-GPU solution" % world)
+
+
+def _c4_rhs(torch, dev, r0, r1):
+    """A deterministic right-hand side as a function of the GLOBAL row index, generated on the device (a 16384^2
+    image never exists on one host): values in [-0.5, 0.5)."""
+    idx = torch.arange(r0, r1, device=dev, dtype=torch.int64)
+    return (((idx * 2654435761) % 1000003).to(torch.float64) / 1000003.0 - 0.5).reshape(1, -1).contiguous()
+
+
+def config4_strips(args, pkg, wl, dist, torch, solver, rank, world, dev):
+    """BASELINE configs[3]: 16384 x 16384 full-grid Poisson system (n = 268 M, nnz = 1.342 G), one channel, row strips
+    generated on the devices, 200 sweeps with the reference's stop-rule cadence; then 10 sweeps from x0 = 1 gathered
+    on rank 0 and compared BIT FOR BIT with the single-GPU solver on the same system (it fits one B200)."""
+    import hashlib
+    from bench import algorithmic_bytes_per_sweep, peaks
+    W = H = int(getattr(args, "c4_size", 16384))
+    sweeps = 200
+    y0, y1 = wl.strip_bounds(H, world)[rank]
+    n_local = W * (y1 - y0)
+    solver.poisson_strip(W, H, y0, y1)
+    b_dev = _c4_rhs(torch, dev, y0 * W, y1 * W)
+    x_dev = torch.empty_like(b_dev)
+    opts = pkg.SparseMatrix.options(check_every=args.check_every)
+    solver.gauss_seidel_dev(b_dev.data_ptr(), x_dev.data_ptr(), 1, 0.0, 20, opts)  # warm-up: plan, peer mappings
+    dist.barrier()
+    torch.cuda.synchronize()
+    st = solver.gauss_seidel_dev(b_dev.data_ptr(), x_dev.data_ptr(), 1, 0.0, sweeps, opts)
+    ms = torch.tensor([float(st.solve_ms)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # parity: PARITY_SWEEPS sweeps, strips vs one GPU
+    stp = solver.gauss_seidel_dev(b_dev.data_ptr(), x_dev.data_ptr(), 1, 0.0, PARITY_SWEEPS, opts)
+    bounds = [b1 - a1 for a1, b1 in wl.strip_bounds(H, world)]
+    nmax = max(bounds) * W
+    pad = torch.zeros(1, nmax, device=dev, dtype=torch.float64)
+    pad[:, :n_local] = x_dev
+    got = [torch.empty(1, nmax, device=dev, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, got, dst=0)
+    del pad
+    if rank != 0:
+        return None
+    x_full = torch.cat([got[r][:, :bounds[r] * W] for r in range(world)], dim=1).contiguous()
+    del got
+    nnz = wl.poisson_nnz(W, H)
+    n = W * H
+    peak, _ = peaks()
+    ab = algorithmic_bytes_per_sweep(nnz, n, 1) / world
+    per_sweep_ms = float(ms[0]) / sweeps
+    out = {"workload": "poisson_%dx%d_x1ch_full_grid, %d row strips generated on the devices (BASELINE configs[3])" % (W, H, world),
+           "n": n, "nnz": int(nnz), "sweeps": sweeps, "ms": float(ms[0]), "ms_per_sweep": per_sweep_ms,
+           "Gnnz_per_s": nnz * sweeps / (float(ms[0]) * 1e-3) / 1e9, "kernel": int(st.kernel_used),
+           "per_gpu_algorithmic_GBps": ab / (per_sweep_ms * 1e-3) / 1e9,
+           "per_gpu_frac_of_hbm_peak": ab / (per_sweep_ms * 1e-3) / 1e9 / peak}
+    try:
+        sp = pkg.SparseMatrix(np.float64)
+        sp.poisson(W, H)
+        b_full = _c4_rhs(torch, dev, 0, n)
+        x_one = torch.empty_like(b_full)
+        st1 = sp.gaussSeidel_dev(b_full.data_ptr(), x_one.data_ptr(), 1, 0.0, PARITY_SWEEPS,
+                                 pkg.SparseMatrix.options(check_every=args.check_every))
+        torch.cuda.synchronize()
+        out["parity_bitwise_vs_1gpu"] = bool(torch.equal(x_full, x_one))
+        out["parity"] = {"what": "%d sweeps from x0 = 1, %d strips vs one GPU" % (PARITY_SWEEPS, world),
+                         "max_abs_diff": float((x_full - x_one).abs().max()), "kernel_1gpu": int(st1.kernel_used),
+                         "x_sha256": hashlib.sha256(x_full.cpu().numpy().tobytes()).hexdigest()}
+        del sp, b_full, x_one
+    except Exception as e:
+        out["parity_error"] = repr(e)[:300]
+    torch.cuda.empty_cache()
+    return out
 
 
 PARITY_SWEEPS = 10

@@ -364,6 +364,24 @@ class SparseMatrix:
         self.last_iters = it.value
         return x
 
+    def conjugateGradientMulti(self, b, epsilon=1e-16, max_iteration=1000, initialize=None):
+        """EXTENSION: b (nrhs, n), nrhs <= 4: the right-hand sides share every pass over the matrix; each stops on its
+        own.  self.last_iters = list of the nrhs loop counts."""
+        self._push()
+        b = np.ascontiguousarray(b, np.float64)
+        nrhs = 1 if b.ndim == 1 else b.shape[0]
+        x = np.empty_like(b)
+        it = (C.c_int * 4)()
+        x0 = None
+        if initialize is not None and len(initialize):
+            x0 = np.ascontiguousarray(initialize, np.float64)
+            if x0.shape != b.shape:
+                raise ValueError("initialize must have the shape of b")
+        check(self.L.gsb_conjugate_gradient_multi(self._h, ptr(b), nrhs, float(epsilon), int(max_iteration), ptr(x0),
+                                                  ptr(x), it), "gsb_conjugate_gradient_multi")
+        self.last_iters = [it[i] for i in range(nrhs)]
+        return x
+
     def conjugateGradientEigen(self, b, epsilon=1e-16, max_iteration=180):
         """v2 :494-535 (Jacobi-preconditioned CG)"""
         self._push()

@@ -222,6 +222,27 @@ def random_spd_system(n=1_000_000, pairs_per_row=13, seed=5):
     return ro, ci, va, b, xstar
 
 
+def random_spd_coo(n=10_000_000, pairs_per_row=13, seed=5):
+    """C5 at full size, cheap to generate: UNSORTED COO triplets (the input of initializeFromTriplets, whose device
+    radix sort does the ordering).  Each row draws `pairs_per_row` random partners; pairs are stored once per
+    direction with the same value U(-1, 0) (orientation canonicalised, so that the last-duplicate-wins rule of the
+    triplet build keeps the matrix symmetric); diagonal = (entries in the row) + 1 >= sum|off| + 1 (strictly
+    dominant => SPD).  ~2 * pairs_per_row + 1 stored entries per row.  Returns rows, cols, vals (int32, int32, f64)."""
+    rng = np.random.default_rng(seed)
+    i = np.repeat(np.arange(n, dtype=np.int32), pairs_per_row)
+    j = rng.integers(0, n, i.size, dtype=np.int32)
+    keep = i != j
+    i, j = i[keep], j[keep]
+    lo, hi = np.minimum(i, j), np.maximum(i, j)
+    v = rng.uniform(-1.0, 0.0, lo.size)
+    cnt = np.bincount(lo, minlength=n) + np.bincount(hi, minlength=n)
+    d = np.arange(n, dtype=np.int32)
+    rows = np.concatenate([lo, hi, d])
+    cols = np.concatenate([hi, lo, d])
+    vals = np.concatenate([v, v, cnt.astype(np.float64) + 1.0])
+    return rows, cols, vals
+
+
 # ---- numpy restatement of the reference Poisson stencil (host-side reference for generators) ----------
 def poisson_nnz(W, H):
     return (W * H - 1) + 4 * (W - 1) * (H - 1)

@@ -186,6 +186,10 @@ int gsb_vecmul(const double *a, const double *b, int64_t n, double *out);       
  * x0 may be NULL (zero start).  iters = loop count at exit. */
 int gsb_conjugate_gradient(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
                            const double *x0, double *x_out, int *iters);
+/* EXTENSION: nrhs in 1..4 right-hand sides (colour channels) in one call -- every SpMV reads the matrix once for
+ * all of them; each right-hand side stops on its own (iters: nrhs counters).  b, x0, x_out: nrhs * n doubles. */
+int gsb_conjugate_gradient_multi(gsb_matrix *m, const double *b, int nrhs, double epsilon, int max_iteration,
+                                 const double *x0, double *x_out, int *iters);
 int gsb_conjugate_gradient_jacobi(gsb_matrix *m, const double *b, double epsilon, int max_iteration,
                                   double *x_out, int *iters);
 

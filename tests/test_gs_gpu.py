@@ -249,6 +249,46 @@ def test_cg_and_pcg_vs_oracle(gsb, oracle_mod):
     assert np.abs(xj[:-1] - xjo[:-1]).max() < 1e-5 * 255
 
 
+def test_cg_device_loop_multi_rhs_and_stop_semantics(gsb, oracle_mod):
+    """conjugateGradient as a device loop: (a) three right-hand sides in one call == three single calls, bit for bit,
+    each with its own loop count; (b) the reference's stop semantics (v2 :417-431): max_iteration caps the count, a
+    break on sqrt(r.r) < eps leaves the count un-bumped, max_iteration = 0 returns the initial guess; (c) vs the
+    oracle (itself bit-pinned to the reference's CG) with an initial guess, to rounding."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    W, H = 96, 80
+    img, b = _poisson_rhs_for(gsb, wl, W, H, C=3)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    init = img.reshape(3, -1).astype(np.float64)
+    xm = sp.conjugateGradientMulti(b, 1e-8, 400, init)
+    its = list(sp.last_iters)
+    assert len(its) == 3 and all(0 < k < 400 for k in its)
+    for c in range(3):
+        x1 = sp.conjugateGradient(b[c], 1e-8, 400, init[c])
+        assert sp.last_iters == its[c] and np.array_equal(x1, xm[c]), c
+    ro, ci, va = oracle_mod.poisson_csr(W, H)
+    o = oracle_from_csr(oracle_mod, ro, ci, va)
+    for c in range(3):
+        xo, it = o.cg(b[c], 1e-8, 400, init[c])
+        assert abs(it - its[c]) <= 2 and np.abs(xo - xm[c]).max() < 1e-6 * 255
+    # caps and the zero-iteration case
+    x5 = sp.conjugateGradient(b[0], 1e-30, 5, init[0])
+    assert sp.last_iters == 5
+    xo5, it5 = o.cg(b[0], 1e-30, 5, init[0])
+    assert it5 == 5 and np.abs(x5 - xo5).max() < 1e-9 * 255
+    x0 = sp.conjugateGradient(b[0], 1e-8, 0, init[0])
+    assert sp.last_iters == 0 and np.array_equal(x0, init[0])
+    # mixed stopping: one channel starts at its solution (stops at once, count 0), the others go on
+    start = init.copy()
+    start[1] = xm[1]
+    xs = sp.conjugateGradientMulti(b, 1e-6, 400, start)
+    assert sp.last_iters[1] <= 1 and sp.last_iters[0] > 3 and np.abs(xs - xm).max() < 1e-4
+    # Jacobi variant unchanged in meaning
+    xj = sp.conjugateGradientEigen(b[0], 1e-10, 600)
+    xjo, _ = o.pcg(b[0], 1e-10, 600)
+    assert np.abs(xj[:-1] - xjo[:-1]).max() < 1e-5 * 255
+
+
 def test_full_size_properties_4096(gsb):
     """BASELINE configs[2] size: 4096^2 x 3 channels.  Size-independent properties instead of an oracle run."""
     import ctypes as C
