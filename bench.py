@@ -338,7 +338,7 @@ def run_ours(args):
         x_pin = pinned_like(pkg, np.zeros_like(b_host))
         spe = pkg.SparseMatrix(np.float64)
         t_e2e, t_imp, t_setup, steps_e2e = 0.0, 0.0, 0.0, max(1, args.e2e_steps)
-        per_step = []
+        per_step, per_step_parts = [], []
         st_e = pkg.GsStats()
         for it in range(steps_e2e + 1):
             torch.cuda.synchronize()
@@ -354,11 +354,13 @@ def run_ours(args):
                 t_imp += t1 - t0
                 t_setup += st_e.setup_ms
                 per_step.append((t2 - t0) * 1e3)
+                per_step_parts.append([round((t1 - t0) * 1e3, 2), round(float(st_e.setup_ms), 2), round(float(st_e.solve_ms), 2)])
         h2d = va.nbytes + ci.nbytes + ro_in.nbytes + b_pin.nbytes
         d2h = x_pin.nbytes
         e2e = {"value": nnz * ch * args.sweeps * steps_e2e / t_e2e / 1e9, "unit": "Gnnz/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / steps_e2e * 1e3,
                "steps": steps_e2e, "ms_per_step_min": min(per_step), "ms_per_step_median": float(np.median(per_step)),
+               "per_step_ms": [round(v, 2) for v in per_step], "per_step_import_analysis_sweeps_ms": per_step_parts,
                "includes": "CSR import (H2D) + ordering analysis + b H2D + sweeps + x D2H",
                "import_ms": t_imp / steps_e2e * 1e3, "analysis_ms": t_setup / steps_e2e,
                "host_memory": "pinned (gsb_host_alloc)"}

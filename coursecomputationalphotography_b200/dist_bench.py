@@ -116,7 +116,6 @@ def run(args, pkg, wl, dist, rank, world, local):
             c4 = config4_strips(args, pkg, wl, dist, torch, solver, rank, world, dev)
         except Exception as e:  # nothing in this leg may cost the main line
             c4 = {"error": repr(e)[:300]}
-    solver.poisson_strip(W, H, y0, y1)  # (the handle is finalised below; leave it on the headline system)
 
     if rank == 0:
         assert sweeps_done == args.sweeps * args.steps

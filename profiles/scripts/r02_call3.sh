@@ -20,4 +20,9 @@ cat $O/summary.txt
 N="python bench.py --steps 1 --warmup 3 --sweeps 4 --no-cpu-baseline --no-e2e --no-time-to-tol --kernel 5"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_k5.csv $N > $O/ncu_list.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gs_sweep_fused -s 14 -c 1 -o $O/fused_rhs3 -f $N > $O/ncu_full3.log 2>&1
+# the whole GPU suite (new this call: CG device loop, masked Gradients, 4096^2 golden test) and the driver's default line
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_full.log 2>&1; echo "pytest rc=$?" >> $O/pytest_full.log
+tail -6 $O/pytest_full.log
+timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "default rc=$?"
+timeout 300 python bench.py --impl reference --steps 3 --warmup 3 > $O/bench_reference.json 2>&1
 ls -la $O

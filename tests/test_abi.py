@@ -81,6 +81,16 @@ def test_fails_loudly_without_a_gpu(gsb):
     assert e.value.status == 6
     with pytest.raises(gsb.GsbError):
         gsb.writeback_u8(np.zeros(4))
+    # the multi-device entry points likewise: no device, no group, no device list
+    from coursecomputationalphotography_b200 import strips
+    with pytest.raises(gsb.GsbError) as e:
+        strips.LocalGroup([0, 1])
+    assert e.value.status == 6
+    with pytest.raises(gsb.GsbError) as e:
+        strips.set_devices([0, 1])
+    assert e.value.status == 6
+    strips.set_devices([])  # clearing the list needs no device
+    assert strips.get_devices() == []
 
 
 def test_cpp_dropin_header_compiles():

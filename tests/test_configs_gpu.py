@@ -111,3 +111,42 @@ def test_config4_scale_2e6_residual(gsb):
     assert st.sweeps < 3000 and st.last_eps[0] <= 1e-7
     assert np.abs(x - xstar).max() <= 1e-7
     assert sp.residual(b, x) <= 1e-6 * np.linalg.norm(b)
+
+
+def test_config2_4096_masked_blend_vs_reference_golden(gsb):
+    """BASELINE configs[2] at full size, converged: the 4096^2 x 3-channel Dirichlet-masked blend solved to the
+    reference's stop rule, against the golden the UNMODIFIED reference gaussSeidel produced on this very system
+    (tests/golden/c3_masked_4096.*, generator tests/golden/make_golden_c3.py, ~14 CPU-minutes per channel):
+    max-abs <= 1e-4 * 255 on the 3 x 65 536 sampled unknowns, the written-back 8-bit values equal, and about the
+    same number of sweeps as the reference's lexicographic order needs."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_golden_c3 import c3_system, sample_index
+    meta = json.load(open(os.path.join(here, "golden", "c3_masked_4096.json")))
+    gold = np.load(os.path.join(here, "golden", "c3_masked_4096.npz"))
+    ro, ci, va, b, pix, colors = c3_system(4096)
+    n = len(pix)
+    assert n == meta["n"] and len(va) == meta["nnz"]
+    idx = sample_index(n)
+    assert np.array_equal(idx, gold["index"])
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
+    sp.analyze(gsb._lib.ORDER_USER, colors)
+    for eps in (1e-5, 1e-6):
+        x = sp.gaussSeidel(b, epsilon=eps, max_iteration=meta["cap"])
+        st = sp.last_stats
+        runs = [r for r in meta["runs"] if r["epsilon"] == eps]
+        assert st.sweeps < meta["cap"] and max(list(st.last_eps)[:3]) <= eps
+        worst = 0.0
+        for c in range(3):
+            ref = gold["x_eps%g_ch%d" % (eps, c)]
+            worst = max(worst, float(np.abs(x[c][idx] - ref).max()))
+            assert np.array_equal(gsb.writeback_u8(x[c][idx]), gsb.writeback_u8(ref))
+        assert worst <= TOL_IMAGE, worst
+        ref_sweeps = max(r["sweeps"] for r in runs)
+        assert abs(st.sweeps - ref_sweeps) <= 0.02 * ref_sweeps, (st.sweeps, ref_sweeps)
+        print("C3 4096^2 masked, eps %g: %d sweeps (reference %s), max-abs vs reference %.3e, %.0f ms" %
+              (eps, st.sweeps, [r["sweeps"] for r in runs], worst, st.solve_ms))
