@@ -136,7 +136,9 @@ template <int NRHS, bool CHECK, int STAGES>
 __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
     gs_sweep_fused(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                    const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int cap, GsCtl *ctl,
-                   double *__restrict__ partials, const FusedItem *__restrict__ items, int total, int *flags, int debug) {
+                   double *__restrict__ partials, const FusedItem *__restrict__ items, int total, int *flags, int debug,
+                   int pubk) {
+    static_assert(STAGES == 2, "the control warp's item pipeline (r0..r3) is written for two stages");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RingLayout L = ring_layout(cap, NRHS, CHECK, 0);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
@@ -198,43 +200,84 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
                 if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
             }
         };
-        // release an item to the compute warps: its dependencies are met (its copies were issued earlier)
-        auto make_runnable = [&](const FusedItem &d, int j) {
-            if (d.dep_hi >= d.dep_lo && !(debug & 1)) fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl);
-            if (lane == 0) mbar_arrive(&full[j % STAGES]);
+        // ---- dependency polls, issued one iteration before they are needed ------------------------------------
+        // start: every lane loads one flag of the item's range (relaxed; the load completes in the background -- its
+        // value is first looked at an iteration later).  finish: all lanes saw `epoch` -> one acquire fence; else the
+        // blocking path.  Ranges wider than the warp always take the blocking path.
+        auto start_poll = [&](const FusedItem &d) -> int {
+            int v = epoch;
+            const int i = d.dep_lo + lane;
+            if (!(debug & 1) && i <= d.dep_hi)
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            return v;
         };
-        // items in flight: cur = item j (being computed), nxt = item j+1 (staged, about to be released); the record of
-        // item j+STAGES is fetched one iteration before it is issued
-        FusedItem cur, nxt, far;
-        if (my_items > 0) cur = load_item(0);
-        if (my_items > 1) nxt = load_item(1);
+        // ---- colour-0 tiles this CTA has finished but not yet published -------------------------------------
+        // One release fence covers up to `pubk` tiles (the fence has to wait for the SM's outstanding stores: ~0.6 us
+        // each time).  Never held across a blocking wait: a CTA that waits has published everything it computed, so
+        // the in-order argument for deadlock freedom is unchanged.
+        int pend_n = 0, pend_t0 = 0, pend_t1 = 0, pend_t2 = 0, pend_t3 = 0;
+        auto flush = [&]() {
+            if (pend_n && lane == 0 && !(debug & 2)) {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory"); // release: cumulative over the compute warps' stores
+                                                                  // observed through the `empty` mbarriers
+                asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t0), "r"(epoch) : "memory");
+                if (pend_n > 1) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t1), "r"(epoch) : "memory");
+                if (pend_n > 2) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t2), "r"(epoch) : "memory");
+                if (pend_n > 3) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t3), "r"(epoch) : "memory");
+            }
+            pend_n = 0;
+        };
+        auto finish_poll = [&](const FusedItem &d, int v) {
+            if (d.dep_hi < d.dep_lo || (debug & 1)) return; // a colour-0 item: nothing to wait for
+            const bool wide = d.dep_hi - d.dep_lo >= 32;
+            if (wide || !__all_sync(0xffffffffu, v >= epoch)) {
+                flush();
+                fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl); // (fences and re-converges the warp itself)
+            } else {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                __syncwarp();
+            }
+        };
+        // items in flight: r0 = item j (being computed), r1 = item j+1 (staged, released this iteration), r2 = item
+        // j+2 (issued this iteration), r3 = item j+3 (record being fetched); pv1 / pv2 = the polls of r1 / r2
+        FusedItem r0, r1, r2, r3;
+        r0 = r1 = r2 = r3 = FusedItem{0, 0, 0, 0, 0, 0, 0, -1};
+        if (my_items > 0) r0 = load_item(0);
+        if (my_items > 1) r1 = load_item(1);
+        if (my_items > 2) r2 = load_item(2);
         if (lane == 0) {
-            if (my_items > 0) issue(cur, 0);
-            if (STAGES >= 2 && my_items > 1) issue(nxt, 1);
-#pragma unroll
-            for (int s = 2; s < STAGES; ++s)
-                if (s < my_items) issue(load_item(s), s);
+            if (my_items > 0) issue(r0, 0);
+            if (my_items > 1) issue(r1, 1);
         }
-        if (my_items > 0) make_runnable(cur, 0);
+        int pv1 = epoch, pv2 = epoch;
+        if (my_items > 0) {
+            finish_poll(r0, start_poll(r0));
+            if (lane == 0) mbar_arrive(&full[0]);
+        }
+        if (my_items > 1) pv1 = start_poll(r1);
         for (int j = 0; j < my_items; ++j) {
             const int s = j % STAGES;
-            const bool refill = j + STAGES < my_items;
-            if (refill) far = load_item(j + STAGES); // (L2 latency hidden behind the waits below)
-            if (j + 1 < my_items) make_runnable(nxt, j + 1);
+            if (j + 1 < my_items) { // release item j+1 to the compute warps: its dependencies are met
+                finish_poll(r1, pv1);
+                if (lane == 0) mbar_arrive(&full[(j + 1) % STAGES]);
+            }
+            if (j + 2 < my_items) pv2 = start_poll(r2);
+            if (j + 3 < my_items) r3 = load_item(j + 3);
             mbar_wait(&empty[s], (uint32_t)(j / STAGES) & 1u); // every compute warp has stored item j's rows
-            if (lane == 0) {
-                if (refill) issue(far, s); // first the refill (the copies are what the pipeline waits for) ...
-                if (cur.c == 0 && !(debug & 2)) // ... then the flag (release: cumulative over the compute warps'
-                                                // stores observed through `empty`)
-                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + cur.t), "r"(epoch) : "memory");
+            if (lane == 0 && j + 2 < my_items) issue(r2, s);   // the refill first: it is what the pipeline waits for
+            if (r0.c == 0) {
+                if (pend_n == 0) pend_t0 = r0.t;
+                else if (pend_n == 1) pend_t1 = r0.t;
+                else if (pend_n == 2) pend_t2 = r0.t;
+                else pend_t3 = r0.t;
+                if (++pend_n >= pubk) flush();
             }
-            cur = nxt;
-            if (STAGES == 2) {
-                nxt = far; // item j+2 is item (j+1)+1
-            } else if (j + 2 < my_items) {
-                nxt = load_item(j + 2);
-            }
+            r0 = r1;
+            r1 = r2;
+            r2 = r3;
+            pv1 = pv2;
         }
+        flush();
     } else {
         // ------------------------------------ compute warps ------------------------------------
         double acc[NRHS];
@@ -407,37 +450,39 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     return GSB_OK;
 }
 
+// tuning knobs of kernel 5 (defaults measured on B200, profiles/README.md); read once
+struct FusedEnv {
+    int ctas, lead, debug, pubk;
+};
+static const FusedEnv &fused_env() {
+    static FusedEnv e = {-1, 0, 0, 0};
+    if (e.ctas < 0) {
+        const char *v = getenv("GSB_FUSED_DEBUG"); // measurement aid, WRONG RESULTS: 1 = no dependency waits, 2 = no flags
+        e.debug = v ? atoi(v) : 0;
+        v = getenv("GSB_FUSED_LEAD"); // tiles colour 0 runs ahead beyond the dependency distance
+        e.lead = v ? atoi(v) : 0;
+        v = getenv("GSB_FUSED_PUBK"); // colour-0 tiles published per release fence (1..4)
+        e.pubk = v ? atoi(v) : 0;
+        v = getenv("GSB_RING_CTAS");
+        e.ctas = v ? atoi(v) : 0;
+    }
+    return e;
+}
+#define GS_FUSED_LEAD_DEFAULT 128 // beyond the dependency distance: long enough for the dependencies of a tile to be
+                                  // finished when it comes up, short enough for the reuse to stay in L2 (measured)
+#define GS_FUSED_PUBK_DEFAULT 2
+
+// Once per solve, OUTSIDE any graph capture: reset the tile flags (ctl->sweeps restarts at 0) and (re)build the item
+// table when the lead changed.
 int gsb_plan_fused_reset(const GsbPlan *p, cudaStream_t st) {
     if (!p->fused_ok) return GSB_OK;
-    GSB_CUDA(cudaMemsetAsync(p->fused_flags.p, 0, sizeof(int) * (size_t)p->blocks[0], st));
-    return GSB_OK;
-}
-
-template <int NRHS>
-static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const double *va, const double *dg,
-                          const double *b, double *x, int64_t ld, bool check, GsCtl *ctl, double *partials,
-                          cudaStream_t st, int *slots) {
-    typedef void (*fused_fn)(const int *, const int *, const double *, const double *, const double *, double *, int64_t,
-                             int, GsCtl *, double *, const FusedItem *, int, int *, int);
-    fused_fn kern = check ? (fused_fn)gs_sweep_fused<NRHS, true, GS_RING_STAGES_DEFAULT>
-                          : (fused_fn)gs_sweep_fused<NRHS, false, GS_RING_STAGES_DEFAULT>;
-    const int smem = 64 + GS_RING_STAGES_DEFAULT * ring_layout(p->cap, NRHS, check, 0).stage_bytes;
-    int per_sm = 1;
-    GSB_TRY(gsb_kernel_occupancy((const void *)kern, smem, &per_sm, GS_FUSED_THREADS));
-    static int env_ctas = -1, env_lead = -1, env_debug = 0;
-    if (env_ctas < 0) {
-        const char *dbg = getenv("GSB_FUSED_DEBUG"); // measurement aid, WRONG RESULTS: 1 = no dependency waits, 2 = no flags
-        env_debug = dbg ? atoi(dbg) : 0;
-        const char *e = getenv("GSB_RING_CTAS");
-        env_ctas = e ? atoi(e) : 0;
-        e = getenv("GSB_FUSED_LEAD"); // extra lead in tiles on top of the dependency distance; default = the grid size
-        env_lead = e ? atoi(e) : 0;
-    }
-    if (env_ctas && env_ctas < per_sm) per_sm = env_ctas;
+    GsbPlan *pm = const_cast<GsbPlan *>(p); // the table is a cache that belongs to (matrix, lead)
     const int nt0 = p->blocks[0], nt1 = p->blocks[1];
-    int grid = gsb_sm_count() * per_sm; // every CTA must be resident: the walk waits on other CTAs' tiles
-    if (grid > nt0 + nt1) grid = nt0 + nt1;
-    if (grid > GSB_RING_SLOTS_MAX) grid = GSB_RING_SLOTS_MAX;
+    GSB_CUDA(cudaMemsetAsync(p->fused_flags.p, 0, sizeof(int) * (size_t)nt0, st));
+    const FusedEnv &env = fused_env();
+    int lead = p->fused_lead_min + (p->fused_lead_extra > 0 ? p->fused_lead_extra : env.lead > 0 ? env.lead : GS_FUSED_LEAD_DEFAULT);
+    if (lead > nt0) lead = nt0;
+    if (pm->fused_items.p && pm->fused_items_lead == lead) return GSB_OK;
     GsbFusedArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.row0_0 = p->color_start[0];
@@ -449,20 +494,38 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     fa.tile_k1 = p->tile_k.p + p->tile_off[1];
     fa.dep = reinterpret_cast<const int2 *>(p->fused_dep.p);
     fa.flags = p->fused_flags.p;
-    // lead: the dependency distance plus the items in flight (one per CTA), so that a colour-1 tile's dependencies
-    // are finished, not merely started, when it comes up
-    int lead = p->fused_lead_min + (p->fused_lead_extra > 0 ? p->fused_lead_extra : env_lead > 0 ? env_lead : grid);
-    if (lead > nt0) lead = nt0;
     fa.lead = lead;
     fa.nalt = nt1 < nt0 - lead ? nt1 : nt0 - lead;
-    // the item table belongs to (matrix, lead): rebuilt when the lead changes (stream-ordered before the launch)
-    GsbPlan *pm = const_cast<GsbPlan *>(p);
-    if (!pm->fused_items.p || pm->fused_items_lead != lead) {
-        GSB_TRY(pm->fused_items.alloc((int64_t)(nt0 + nt1) * (int64_t)(sizeof(FusedItem) / sizeof(int4))));
-        plan_fused_items<<<(nt0 + nt1 + 255) / 256, 256, 0, st>>>(fa, reinterpret_cast<FusedItem *>(pm->fused_items.p));
-        GSB_KERNEL_CHECK();
-        pm->fused_items_lead = lead;
+    GSB_TRY(pm->fused_items.alloc((int64_t)(nt0 + nt1) * (int64_t)(sizeof(FusedItem) / sizeof(int4))));
+    plan_fused_items<<<(nt0 + nt1 + 255) / 256, 256, 0, st>>>(fa, reinterpret_cast<FusedItem *>(pm->fused_items.p));
+    GSB_KERNEL_CHECK();
+    pm->fused_items_lead = lead;
+    return GSB_OK;
+}
+
+template <int NRHS>
+static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const double *va, const double *dg,
+                          const double *b, double *x, int64_t ld, bool check, GsCtl *ctl, double *partials,
+                          cudaStream_t st, int *slots) {
+    typedef void (*fused_fn)(const int *, const int *, const double *, const double *, const double *, double *, int64_t,
+                             int, GsCtl *, double *, const FusedItem *, int, int *, int, int);
+    fused_fn kern = check ? (fused_fn)gs_sweep_fused<NRHS, true, GS_RING_STAGES_DEFAULT>
+                          : (fused_fn)gs_sweep_fused<NRHS, false, GS_RING_STAGES_DEFAULT>;
+    const int smem = 64 + GS_RING_STAGES_DEFAULT * ring_layout(p->cap, NRHS, check, 0).stage_bytes;
+    int per_sm = 1;
+    GSB_TRY(gsb_kernel_occupancy((const void *)kern, smem, &per_sm, GS_FUSED_THREADS));
+    const FusedEnv &env = fused_env();
+    if (env.ctas && env.ctas < per_sm) per_sm = env.ctas;
+    const int nt0 = p->blocks[0], nt1 = p->blocks[1];
+    int grid = gsb_sm_count() * per_sm; // every CTA must be resident: the walk waits on other CTAs' tiles
+    if (grid > nt0 + nt1) grid = nt0 + nt1;
+    if (grid > GSB_RING_SLOTS_MAX) grid = GSB_RING_SLOTS_MAX;
+    if (!p->fused_items.p || p->fused_items_lead < 0) {
+        gsb_set_error("internal: kernel 5 launched without gsb_plan_fused_reset");
+        return GSB_ERR_STATE;
     }
+    int pubk = env.pubk > 0 ? env.pubk : GS_FUSED_PUBK_DEFAULT;
+    if (pubk > 4) pubk = 4;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(GS_FUSED_THREADS);
@@ -474,7 +537,7 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     cfg.attrs = attr;
     cfg.numAttrs = gsb_pdl_mode((int64_t)p->color_start[2] - p->color_start[0]) ? 1 : 0;
     GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, ci, va, dg, b, x, ld, p->cap, ctl, partials,
-                                (const FusedItem *)pm->fused_items.p, nt0 + nt1, p->fused_flags.p, env_debug));
+                                (const FusedItem *)p->fused_items.p, nt0 + nt1, p->fused_flags.p, env.debug, pubk));
     if (slots) *slots = grid;
     return GSB_OK;
 }

@@ -181,23 +181,34 @@ __device__ __noinline__ void halo_tile_done(int *counter, int n_halo_tiles, int 
     if (flag1) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag1), "r"(epoch) : "memory");
 }
 
-// Fused end of sweep (GsbEndArgs): run by the last CTA of the sweep's last colour phase to retire, all GS_THREADS
-// threads.  Same steps as gs_end_sweep (mode 0) / gs_end_sweep_peer, folded by 256 threads instead of 1024 (the
-// stop norm therefore agrees with the separate kernels to rounding, not bit for bit; the fold order is fixed).
+// End of a sweep, ONE implementation for every path: the separate kernels (gs_end_sweep, gs_end_sweep_peer) and the
+// fused end (GsbEndArgs: the last CTA of the sweep's last colour phase to retire).  Always run by GS_THREADS threads
+// of one CTA, so the fold order -- and with it the stop norm, bit for bit -- does not depend on the path.
+//   mode 0: fold the partials, (strip solver: exchange the sums with the peers,) bump the counter, decide
+//   mode 1: fold into ctl->eps_local only (strip solver on the ncclAllReduce path, before the all-reduce)
+//   mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
+// Peer exchange (GsbEpsExchange): this rank's k sums go into slot `rank` of every rank's box (NVLink peer stores)
+// with the slot's flag raised to `epoch` (release, system scope); the rank then waits for the `world` flags of its
+// own box (bounded: a missing rank raises ctl->error instead of hanging the GPU) and adds the slots in rank order --
+// the same bits, hence the same decision, on every rank.
 // Out of line: it runs once per sweep and must not weigh on the tile loop's register allocation.
 template <int NRHS>
-__device__ __noinline__ void ring_end_of_sweep(GsCtl *ctl, const double *partials, int n_partials, int checked,
-                                               int exchange, const GsbEpsExchange ex) {
+__device__ __noinline__ void gs_end_of_sweep_body(GsCtl *ctl, const double *partials, int n_partials, int checked,
+                                                  int mode, int exchange, const GsbEpsExchange ex) {
     __shared__ double ws[NRHS][GS_THREADS / 32];
     __shared__ double tot[NRHS];
     __shared__ double all[GSB_DIST_MAX_WORLD][NRHS];
     __shared__ int timed_out;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (!checked) {
+    if (mode == 2 || !checked) {
         if (tid == 0) {
+            bool all_ok = checked != 0;
+            if (checked)
+                for (int r = 0; r < NRHS; ++r)
+                    if (ctl->eps_last[r] > ctl->epsilon) all_ok = false;
             const int cnt = ctl->sweeps + 1;
             ctl->sweeps = cnt;
-            if (cnt >= ctl->max_iter) ctl->done = 1;
+            if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
         }
         return;
     }
@@ -223,10 +234,14 @@ __device__ __noinline__ void ring_end_of_sweep(GsCtl *ctl, const double *partial
         tot[tid] = t;
     }
     __syncthreads();
-    if (exchange) { // strip solver: the same protocol as gs_end_sweep_peer
+    if (mode == 1) { // this rank's share; the all-reduce writes eps_last (idempotent after the stop)
+        if (tid < NRHS) ctl->eps_local[tid] = tot[tid];
+        return;
+    }
+    if (exchange) {
         const int par = ex.epoch & 1;
         const size_t flag_off = (size_t)2 * ex.world * GSB_MAX_RHS; // in doubles
-        if (tid < ex.world) {
+        if (tid < ex.world) { // push this rank's sums into slot `rank` of rank q's box
             const int q = tid;
             double *dst = ex.box[q] + (size_t)(par * ex.world + ex.rank) * GSB_MAX_RHS;
 #pragma unroll
@@ -235,7 +250,7 @@ __device__ __noinline__ void ring_end_of_sweep(GsCtl *ctl, const double *partial
             int *flag = reinterpret_cast<int *>(ex.box[q] + flag_off) + par * ex.world + ex.rank;
             asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(ex.epoch) : "memory");
         }
-        if (tid < ex.world) {
+        if (tid < ex.world) { // collect slot q of the own box
             const int q = tid;
             const int *flag = reinterpret_cast<const int *>(ex.box[ex.rank] + flag_off) + par * ex.world + q;
             int v = 0;
@@ -269,7 +284,7 @@ __device__ __noinline__ void ring_end_of_sweep(GsCtl *ctl, const double *partial
                 for (int q = 0; q < ex.world; ++q) t += all[q][r];
             }
             ctl->eps_last[r] = t;
-            if (t > ctl->epsilon) all_ok = false; // v2 :356
+            if (t > ctl->epsilon) all_ok = false; // v2 :356: the loop continues while eps > epsilon
         }
         const int cnt = ctl->sweeps + 1;
         ctl->sweeps = cnt;
@@ -557,7 +572,7 @@ __global__ void __launch_bounds__(GS_THREADS, (NRHS >= 3 && WIN ? 3 : 4))
         __syncthreads();
         if (s_last) {
             if (tid == 0) end.ctl->ticket = 0;
-            ring_end_of_sweep<NRHS>(end.ctl, end.partials, end.n_partials, end.checked, end.exchange, end.ex);
+            gs_end_of_sweep_body<NRHS>(end.ctl, end.partials, end.n_partials, end.checked, 0, end.exchange, end.ex);
         }
     }
 }
@@ -678,144 +693,27 @@ __global__ void __launch_bounds__(GS_THREADS) plan_tile_slots(const int *__restr
 //   mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)
 // ---------------------------------------------------------------------------------------------
 template <int NRHS>
-__global__ void __launch_bounds__(1024) gs_end_sweep(GsCtl *ctl, const double *__restrict__ partials, int n_partials,
-                                                     int checked, int mode) {
-    pdl_launch_dependents();
+__global__ void __launch_bounds__(GS_THREADS) gs_end_sweep(GsCtl *ctl, const double *__restrict__ partials, int n_partials,
+                                                           int checked, int mode) {
+    // the predecessor (the sweep's last colour phase, or the all-reduce) must be complete before anything is read;
+    // the dependents are released only after that, so that the next sweep's first kernel can overlap this one but
+    // never the colour phase before it
     pdl_wait();
+    pdl_launch_dependents();
     if (*(volatile const int *)&ctl->done) return;
-    if (mode == 2) {
-        if (threadIdx.x == 0) {
-            bool all_ok = checked != 0;
-            if (checked)
-                for (int r = 0; r < NRHS; ++r)
-                    if (ctl->eps_last[r] > ctl->epsilon) all_ok = false;
-            const int cnt = ctl->sweeps + 1;
-            ctl->sweeps = cnt;
-            if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
-        }
-        return;
-    }
-    __shared__ double ws[NRHS][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (checked) {
-        double s[NRHS];
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
-        for (int i = threadIdx.x; i < n_partials; i += 1024) {
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) s[r] += __ldcg(partials + (size_t)i * NRHS + r); // L2: written by the predecessor
-        }
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            double t = s[r];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
-            if (lane == 0) ws[r][wid] = t;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        bool all_ok = checked != 0;
-        if (checked) {
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) {
-                double t = 0.0;
-                for (int w = 0; w < 32; ++w) t += ws[r][w];
-                if (mode == 1)
-                    ctl->eps_local[r] = t; // this rank's share; the all-reduce writes eps_last (idempotent after the stop)
-                else
-                    ctl->eps_last[r] = t;
-                if (t > ctl->epsilon) all_ok = false; // v2 :356: the loop continues while eps > epsilon
-            }
-        }
-        if (mode == 1) return;
-        const int cnt = ctl->sweeps + 1;
-        ctl->sweeps = cnt;
-        if (all_ok || cnt >= ctl->max_iter) ctl->done = 1;
-    }
+    GsbEpsExchange none;
+    none.world = none.rank = none.epoch = 0;
+    gs_end_of_sweep_body<NRHS>(ctl, partials, n_partials, checked, mode, 0, none);
 }
 
 // end of a checked sweep of the strip solver, stop-rule all-reduce fused in (see GsbEpsExchange)
 template <int NRHS>
-__global__ void __launch_bounds__(1024) gs_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials,
-                                                          const GsbEpsExchange ex) {
-    pdl_launch_dependents();
+__global__ void __launch_bounds__(GS_THREADS) gs_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials,
+                                                                const GsbEpsExchange ex) {
     pdl_wait();
+    pdl_launch_dependents();
     if (*(volatile const int *)&ctl->done) return;
-    __shared__ double ws[NRHS][32];
-    __shared__ double tot[NRHS];
-    __shared__ double all[GSB_DIST_MAX_WORLD][NRHS];
-    __shared__ int timed_out;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double s[NRHS];
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += 1024) {
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) s[r] += __ldcg(partials + (size_t)i * NRHS + r);
-    }
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r) {
-        double t = s[r];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
-        if (lane == 0) ws[r][wid] = t;
-    }
-    if (threadIdx.x == 0) timed_out = 0;
-    __syncthreads();
-    if (threadIdx.x < NRHS) {
-        double t = 0.0;
-        for (int w = 0; w < 32; ++w) t += ws[threadIdx.x][w];
-        tot[threadIdx.x] = t;
-    }
-    __syncthreads();
-    const int par = ex.epoch & 1;
-    const size_t flag_off = (size_t)2 * ex.world * GSB_MAX_RHS; // in doubles
-    if (threadIdx.x < ex.world) { // push this rank's sums into slot `rank` of rank q's box
-        const int q = threadIdx.x;
-        double *dst = ex.box[q] + (size_t)(par * ex.world + ex.rank) * GSB_MAX_RHS;
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + r), "d"(tot[r]) : "memory");
-        int *flag = reinterpret_cast<int *>(ex.box[q] + flag_off) + par * ex.world + ex.rank;
-        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(ex.epoch) : "memory");
-    }
-    if (threadIdx.x < ex.world) { // collect slot q of the own box
-        const int q = threadIdx.x;
-        const int *flag = reinterpret_cast<const int *>(ex.box[ex.rank] + flag_off) + par * ex.world + q;
-        int v = 0;
-        long long spins = 0;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v >= ex.epoch) break;
-            if (++spins > (1ll << 25)) { // ~10 s: a rank is missing
-                timed_out = 1;
-                break;
-            }
-            __nanosleep(spins < 64 ? 20 : 200);
-        }
-        const double *src = ex.box[ex.rank] + (size_t)(par * ex.world + q) * GSB_MAX_RHS;
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            double t;
-            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t) : "l"(src + r) : "memory");
-            all[q][r] = t;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        bool all_ok = true;
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            double t = 0.0;
-            for (int q = 0; q < ex.world; ++q) t += all[q][r];
-            ctl->eps_last[r] = t;
-            if (t > ctl->epsilon) all_ok = false; // v2 :356
-        }
-        const int cnt = ctl->sweeps + 1;
-        ctl->sweeps = cnt;
-        if (timed_out) ctl->error = 1;
-        if (all_ok || cnt >= ctl->max_iter || timed_out) ctl->done = 1;
-    }
+    gs_end_of_sweep_body<NRHS>(ctl, partials, n_partials, 1, 0, 1, ex);
 }
 
 int gsb_launch_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials, int nrhs, const GsbEpsExchange *ex,
@@ -835,7 +733,7 @@ int gsb_launch_end_sweep_peer(GsCtl *ctl, const double *partials, int n_partials
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
-    cfg.blockDim = dim3(1024);
+    cfg.blockDim = dim3(GS_THREADS);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -912,7 +810,7 @@ int gsb_launch_end_sweep(GsCtl *ctl, const double *partials, int n_partials, int
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
-    cfg.blockDim = dim3(1024);
+    cfg.blockDim = dim3(GS_THREADS);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
