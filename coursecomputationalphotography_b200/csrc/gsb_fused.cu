@@ -227,13 +227,19 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
             }
             pend_n = 0;
         };
-        auto finish_poll = [&](const FusedItem &d, int v) {
-            if (d.dep_hi < d.dep_lo || (debug & 1)) return; // a colour-0 item: nothing to wait for
-            const bool wide = d.dep_hi - d.dep_lo >= 32;
-            if (wide || !__all_sync(0xffffffffu, v >= epoch)) {
-                flush();
-                fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl); // (fences and re-converges the warp itself)
-            } else {
+        // blocking completion of a poll (the slow path); fences and re-converges the warp itself
+        auto wait_blocking = [&](const FusedItem &d) {
+            flush();
+            fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl);
+        };
+        // did the poll started an iteration ago see every flag?  (uniform over the warp)
+        auto poll_ready = [&](const FusedItem &d, int v) -> bool {
+            if (d.dep_hi < d.dep_lo || (debug & 1)) return true; // a colour-0 item: nothing to wait for
+            if (d.dep_hi - d.dep_lo >= 32) return false;          // wider than the warp: always the blocking path
+            return __all_sync(0xffffffffu, v >= epoch);
+        };
+        auto acquire = [&](const FusedItem &d) {
+            if (d.dep_hi >= d.dep_lo && !(debug & 1)) {
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 __syncwarp();
             }
@@ -250,28 +256,50 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
             if (my_items > 1) issue(r1, 1);
         }
         int pv1 = epoch, pv2 = epoch;
-        if (my_items > 0) {
-            finish_poll(r0, start_poll(r0));
+        if (my_items > 0) { // (nothing of this CTA is unpublished yet: blocking here is harmless)
+            if (poll_ready(r0, start_poll(r0)))
+                acquire(r0);
+            else
+                wait_blocking(r0);
             if (lane == 0) mbar_arrive(&full[0]);
         }
         if (my_items > 1) pv1 = start_poll(r1);
         for (int j = 0; j < my_items; ++j) {
             const int s = j % STAGES;
-            if (j + 1 < my_items) { // release item j+1 to the compute warps: its dependencies are met
-                finish_poll(r1, pv1);
+            // retire item j: every compute warp has stored its rows -> refill the stage (first: the copies are what the
+            // pipeline waits for), then make a colour-0 tile's values public
+            auto retire = [&]() {
+                mbar_wait(&empty[s], (uint32_t)(j / STAGES) & 1u);
+                if (lane == 0 && j + 2 < my_items) issue(r2, s);
+                if (r0.c == 0) {
+                    if (pend_n == 0) pend_t0 = r0.t;
+                    else if (pend_n == 1) pend_t1 = r0.t;
+                    else if (pend_n == 2) pend_t2 = r0.t;
+                    else pend_t3 = r0.t;
+                    if (++pend_n >= pubk) flush();
+                }
+            };
+            bool retired = false;
+            if (j + 1 < my_items) { // release item j+1 to the compute warps once its dependencies are met
+                if (poll_ready(r1, pv1)) {
+                    acquire(r1);
+                } else {
+                    // NEVER block while this CTA holds a tile that is computed (or being computed) but not yet
+                    // published: item j will finish -- it was released -- so retire and publish it first.  A CTA
+                    // that waits has then published every tile it is responsible for up to j, and the earliest
+                    // unpublished colour-0 tile of the whole sweep always belongs to a CTA that is not waiting:
+                    // no cycle of CTAs waiting on each other's current tile can form, whatever the lead.
+                    // (Without this a lead of about half the grid size deadlocked: tile j+1 of CTA X needed the
+                    // current tile of CTA Y, whose tile j+1 needed the current tile of X -- measured, round 2.)
+                    retire();
+                    retired = true;
+                    wait_blocking(r1);
+                }
                 if (lane == 0) mbar_arrive(&full[(j + 1) % STAGES]);
             }
+            if (!retired) retire();
             if (j + 2 < my_items) pv2 = start_poll(r2);
             if (j + 3 < my_items) r3 = load_item(j + 3);
-            mbar_wait(&empty[s], (uint32_t)(j / STAGES) & 1u); // every compute warp has stored item j's rows
-            if (lane == 0 && j + 2 < my_items) issue(r2, s);   // the refill first: it is what the pipeline waits for
-            if (r0.c == 0) {
-                if (pend_n == 0) pend_t0 = r0.t;
-                else if (pend_n == 1) pend_t1 = r0.t;
-                else if (pend_n == 2) pend_t2 = r0.t;
-                else pend_t3 = r0.t;
-                if (++pend_n >= pubk) flush();
-            }
             r0 = r1;
             r1 = r2;
             r2 = r3;
@@ -470,7 +498,7 @@ static const FusedEnv &fused_env() {
 }
 #define GS_FUSED_LEAD_DEFAULT 128 // beyond the dependency distance: long enough for the dependencies of a tile to be
                                   // finished when it comes up, short enough for the reuse to stay in L2 (measured)
-#define GS_FUSED_PUBK_DEFAULT 2
+#define GS_FUSED_PUBK_DEFAULT 1 // measured: batching delays availability by a whole item of the owning CTA (-13 %)
 
 // Once per solve, OUTSIDE any graph capture: reset the tile flags (ctl->sweeps restarts at 0) and (re)build the item
 // table when the lead changed.

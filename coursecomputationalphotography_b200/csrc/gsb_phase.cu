@@ -841,16 +841,23 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
 // Measured on B200 (profiles/README.md): one right-hand side is fastest with the windows (4); with several
 // fused right-hand sides a window stage (49 KB at k = 3) leaves room for two CTAs per SM only, and the ring
 // with global gathers (3), which fits three, wins.  Kernel 4 stays selectable explicitly.
-static bool fused_sweep_auto() {
+// Kernel 5 (both colours in one launch, gsb_fused.cu) pays when the reuse it creates cannot happen otherwise -- the
+// sweep's working set must exceed L2 -- and when a tile carries enough bytes to amortise its flag traffic.  Measured on
+// B200 (profiles/README.md, 4096^2): k = 3: 0.85 of the copy bandwidth against 0.80 for kernel 3; k = 1: 0.82 against
+// 0.93 for the window kernel (4); 1024^2 (L2-resident): 0.45 against 0.70.  GSB_FUSED_SWEEP=0 never, =2 whenever possible.
+#define GS_FUSED_AUTO_MIN_ROWS (3 << 20)
+static bool fused_sweep_auto(const GsbPlan *p, int nrhs) {
     static int env = -1;
     if (env < 0) {
         const char *e = getenv("GSB_FUSED_SWEEP");
-        env = e ? atoi(e) : 1; // measured on B200 (profiles/README.md): on where the plan allows it
+        env = e ? atoi(e) : 1;
     }
-    return env != 0;
+    if (env == 0) return false;
+    if (env == 2) return true;
+    return nrhs >= 2 && p->color_start[p->n_colors] - p->color_start[0] >= GS_FUSED_AUTO_MIN_ROWS;
 }
 int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
-    if (p->fused_ok && (p->requested == 5 || (p->requested == 0 && fused_sweep_auto()))) return 5;
+    if (p->fused_ok && (p->requested == 5 || (p->requested == 0 && fused_sweep_auto(p, nrhs)))) return 5;
     if (p->kernel != 4) return p->kernel;
     if (p->requested == 4) return 4;
     if (p->requested == 3) return 3;
