@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
     gs_sweep_fused(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                    const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int cap, GsCtl *ctl,
                    double *__restrict__ partials, const FusedItem *__restrict__ items, int total, int *flags, int debug,
-                   int pubk) {
+                   int pubk, int hints) {
     static_assert(STAGES == 2, "the control warp's item pipeline (r0..r3) is written for two stages");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const RingLayout L = ring_layout(cap, NRHS, CHECK, 0);
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
     if (tid >= GS_THREADS) {
         // ------------------------------------ control warp -------------------------------------
         const int lane = tid - GS_THREADS;
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
         auto load_item = [&](int j) -> FusedItem { // all lanes read the same 32 bytes (one broadcast transaction)
             const int4 *src = reinterpret_cast<const int4 *>(items + (bid + j * gsz));
             const int4 a = __ldg(src), c4 = __ldg(src + 1);
@@ -189,15 +190,32 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
             hdr[1] = r_begin;
             hdr[2] = rows;
             mbar_expect_tx_only(&full[s], tx);
-            if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
-            if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
-            bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
-            bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
+            // the matrix, the diagonal and b are streamed once per sweep: evict-first, so that they do not push the
+            // x lines out of L2 on whose reuse this kernel lives (hints & 1; measured, profiles/README.md)
+            if (hints & 1) {
+                if (bytes_v) bulk_g2s_hint(st + L.va_off, va + kv0, bytes_v, &full[s], pol_stream);
+                if (bytes_c) bulk_g2s_hint(st + L.ci_off, ci + kc0, bytes_c, &full[s], pol_stream);
+                bulk_g2s_hint(st + L.rp_off, rp + ra, bytes_r, &full[s], pol_stream);
+                bulk_g2s_hint(st + L.dg_off, dg + ea, bytes_p, &full[s], pol_stream);
+            } else {
+                if (bytes_v) bulk_g2s(st + L.va_off, va + kv0, bytes_v, &full[s]);
+                if (bytes_c) bulk_g2s(st + L.ci_off, ci + kc0, bytes_c, &full[s]);
+                bulk_g2s(st + L.rp_off, rp + ra, bytes_r, &full[s]);
+                bulk_g2s(st + L.dg_off, dg + ea, bytes_p, &full[s]);
+            }
 #pragma unroll
             for (int r = 0; r < NRHS; ++r) {
-                bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
+                if (hints & 1)
+                    bulk_g2s_hint(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s], pol_stream);
+                else
+                    bulk_g2s(st + L.b_off + r * L.plane * 8, b + r * n + ea, bytes_p, &full[s]);
                 // x_old: this tile's own rows, which nobody but this tile writes during the sweep
-                if (CHECK) bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
+                if (CHECK) {
+                    if (hints & 2)
+                        bulk_g2s_hint(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s], pol_keep);
+                    else
+                        bulk_g2s(st + L.xo_off + r * L.plane * 8, x + r * n + ea, bytes_p, &full[s]);
+                }
             }
         };
         // ---- dependency polls, issued one iteration before they are needed ------------------------------------
@@ -311,6 +329,7 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
         double acc[NRHS];
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
+        const uint64_t pol_x = l2_policy_evict_last();
         for (int j = 0; j < my_items; ++j) {
             const int s = j % STAGES;
             unsigned char *st = stage0 + (size_t)s * L.stage_bytes;
@@ -333,7 +352,11 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
                         const double bb = reinterpret_cast<const double *>(st + L.b_off)[r * L.plane + po];
                         const double xn = __ddiv_rn(__dsub_rn(bb, sig[r]), d);
                         if (CHECK) acc[r] += fabs(xn - reinterpret_cast<const double *>(st + L.xo_off)[r * L.plane + po]);
-                        x[r * n + i] = xn;
+                        if (hints & 4) // keep the new value in L2: the other colour gathers it a few hundred tiles later
+                            asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(x + r * n + i), "d"(xn), "l"(pol_x)
+                                         : "memory");
+                        else
+                            x[r * n + i] = xn;
                     }
                 }
             }
@@ -478,12 +501,16 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     return GSB_OK;
 }
 
+#define GS_FUSED_L2HINT_DEFAULT 0
+#define GS_FUSED_LEAD_DEFAULT 128 // beyond the dependency distance: long enough for the dependencies of a tile to be
+                                  // finished when it comes up, short enough for the reuse to stay in L2 (measured)
+#define GS_FUSED_PUBK_DEFAULT 1 // measured: batching delays availability by a whole item of the owning CTA (-13 %)
 // tuning knobs of kernel 5 (defaults measured on B200, profiles/README.md); read once
 struct FusedEnv {
-    int ctas, lead, debug, pubk;
+    int ctas, lead, debug, pubk, hints;
 };
 static const FusedEnv &fused_env() {
-    static FusedEnv e = {-1, 0, 0, 0};
+    static FusedEnv e = {-1, 0, 0, 0, 0};
     if (e.ctas < 0) {
         const char *v = getenv("GSB_FUSED_DEBUG"); // measurement aid, WRONG RESULTS: 1 = no dependency waits, 2 = no flags
         e.debug = v ? atoi(v) : 0;
@@ -491,14 +518,13 @@ static const FusedEnv &fused_env() {
         e.lead = v ? atoi(v) : 0;
         v = getenv("GSB_FUSED_PUBK"); // colour-0 tiles published per release fence (1..4)
         e.pubk = v ? atoi(v) : 0;
+        v = getenv("GSB_FUSED_L2HINT"); // 1: matrix / b copies evict-first; 2: x_old copies evict-last; 3: both
+        e.hints = v ? atoi(v) : GS_FUSED_L2HINT_DEFAULT;
         v = getenv("GSB_RING_CTAS");
         e.ctas = v ? atoi(v) : 0;
     }
     return e;
 }
-#define GS_FUSED_LEAD_DEFAULT 128 // beyond the dependency distance: long enough for the dependencies of a tile to be
-                                  // finished when it comes up, short enough for the reuse to stay in L2 (measured)
-#define GS_FUSED_PUBK_DEFAULT 1 // measured: batching delays availability by a whole item of the owning CTA (-13 %)
 
 // Once per solve, OUTSIDE any graph capture: reset the tile flags (ctl->sweeps restarts at 0) and (re)build the item
 // table when the lead changed.
@@ -536,7 +562,7 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
                           const double *b, double *x, int64_t ld, bool check, GsCtl *ctl, double *partials,
                           cudaStream_t st, int *slots) {
     typedef void (*fused_fn)(const int *, const int *, const double *, const double *, const double *, double *, int64_t,
-                             int, GsCtl *, double *, const FusedItem *, int, int *, int, int);
+                             int, GsCtl *, double *, const FusedItem *, int, int *, int, int, int);
     fused_fn kern = check ? (fused_fn)gs_sweep_fused<NRHS, true, GS_RING_STAGES_DEFAULT>
                           : (fused_fn)gs_sweep_fused<NRHS, false, GS_RING_STAGES_DEFAULT>;
     const int smem = 64 + GS_RING_STAGES_DEFAULT * ring_layout(p->cap, NRHS, check, 0).stage_bytes;
@@ -565,7 +591,7 @@ static int launch_fused_t(const GsbPlan *p, const int *rp, const int *ci, const 
     cfg.attrs = attr;
     cfg.numAttrs = gsb_pdl_mode((int64_t)p->color_start[2] - p->color_start[0]) ? 1 : 0;
     GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, ci, va, dg, b, x, ld, p->cap, ctl, partials,
-                                (const FusedItem *)p->fused_items.p, nt0 + nt1, p->fused_flags.p, env.debug, pubk));
+                                (const FusedItem *)p->fused_items.p, nt0 + nt1, p->fused_flags.p, env.debug, pubk, env.hints));
     if (slots) *slots = grid;
     return GSB_OK;
 }
