@@ -264,7 +264,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_PORT", "29555")
         os.environ.setdefault("RANK", "0")
         os.environ.setdefault("WORLD_SIZE", "1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank that dies must not hold a multi-GPU box for ten minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         from coursecomputationalphotography_b200 import dist_bench
         return dist_bench.run(args, pkg, wl, dist, rank, world, local)
 

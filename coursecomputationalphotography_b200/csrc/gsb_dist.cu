@@ -869,10 +869,11 @@ static int dist_peer_setup(gsb_dist *d, cudaStream_t st) {
     memset(&hx, 0, sizeof(hx));
     memset(&hf, 0, sizeof(hf));
     if (d->lg) {
-        // same process: direct peer access between the devices replaces the IPC mappings
-        for (int p = 0; p < 2 && ok; ++p) {
-            if (!d->has_peer(p)) continue;
-            const int pd = d->lg->dev[d->peer_rank(p)];
+        // same process: direct peer access between the devices replaces the IPC mappings -- to EVERY rank's device,
+        // not only the neighbours': the stop-rule exchange stores into all ranks' boxes
+        for (int q = 0; q < d->world && ok; ++q) {
+            if (q == d->rank) continue;
+            const int pd = d->lg->dev[q];
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, d->device, pd) != cudaSuccess || !can) ok = 0;
             if (ok) {
@@ -1263,9 +1264,9 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             trace_mark(); // 4 marks per sweep: start, after phase 0, after phase 1, after the end-of-sweep step
             const bool check = (sweep_no % opts.check_every) == 0 || sweep_no == max_iteration;
             int poff = 0;
-            // opt-in (GSB_FUSED_END=1): the second colour phase ends the sweep itself -- fold, peer exchange, decision
+            // default for strips (GSB_FUSED_END=0 turns it off): the second colour phase ends the sweep itself -- fold, peer exchange, decision
             // (GsbEndArgs); needs the fused stop-rule exchange on checked sweeps and both colours non-empty
-            const bool fuse_end = use_peer && fused_eps && gsb_fused_end_enabled() &&
+            const bool fuse_end = use_peer && fused_eps && gsb_fused_end_enabled_strips() &&
                                   gsb_plan_can_fuse_end(&d->plan, nrhs) && d->color_start[1] > d->color_start[0] &&
                                   d->color_start[2] > d->color_start[1];
             for (int c = 0; c < 2 && status == GSB_OK; ++c) {

@@ -291,6 +291,7 @@ struct GsbEndArgs {
     GsbEpsExchange ex;
 };
 bool gsb_fused_end_enabled();                          // GSB_FUSED_END=1
+bool gsb_fused_end_enabled_strips();                   // strip solver: on unless GSB_FUSED_END=0
 bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs); // the effective kernel is a ring kernel
 
 // one colour phase; x and b have leading dimension ld; partials: blocks[c] * nrhs doubles

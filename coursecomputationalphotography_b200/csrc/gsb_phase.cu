@@ -864,14 +864,19 @@ int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
     return nrhs >= 2 ? 3 : 4;
 }
 
-bool gsb_fused_end_enabled() {
-    static int env = -1;
-    if (env < 0) {
+// GSB_FUSED_END: 1 = on everywhere it applies, 0 = off; unset = on for the strip solver (measured on B200, N = 2:
+// 1086 against 1057 Gnnz/s, bit-identical x; one launch and one drain / fill of the GPU less per sweep, which is what
+// an 8-GPU strip of ~70 us per sweep is short of), off for the single-GPU per-phase kernels.
+static int fused_end_env() {
+    static int env = -2;
+    if (env == -2) {
         const char *e = getenv("GSB_FUSED_END");
-        env = e ? atoi(e) : 0; // opt-in until it has been measured
+        env = e ? atoi(e) : -1;
     }
-    return env == 1;
+    return env;
 }
+bool gsb_fused_end_enabled() { return fused_end_env() == 1; }
+bool gsb_fused_end_enabled_strips() { return fused_end_env() != 0; }
 bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs) {
     const int eff = gsb_plan_effective_kernel(p, nrhs);
     const char *e = getenv("GSB_RING_STAGES"); // fused-end variants are built for the default stage count only

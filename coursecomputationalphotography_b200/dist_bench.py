@@ -66,47 +66,62 @@ def run(args, pkg, wl, dist, rank, world, local):
     e2e = None
     if not args.no_e2e:
         from bench import pinned_like
-        full = pkg.SparseMatrix(np.float64)   # untimed: stands for the reference's Eigen A^T*A step
-        full.poisson(W, H)
-        va, ci, rb, rn, _ = full.layout()
-        r0, r1 = y0 * W, y1 * W
-        k0, k1 = int(rb[r0]), int(rb[r1 - 1] + rn[r1 - 1])
-        ro_s = np.zeros(n_local + 1, np.int32)
-        ro_s[1:] = np.cumsum(rn[r0:r1])
-        assert ro_s[-1] == k1 - k0  # compressed layout: the strip's entries are one contiguous span
-        va_s, ci_s, ro_s = pinned_like(pkg, va[k0:k1]), pinned_like(pkg, ci[k0:k1]), pinned_like(pkg, ro_s)
-        del full, va, ci, rb, rn
-        torch.cuda.empty_cache()
-        bh = torch.from_numpy(b_host).pin_memory()
-        xh = torch.empty_like(bh).pin_memory()
-        steps_e2e = max(1, args.e2e_steps)
-        per_step = []
-        for it in range(steps_e2e + 1):
-            dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            solver.matrix_rows(va_s, ro_s, ci_s, r0, n, W)
-            bd = bh.to(dev, non_blocking=True)
-            torch.cuda.synchronize()
-            xd = torch.empty_like(bd)
-            solver.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, args.sweeps, opts)
-            xh.copy_(xd)
-            torch.cuda.synchronize()
-            dist.barrier()
-            if it > 0:
-                per_step.append(time.perf_counter() - t0)
-        tt = torch.tensor(per_step, device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)  # per step: the slowest rank
-        per = [float(v) for v in tt]
-        h2d = torch.tensor([float(va_s.nbytes + ci_s.nbytes + ro_s.nbytes + b_host.nbytes)], device=dev, dtype=torch.float64)
-        dist.all_reduce(h2d)
-        e2e = {"value": nnz * ch * args.sweeps * steps_e2e / sum(per) / 1e9, "unit": "Gnnz/s",
-               "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(b_host.nbytes) * world,
-               "ms_per_step": sum(per) / steps_e2e * 1e3, "ms_per_step_min": min(per) * 1e3,
-               "ms_per_step_median": float(np.median(per)) * 1e3, "steps": steps_e2e,
-               "includes": "host CSR import of every rank's rows (H2D) + ordering + halo setup + b H2D + sweeps + x D2H "
-                           "(all ranks, slowest rank per step)", "host_memory": "pinned"}
-        assert torch.equal(xd, x_dev), "e2e result differs from the resident-input result"
+        # everything that can fail locally comes BEFORE the leg's first collective; the ranks then agree (min) on
+        # whether to run it, so that a failure on one rank cannot leave the others waiting in a barrier
+        prep, err = None, None
+        try:
+            full = pkg.SparseMatrix(np.float64)   # untimed: stands for the reference's Eigen A^T*A step
+            full.poisson(W, H)
+            va, ci, rb, rn, _ = full.layout()
+            r0, r1 = y0 * W, y1 * W
+            ro_s = np.zeros(n_local + 1, np.int32)
+            ro_s[1:] = np.cumsum(rn[r0:r1])
+            k0 = int(rb[r0])
+            k1 = k0 + int(ro_s[-1])  # compressed layout: the strip's entries are one contiguous span
+            prep = (pinned_like(pkg, va[k0:k1]), pinned_like(pkg, ci[k0:k1]), pinned_like(pkg, ro_s), r0)
+            del full, va, ci, rb, rn
+            torch.cuda.empty_cache()
+        except Exception as e:
+            err = repr(e)[:300]
+        ok = torch.tensor([1 if prep is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            e2e = {"error": err or "another rank could not prepare the host CSR"}
+        else:
+            va_s, ci_s, ro_s, r0 = prep
+            bh = torch.from_numpy(b_host).pin_memory()
+            xh = torch.empty_like(bh).pin_memory()
+            steps_e2e = max(1, args.e2e_steps)
+            per_step = []
+            for it in range(steps_e2e + 1):
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                solver.matrix_rows(va_s, ro_s, ci_s, r0, n, W)
+                bd = bh.to(dev, non_blocking=True)
+                torch.cuda.synchronize()
+                xd = torch.empty_like(bd)
+                solver.gauss_seidel_dev(bd.data_ptr(), xd.data_ptr(), ch, 0.0, args.sweeps, opts)
+                xh.copy_(xd)
+                torch.cuda.synchronize()
+                dist.barrier()
+                if it > 0:
+                    per_step.append(time.perf_counter() - t0)
+            tt = torch.tensor(per_step, device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)  # per step: the slowest rank
+            per = [float(v) for v in tt]
+            h2d = torch.tensor([float(va_s.nbytes + ci_s.nbytes + ro_s.nbytes + b_host.nbytes)], device=dev, dtype=torch.float64)
+            dist.all_reduce(h2d)
+            same = torch.tensor([1 if torch.equal(xd, x_dev) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            e2e = {"value": nnz * ch * args.sweeps * steps_e2e / sum(per) / 1e9, "unit": "Gnnz/s",
+                   "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(b_host.nbytes) * world,
+                   "ms_per_step": sum(per) / steps_e2e * 1e3, "ms_per_step_min": min(per) * 1e3,
+                   "ms_per_step_median": float(np.median(per)) * 1e3, "steps": steps_e2e,
+                   "per_step_ms": [round(v * 1e3, 2) for v in per],
+                   "includes": "host CSR import of every rank's rows (H2D) + ordering + halo setup + b H2D + sweeps + x D2H "
+                               "(all ranks, slowest rank per step)", "host_memory": "pinned",
+                   "equals_resident_input_result": bool(int(same[0]))}
 
     parity = parity_vs_one_gpu(args, pkg, wl, dist, torch, solver, b_dev, rank, world, dev, W, H, ch, n_local, opts)
 

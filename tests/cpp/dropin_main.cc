@@ -2,6 +2,7 @@
 // drop-in header: 3x5 fixture + the five insert cases checked against a dense mirror, manhattonDist,
 // the 4x4 Gauss-Seidel / CG known answer, then a small Poisson import + multi-RHS solve.
 // Exit code 0 = all checks passed.  Needs a GPU (libgsb200 has no CPU path).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -65,23 +66,37 @@ static int multi_device_check(int ndev) {
     REQUIRE(SparseMatrix<double>::lastStatus() == GSB_OK, "import of the masked system");
     REQUIRE(gsb_matrix_analyze(sp.device_handle(), GSB_ORDER_USER, colors.data()) == GSB_OK, "parity colouring");
     REQUIRE(SparseMatrix<double>::setDevices({}), "setDevices({})");
-    auto x1 = sp.gaussSeidelMulti(b, 3, 1e-3, 400);
-    const int sweeps1 = sp.last_stats.sweeps, kernel1 = sp.last_stats.kernel_used;
-    REQUIRE(kernel1 < 10 && sweeps1 > 10 && sweeps1 < 400, "single-device solve of the masked system");
+    auto x1 = sp.gaussSeidelMulti(b, 3, 0.0, 40);
+    REQUIRE(sp.last_stats.kernel_used < 10 && sp.last_stats.sweeps == 40, "single-device solve of the masked system");
+    // a real epsilon: a right-hand side whose solution is close to the start vector (the reference's loop only runs
+    // while the update norm is below its initial eps = 10, v2 :354-356); threshold = 1.5 x the update norm of sweep 40
+    std::vector<double> ones((size_t)n, 1.0), a1((size_t)n, 0.0), bs(b.size());
+    sp.applyToVector(ones, a1);
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < n; ++i) bs[(size_t)r * n + i] = a1[i] + 1e-7 * b[(size_t)r * n + i];
+    sp.gaussSeidelMulti(bs, 3, 0.0, 40);
+    double eps = 0;
+    for (int r = 0; r < 3; ++r) eps = std::max(eps, 1.5 * sp.last_stats.last_eps[r]);
+    REQUIRE(eps > 0 && eps < 10, "threshold below the reference's initial eps");
+    auto xs1 = sp.gaussSeidelMulti(bs, 3, eps, 500);
+    const int sweeps1 = sp.last_stats.sweeps;
+    REQUIRE(sweeps1 > 5 && sweeps1 <= 40, "stop rule on one device");
     std::vector<int> devs;
     for (int d = 0; d < ndev; ++d) devs.push_back(d);
     REQUIRE(gsb_set_devices(devs.data(), ndev) == GSB_OK, "gsb_set_devices");
-    auto xn = sp.gaussSeidelMulti(b, 3, 1e-3, 400);
+    auto xn = sp.gaussSeidelMulti(b, 3, 0.0, 40);
     REQUIRE(SparseMatrix<double>::lastStatus() == GSB_OK, "multi-device solve");
     REQUIRE(sp.last_stats.kernel_used >= 30, "the solve ran on row strips (fused halo + stop-rule exchange)");
-    REQUIRE(sp.last_stats.sweeps == sweeps1, "same stop sweep on 1 and N devices");
     REQUIRE(std::memcmp(x1.data(), xn.data(), sizeof(double) * x1.size()) == 0, "N-device solution == 1-device solution, bit for bit");
-    // the reference signature (one right-hand side, defaults) takes the same path
+    auto xsn = sp.gaussSeidelMulti(bs, 3, eps, 500);
+    REQUIRE(sp.last_stats.sweeps == sweeps1, "same stop sweep on 1 and N devices");
+    REQUIRE(std::memcmp(xs1.data(), xsn.data(), sizeof(double) * xs1.size()) == 0, "stopped solve: N devices == 1 device");
+    // the reference signature (one right-hand side) takes the same path
     std::vector<double> b0(b.begin(), b.begin() + n);
-    auto xa = sp.gaussSeidel(b0, 1e-3, 400);
+    auto xa = sp.gaussSeidel(b0, 0.0, 25);
     REQUIRE(sp.last_stats.kernel_used >= 30, "gaussSeidel(b) on row strips");
     SparseMatrix<double>::setDevices({});
-    auto xb = sp.gaussSeidel(b0, 1e-3, 400);
+    auto xb = sp.gaussSeidel(b0, 0.0, 25);
     REQUIRE(std::memcmp(xa.data(), xb.data(), sizeof(double) * xa.size()) == 0, "gaussSeidel(b): N devices == 1 device");
     std::printf("dropin multi-device ok: masked %dx%d (n = %d), %d devices == 1 device bit for bit, %d sweeps\n", W, H, n,
                 ndev, sweeps1);

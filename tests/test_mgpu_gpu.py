@@ -57,15 +57,26 @@ def test_host_api_shards_imported_csr(gsb, ndev):
     sp.analyze(gsb._lib.ORDER_USER, colors)
     try:
         strips.set_devices([])
-        x1 = sp.gaussSeidel(b, epsilon=1e-3, max_iteration=3000)
+        x1 = sp.gaussSeidel(b, epsilon=0.0, max_iteration=40)
+        assert sp.last_stats.kernel_used < 10 and sp.last_stats.sweeps == 40
+        # a real epsilon: a right-hand side whose solution is close to the start vector (the reference's loop only
+        # runs while the update norm is below its initial eps = 10, v2 :354-356), stop threshold = 1.5 x the update
+        # norm of sweep 40 -> the solve must stop at that sweep or a little earlier, on one device and on N alike
+        bs = sp.applyToVector(np.ones(n))[None, :] + 1e-7 * b
+        sp.gaussSeidel(bs, epsilon=0.0, max_iteration=40)
+        eps = 1.5 * max(list(sp.last_stats.last_eps)[:3])
+        assert 0.0 < eps < 10.0
+        xs1 = sp.gaussSeidel(bs, epsilon=eps, max_iteration=500)
         s1 = sp.last_stats.sweeps
-        assert sp.last_stats.kernel_used < 10 and 10 < s1 < 3000
+        assert 5 < s1 <= 40
         strips.set_devices(list(range(ndev)))
         assert strips.get_devices() == list(range(ndev))
         for rep in range(2):
-            xn = sp.gaussSeidel(b, epsilon=1e-3, max_iteration=3000)
-            assert sp.last_stats.kernel_used >= 30 and sp.last_stats.sweeps == s1
+            xn = sp.gaussSeidel(b, epsilon=0.0, max_iteration=40)
+            assert sp.last_stats.kernel_used >= 30 and sp.last_stats.sweeps == 40
             assert np.array_equal(xn, x1), "masked system: %d devices differ from one (rep %d)" % (ndev, rep)
+        xsn = sp.gaussSeidel(bs, epsilon=eps, max_iteration=500)
+        assert sp.last_stats.sweeps == s1 and np.array_equal(xsn, xs1)
         # the full grid, imported as Eigen would hand it over
         Wg, Hg = 640, 512
         fg = gsb.SparseMatrix(np.float64)
