@@ -93,9 +93,12 @@ def test_host_api_shards_imported_csr(gsb, ndev):
         assert np.array_equal(xn, imp.gaussSeidel(bg, epsilon=0.0, max_iteration=12))
         # a matrix that needs more than two colours does not shard: it runs on one device
         strips.set_devices(list(range(ndev)))
-        r, c, v, b2, _ = wl.diag_dominant_system(400_000, 4, seed=3)
+        nm = 100_000 * ndev
+        rr, cc, vv = wl.random_spd_coo(nm, 6, seed=3)  # ~13 entries per row, random coupling: needs > 2 colours
         mc = gsb.SparseMatrix(np.float64)
-        mc.initializeFromVector(r, c, v)
+        mc.initialize(nm, nm)
+        mc.initializeFromTriplets(rr, cc, vv)
+        b2 = np.random.default_rng(2).standard_normal(nm)
         xm = mc.gaussSeidel(b2, epsilon=0.0, max_iteration=5)
         assert mc.last_stats.kernel_used < 10 and mc.last_stats.n_colors > 2
         strips.set_devices([])
