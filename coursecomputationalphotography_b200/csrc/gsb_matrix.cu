@@ -112,9 +112,15 @@ __global__ void __launch_bounds__(256) check_coloring(const int *__restrict__ co
 }
 
 // ---------------------------------------------------------------------------------------------
-// greedy multicolour: Jones-Plassmann rounds on hashed priorities, first-fit colour choice,
-// speculative (a row only sees its own entries, so a structurally unsymmetric pattern can
-// produce a clash) followed by a repair pass that un-colours the row that sees the clash.
+// greedy multicolour: Jones-Plassmann rounds on hashed priorities, first-fit colour choice, on the SYMMETRISED
+// pattern: rows i and j conflict when a_ij OR a_ji is stored (either makes one of them read the other inside a
+// colour phase).  A row's own entries are its out-neighbours; the rows that read it (in-neighbours) come from a
+// transposed adjacency built once per analysis (histogram -> scan -> scatter).  With both directions visible two
+// adjacent uncoloured rows never colour themselves in the same round -- the lower priority waits -- so the result
+// is a proper colouring by construction and the rounds terminate in O(log n).
+//   (Round 1 coloured speculatively on the rows' own entries and repaired clashes afterwards.  On structurally
+//    unsymmetric patterns the repairs chase each other: a re-coloured row clashes with a row that reads it, which
+//    re-colours, ...  -- a livelock that ran into the round cap on a 400 000-row matrix, found in round 2.)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned prio_hash(unsigned x) {
     x ^= x >> 16;
@@ -130,9 +136,35 @@ __device__ __forceinline__ bool prio_greater(int a, int b) { // does a outrank b
     return ha > hb || (ha == hb && a > b);
 }
 
+// transposed adjacency: in_cnt[j] = number of rows i != j that store column j
+__global__ void __launch_bounds__(256) jp_count_in(const int *__restrict__ cols, const int *__restrict__ row_begin,
+                                                   const int *__restrict__ row_nnz, int n_rows, int *__restrict__ in_cnt) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rows) return;
+    int b = row_begin[i], len = row_nnz[i];
+    for (int k = 0; k < len; ++k) {
+        int j = cols[b + k];
+        if (j != i) atomicAdd(&in_cnt[j], 1);
+    }
+}
+// (the order inside a row's in-list depends on the atomics; the colouring only uses the list as a set)
+__global__ void __launch_bounds__(256) jp_fill_in(const int *__restrict__ cols, const int *__restrict__ row_begin,
+                                                  const int *__restrict__ row_nnz, int n_rows,
+                                                  const int *__restrict__ in_ptr, int *__restrict__ cursor,
+                                                  int *__restrict__ in_idx) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rows) return;
+    int b = row_begin[i], len = row_nnz[i];
+    for (int k = 0; k < len; ++k) {
+        int j = cols[b + k];
+        if (j != i) in_idx[in_ptr[j] + atomicAdd(&cursor[j], 1)] = i;
+    }
+}
+
 // counters[0] = rows still uncoloured after this round, counters[1] |= 1 if > MAX_COLORS needed
 __global__ void __launch_bounds__(256) jp_round(const int *__restrict__ cols, const int *__restrict__ row_begin,
-                                                const int *__restrict__ row_nnz, int n_rows,
+                                                const int *__restrict__ row_nnz, const int *__restrict__ in_ptr,
+                                                const int *__restrict__ in_idx, int n_rows,
                                                 const int *__restrict__ cin, int *__restrict__ cout,
                                                 int *__restrict__ counters) {
     int i = blockIdx.x * 256 + threadIdx.x;
@@ -142,22 +174,20 @@ __global__ void __launch_bounds__(256) jp_round(const int *__restrict__ cols, co
         cout[i] = cur;
         return;
     }
-    int b = row_begin[i], len = row_nnz[i];
     unsigned long long forbidden = 0ull;
     bool is_max = true;
-    for (int k = 0; k < len; ++k) {
-        int j = cols[b + k];
-        if (j == i) continue;
+    auto visit = [&](int j) {
+        if (j == i) return;
         int cj = cin[j];
         if (cj < 0) {
-            if (prio_greater(j, i)) {
-                is_max = false;
-                break;
-            }
+            if (prio_greater(j, i)) is_max = false;
         } else {
             forbidden |= 1ull << cj;
         }
-    }
+    };
+    const int b = row_begin[i], len = row_nnz[i];
+    for (int k = 0; k < len && is_max; ++k) visit(cols[b + k]);
+    for (int k = in_ptr[i]; k < in_ptr[i + 1] && is_max; ++k) visit(in_idx[k]);
     if (!is_max) {
         cout[i] = -1;
         atomicAdd(&counters[0], 1);
@@ -169,37 +199,6 @@ __global__ void __launch_bounds__(256) jp_round(const int *__restrict__ cols, co
         return;
     }
     cout[i] = __ffsll((long long)~forbidden) - 1;
-}
-
-// A row that sees one of its own entries carrying its colour must yield (it is the only one that
-// is guaranteed to see the clash).  With a structurally symmetric pattern this never fires.
-__global__ void __launch_bounds__(256) jp_repair(const int *__restrict__ cols, const int *__restrict__ row_begin,
-                                                 const int *__restrict__ row_nnz, int n_rows,
-                                                 const int *__restrict__ ccur, unsigned char *__restrict__ marks,
-                                                 int *__restrict__ counters) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_rows) return;
-    int c = ccur[i];
-    bool clash = false;
-    if (c >= 0) {
-        int b = row_begin[i], len = row_nnz[i];
-        for (int k = 0; k < len; ++k) {
-            int j = cols[b + k];
-            if (j != i && ccur[j] == c) clash = true;
-        }
-    }
-    marks[i] = clash ? 1 : 0;
-    if (clash) counters[2] = 1; // benign race: every writer writes 1
-}
-
-__global__ void __launch_bounds__(256) jp_unmark(int n_rows, const unsigned char *__restrict__ marks,
-                                                 int *__restrict__ ccur, int *__restrict__ counters) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_rows) return;
-    if (marks[i]) {
-        ccur[i] = -1;
-        atomicAdd(&counters[0], 1);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -351,28 +350,33 @@ static int try_redblack(gsb_matrix *m, int maxoff, int *bad_dev, cudaStream_t st
 static int run_multicolor(gsb_matrix *m, cudaStream_t st) {
     const int n = m->n_rows;
     const int nb = (n + 255) / 256;
-    DevBuf<int> other, counters;
-    DevBuf<unsigned char> marks;
+    DevBuf<int> other, counters, in_ptr, in_idx, cursor;
     GSB_TRY(other.alloc(n));
-    GSB_TRY(marks.alloc(n));
     GSB_TRY(counters.alloc(4));
+    // transposed adjacency of the stored pattern
+    GSB_TRY(in_ptr.alloc((int64_t)n + 1));
+    GSB_TRY(cursor.alloc(n));
+    GSB_CUDA(cudaMemsetAsync(in_ptr.p, 0, sizeof(int) * (size_t)(n + 1), st));
+    GSB_CUDA(cudaMemsetAsync(cursor.p, 0, sizeof(int) * (size_t)n, st));
+    jp_count_in<<<nb, 256, 0, st>>>(m->cols.p, m->row_begin.p, m->row_nnz.p, n, in_ptr.p);
+    GSB_KERNEL_CHECK();
+    GSB_TRY(gsb_exclusive_scan_i32(in_ptr.p, in_ptr.p, (int64_t)n + 1, nullptr, st));
+    int n_in = 0;
+    GSB_CUDA(cudaMemcpyAsync(&n_in, in_ptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    GSB_TRY(in_idx.alloc(n_in));
+    jp_fill_in<<<nb, 256, 0, st>>>(m->cols.p, m->row_begin.p, m->row_nnz.p, n, in_ptr.p, cursor.p, in_idx.p);
+    GSB_KERNEL_CHECK();
     GSB_CUDA(cudaMemsetAsync(m->colors.p, 0xff, sizeof(int) * (size_t)n, st)); // all -1
     int *cin = m->colors.p, *cout = other.p;
-    int h[4];
-    for (int round = 0; round < 100000; ++round) {
+    int h[4] = {1, 0, 0, 0};
+    int round = 0;
+    for (; round < 4096 && h[0] != 0; ++round) {
         GSB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(int), st));
-        jp_round<<<nb, 256, 0, st>>>(m->cols.p, m->row_begin.p, m->row_nnz.p, n, cin, cout, counters.p);
-        GSB_KERNEL_CHECK();
-        jp_repair<<<nb, 256, 0, st>>>(m->cols.p, m->row_begin.p, m->row_nnz.p, n, cout, marks.p, counters.p);
+        jp_round<<<nb, 256, 0, st>>>(m->cols.p, m->row_begin.p, m->row_nnz.p, in_ptr.p, in_idx.p, n, cin, cout, counters.p);
         GSB_KERNEL_CHECK();
         GSB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
         GSB_CUDA(cudaStreamSynchronize(st));
-        if (h[2]) { // clashes were marked: turn them back into uncoloured rows
-            jp_unmark<<<nb, 256, 0, st>>>(n, marks.p, cout, counters.p);
-            GSB_KERNEL_CHECK();
-            GSB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-            GSB_CUDA(cudaStreamSynchronize(st));
-        }
         if (h[1]) {
             gsb_set_error("multicolour ordering needs more than %d colours (row degree too high)", MAX_COLORS);
             return GSB_ERR_COLORING;
@@ -380,7 +384,10 @@ static int run_multicolor(gsb_matrix *m, cudaStream_t st) {
         int *t = cin;
         cin = cout;
         cout = t;
-        if (h[0] == 0) break;
+    }
+    if (h[0] != 0) { // cannot happen: every round colours at least the highest-priority uncoloured row
+        gsb_set_error("internal: multicolour ordering did not finish in %d rounds (%d rows left)", round, h[0]);
+        return GSB_ERR_COLORING;
     }
     if (cin != m->colors.p)
         GSB_CUDA(cudaMemcpyAsync(m->colors.p, cin, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
