@@ -1081,11 +1081,8 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
         }
         const bool win = eff == 4;
         const int stage_bytes = ring_layout(p->cap, NRHS, check, win ? p->wcap : 0).stage_bytes;
-        int stages = env_stages ? env_stages : GS_RING_STAGES_DEFAULT;
-        if (stages < 2) stages = 2;
-        if (stages > GS_RING_STAGES_MAX) stages = GS_RING_STAGES_MAX;
-        while (stages > 2 && 64 + stages * stage_bytes > 220 * 1024) --stages;
-        if (end.enabled) stages = GS_RING_STAGES_DEFAULT;
+        const int stages = GS_RING_STAGES_DEFAULT;
+        (void)env_stages;
         const int smem = 64 + stages * stage_bytes;
         const int *tk = p->tile_k.p + p->tile_off[c];
         // window descriptors: kernel 4 stages the windows; kernel 3 can use them as L2 prefetch hints (GSB_X_PREFETCH=1|2)
@@ -1102,15 +1099,16 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
                                 const GsbHaloArgs, const GsbEndArgs);
 #define GSB_RING_PICK(ST, WN, HL, FE) \
     (check ? (ring_fn)gs_phase_ring<NRHS, true, ST, WN, HL, FE> : (ring_fn)gs_phase_ring<NRHS, false, ST, WN, HL, FE>)
-#define GSB_RING_PICK_ST(WN, HL, FE) \
-    (stages == 2 ? GSB_RING_PICK(2, WN, HL, FE) : stages == 3 ? GSB_RING_PICK(3, WN, HL, FE) : GSB_RING_PICK(4, WN, HL, FE))
+        // (3- and 4-stage rings were measured in round 1 and never won: only the 2-stage variants are instantiated;
+        // the fused end is never combined with the window kernel -- gsb_plan_can_fuse_end)
+#define GSB_RING_PICK_ST(WN, HL, FE) GSB_RING_PICK(2, WN, HL, FE)
         // the fused-end variants exist for the default stage count only (gsb_plan_can_fuse_end checks it)
 #define GSB_RING_PICK_FE(WN, HL) (end.enabled ? GSB_RING_PICK(2, WN, HL, true) : GSB_RING_PICK_ST(WN, HL, false))
         ring_fn kern = nullptr;
         if (halo.enabled)
-            kern = win ? GSB_RING_PICK_FE(true, true) : GSB_RING_PICK_FE(false, true);
+            kern = win ? GSB_RING_PICK_ST(true, true, false) : GSB_RING_PICK_FE(false, true);
         else
-            kern = win ? GSB_RING_PICK_FE(true, false) : GSB_RING_PICK_FE(false, false);
+            kern = win ? GSB_RING_PICK_ST(true, false, false) : GSB_RING_PICK_FE(false, false);
 #undef GSB_RING_PICK_FE
 #undef GSB_RING_PICK_ST
 #undef GSB_RING_PICK

@@ -183,6 +183,16 @@ def masked_poisson_system(mask, guide, target):
     return ro, ci, va, b, (ys * W + xs), colors
 
 
+def c3_masked_system(size=4096, channels=3):
+    """BASELINE configs[2]'s converged-parity system: the Dirichlet-masked blend on a size x size frame,
+    blob mask 30 %, thickness <= 48 px, guide = the synthetic two-exposure image, target = the same scene rotated.
+    One definition for the golden generator (tests/golden/make_golden_c3.py), the tests and both bench arms."""
+    mask = blob_mask(size, size, 0.30, 48, seed=11)
+    guide = synth_image(size, size, channels, seed=7)
+    target = np.ascontiguousarray(guide[:, ::-1, ::-1])
+    return masked_poisson_system(mask, guide, target)
+
+
 # ---- C5: random sparse SPD -----------------------------------------------------------------------
 def random_spd_system(n=1_000_000, pairs_per_row=13, seed=5):
     """~2*pairs_per_row+1 nnz/row: symmetric random pattern, off-diagonals U(-1,0), diagonal = sum|off| + 1.

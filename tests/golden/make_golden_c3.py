@@ -31,10 +31,7 @@ N_SAMPLE = 65536
 
 def c3_system(size, channels=3):
     """The system bench.py's time-to-tolerance leg and tests/ solve (same generator, same seeds)."""
-    mask = wl.blob_mask(size, size, 0.30, 48, seed=11)
-    guide = wl.synth_image(size, size, channels, seed=7)
-    target = np.ascontiguousarray(guide[:, ::-1, ::-1])
-    return wl.masked_poisson_system(mask, guide, target)
+    return wl.c3_masked_system(size, channels)
 
 
 def sample_index(n):

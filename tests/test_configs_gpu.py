@@ -97,6 +97,49 @@ def test_config4_random_spd_multicolor(gsb, oracle_mod):
     assert np.array_equal(sp.applyToVector(x), on.spmv(x))  # SpMV in storage order is bit-exact
 
 
+def test_config4_random_spd_1e6_triplets_vs_oracle(gsb, oracle_mod):
+    """"CPU oracle on n = 1e6 of the same family".  The full-size path (unsorted triplets -> device radix
+    sort -> slack CSR -> Jones-Plassmann -> sweeps, bench.py's c5 leg) at n = 1e6: the assembled layout equals the
+    oracle's import of the host-sorted CSR, three sweeps are bit-exact against the oracle on P A P^T, and the converged
+    solution matches the oracle's natural-order solve."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    n = 1_000_000
+    rows, cols, vals = wl.random_spd_coo(n, 13, seed=5)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.initialize(n, n)
+    sp.initializeFromTriplets(rows, cols, vals)
+    # host CSR of the same triplets (last duplicate wins, as the insert loop of v2 :256-263 would leave it)
+    key = rows.astype(np.int64) * n + cols
+    order = np.argsort(key, kind="stable")
+    ks, vs = key[order], vals[order]
+    last = np.ones(ks.size, bool)
+    last[:-1] = ks[1:] != ks[:-1]
+    ks, vs = ks[last], vs[last]
+    r, c = (ks // n).astype(np.int32), (ks % n).astype(np.int32)
+    ro, ci, va = wl.coo_to_csr(r, c, vs, n)
+    gv, gc, gb, gn, gl = sp.layout()
+    assert sp._nnz == len(va) and np.array_equal(gn, np.diff(ro)) and np.array_equal(gb, ro[:-1])
+    assert np.array_equal(gc, ci) and np.array_equal(gv, va) and not gl.any()
+    rng = np.random.default_rng(1)
+    xstar = rng.uniform(-1.0, 1.0, n)
+    on = oracle_from_csr(oracle_mod, ro, ci, va)
+    b = on.spmv(xstar)
+    assert np.array_equal(sp.applyToVector(xstar), b)
+    x3 = sp.gaussSeidel(b, epsilon=0.0, max_iteration=3)
+    perm, colors = sp.ordering()
+    assert not np.any(colors[r[r != c]] == colors[c[r != c]])
+    o = oracle_from_csr(oracle_mod, *permuted_csr(ro, ci, va, perm))
+    xp, _, _ = o.gauss_seidel(b[perm], 0.0, 3)
+    xo = np.empty_like(xp)
+    xo[perm] = xp
+    assert np.array_equal(x3, xo)
+    x = sp.gaussSeidel(b, epsilon=1e-8, max_iteration=1000)
+    xn, sw, _ = on.gauss_seidel(b, 1e-8, 1000)
+    print("C5 1e6: %d colours, gpu %d sweeps cpu %d sweeps, max-abs vs cpu %.2e" %
+          (sp.last_stats.n_colors, sp.last_stats.sweeps, sw, np.abs(x - xn).max()))
+    assert np.abs(x - xn).max() <= 1e-8 and np.abs(x - xstar).max() <= 1e-8
+
+
 def test_config4_scale_2e6_residual(gsb):
     """Larger instance of the same family (2e6 rows, ~54e6 nnz): no oracle run, size-independent checks."""
     from coursecomputationalphotography_b200 import workloads as wl
