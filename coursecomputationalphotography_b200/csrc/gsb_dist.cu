@@ -1264,7 +1264,7 @@ extern "C" int gsb_dist_gauss_seidel_dev(gsb_dist *d, const double *b_dev, int n
             trace_mark(); // 4 marks per sweep: start, after phase 0, after phase 1, after the end-of-sweep step
             const bool check = (sweep_no % opts.check_every) == 0 || sweep_no == max_iteration;
             int poff = 0;
-            // default for strips (GSB_FUSED_END=0 turns it off): the second colour phase ends the sweep itself -- fold, peer exchange, decision
+            // opt-in (GSB_FUSED_END=1; measured slower at N = 8): the second colour phase ends the sweep itself -- fold, peer exchange, decision
             // (GsbEndArgs); needs the fused stop-rule exchange on checked sweeps and both colours non-empty
             const bool fuse_end = use_peer && fused_eps && gsb_fused_end_enabled_strips() &&
                                   gsb_plan_can_fuse_end(&d->plan, nrhs) && d->color_start[1] > d->color_start[0] &&

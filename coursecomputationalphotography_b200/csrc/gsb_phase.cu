@@ -864,9 +864,11 @@ int gsb_plan_effective_kernel(const GsbPlan *p, int nrhs) {
     return nrhs >= 2 ? 3 : 4;
 }
 
-// GSB_FUSED_END: 1 = on everywhere it applies, 0 = off; unset = on for the strip solver (measured on B200, N = 2:
-// 1086 against 1057 Gnnz/s, bit-identical x; one launch and one drain / fill of the GPU less per sweep, which is what
-// an 8-GPU strip of ~70 us per sweep is short of), off for the single-GPU per-phase kernels.
+// GSB_FUSED_END=1: the last CTA of the sweep's last colour phase ends the sweep itself (GsbEndArgs) instead of a
+// kernel of its own.  Opt-in.  Measured on B200 (profiles/README.md, round 2): N = 2 strips +2.7 % (1086 against 1057
+// Gnnz/s), N = 8 strips -14 % (2886 against 3344) -- with eight ranks the peer round trip of the stop-rule exchange
+// then sits at the tail of a kernel whose CTAs have all retired, whereas the separate kernel is launched
+// dependently (PDL) and overlaps the drain.  x is bit-identical either way.
 static int fused_end_env() {
     static int env = -2;
     if (env == -2) {
@@ -876,7 +878,7 @@ static int fused_end_env() {
     return env;
 }
 bool gsb_fused_end_enabled() { return fused_end_env() == 1; }
-bool gsb_fused_end_enabled_strips() { return fused_end_env() != 0; }
+bool gsb_fused_end_enabled_strips() { return fused_end_env() == 1; }
 bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs) {
     const int eff = gsb_plan_effective_kernel(p, nrhs);
     const char *e = getenv("GSB_RING_STAGES"); // fused-end variants are built for the default stage count only

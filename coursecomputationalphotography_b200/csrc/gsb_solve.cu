@@ -335,7 +335,7 @@ int gsb_gs_solve_device_x0(gsb_matrix *m, const double *b_dev, const double *x0_
 // device, from this one blocking call (gsb_dist_init_local: worker thread per device, peer-memory halo).  *took = 0
 // when the matrix does not shard that way (more than two colours, fewer rows than GS_MGPU_MIN_ROWS per device): the
 // caller then runs the single-device path.
-#define GS_MGPU_MIN_ROWS 65536
+#define GS_MGPU_MIN_ROWS 32768
 static int gs_host_multi(gsb_matrix *m, const double *b, int nrhs, double epsilon, int max_iteration,
                          const gsb_gs_options *opts_in, double *x_out, gsb_gs_stats *stats, int *took) {
     *took = 0;
