@@ -501,7 +501,7 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     return GSB_OK;
 }
 
-#define GS_FUSED_L2HINT_DEFAULT 0
+#define GS_FUSED_L2HINT_DEFAULT 3 // measured (r02_call9): 0 -> 0.836, 1 -> 0.848, 3 -> 0.855, 7 -> 0.856 of peak
 #define GS_FUSED_LEAD_DEFAULT 128 // beyond the dependency distance: long enough for the dependencies of a tile to be
                                   // finished when it comes up, short enough for the reuse to stay in L2 (measured)
 #define GS_FUSED_PUBK_DEFAULT 1 // measured: batching delays availability by a whole item of the owning CTA (-13 %)

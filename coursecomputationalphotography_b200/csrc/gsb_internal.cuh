@@ -153,6 +153,7 @@ struct gsb_matrix {
     DevBuf<double> stage_b, stage_x; // natural-order device copies of host b / x for the host-pointer entry points
     DevBuf<double> partials;   // per-block partial sums of the stop rule
     DevBuf<unsigned char> ctl; // GsCtl
+    DevBuf<unsigned> small_bar; // kernel 6: grid-barrier counter + generation
     void *ctl_host = nullptr;  // pinned mirror
     // cached CUDA graph of one batch
     void *graph_exec = nullptr;
@@ -299,6 +300,11 @@ bool gsb_plan_can_fuse_end(const GsbPlan *p, int nrhs); // the effective kernel 
 int gsb_plan_launch(const GsbPlan *p, int c, const int *rp, const int *ci, const double *va, const double *dg,
                     const double *b, double *x, int64_t ld, int nrhs, bool check, const GsCtl *ctl, double *partials,
                     cudaStream_t st, const GsbHaloArgs *halo = nullptr, const GsbEndArgs *end = nullptr);
+// kernel 6 (gsb_small.cu): small systems, up to `max_sweeps` sweeps incl. the stop rule in one persistent launch
+bool gsb_small_auto(int64_t n_rows, int n_colors, int check_every);
+int gsb_launch_small_persistent(const int *rp, const int *ci, const double *va, const double *dg, const double *b, double *x,
+                                int64_t ld, int nrhs, const int *color_start, int n_colors, GsCtl *ctl, double *partials,
+                                unsigned *bar, int max_sweeps, cudaStream_t st, int *slots);
 // end of sweep.  mode 0: fold partials, bump the counter, decide (single GPU)
 //                mode 1: fold partials into ctl->eps_last only (strip solver, before the all-reduce)
 //                mode 2: bump the counter and decide from ctl->eps_last (after the all-reduce)

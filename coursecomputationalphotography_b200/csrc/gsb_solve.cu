@@ -198,6 +198,18 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     }
     bool use_graph = opts.use_graph == 1 || (opts.use_graph == -1 && n * (int64_t)m->n_colors < (int64_t)1 << 20);
     if (opts.check_every != 1) use_graph = false; // keep the captured batch simple: one sweep shape
+    // small systems: the whole solve in one persistent launch (kernel 6) instead of ~(colours + 1) graph nodes per sweep
+    const bool use_small = (opts.kernel == 6 || (opts.kernel == 0 && opts.use_graph == -1)) &&
+                           gsb_small_auto(n, m->n_colors, opts.check_every);
+    if (opts.kernel == 6 && !use_small) {
+        gsb_set_error("kernel 6 (persistent small-system kernel) needs check_every = 1 and at most 64 colours");
+        return GSB_ERR_ARG;
+    }
+    if (use_small) {
+        use_graph = false;
+        if (!m->small_bar.p) GSB_TRY(m->small_bar.alloc(2));
+        GSB_CUDA(cudaMemsetAsync(m->small_bar.p, 0, 2 * sizeof(unsigned), st)); // (a solve that gave up may have left it mid-count)
+    }
 
     cudaEvent_t ev0, ev1;
     GSB_CUDA(cudaEventCreate(&ev0));
@@ -209,7 +221,14 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         int todo = max_iteration - issued;
         if (todo > batch) todo = batch;
         if (todo <= 0) todo = 1; // cannot happen (done would be set) -- guards an endless loop
-        if (use_graph) {
+        if (use_small) {
+            int slots = 0;
+            status = gsb_launch_small_persistent(m->rp.p, m->ci.p, m->va.p, m->dg.p, m->bw.p, m->xw.p, ld, nrhs, m->color_start,
+                                                 m->n_colors, (GsCtl *)m->ctl.p, m->partials.p, m->small_bar.p,
+                                                 max_iteration - issued, st, &slots);
+            ++launches;
+            issued = max_iteration; // the launch runs until the stop rule fires or max_iteration is reached
+        } else if (use_graph) {
             int key[6] = {nrhs, batch, 1, gsb_plan_effective_kernel(m->plan, nrhs), m->n_colors, 1};
             if (!m->graph_exec || memcmp(key, m->graph_key, sizeof(key)) != 0) {
                 if (m->graph_exec) {
@@ -286,7 +305,7 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         stats->sweeps = h.sweeps;
         stats->n_colors = m->n_colors;
         stats->ordering_used = m->ordering_used;
-        stats->kernel_used = gsb_plan_effective_kernel(m->plan, nrhs);
+        stats->kernel_used = use_small ? 6 : gsb_plan_effective_kernel(m->plan, nrhs);
         stats->kernel_launches = launches;
         for (int r = 0; r < MAX_RHS; ++r) stats->last_eps[r] = r < nrhs ? h.eps_last[r] : 0.0;
         stats->solve_ms = solve_ms;

@@ -129,7 +129,8 @@ typedef struct gsb_gs_options {
     int use_graph;       /* 1 = replay a captured CUDA graph per batch; 0 = plain launches; -1 auto  */
     int kernel;          /* 0 = auto; 1 = row-per-thread direct; 2 = staged tiles (bulk copies);
                             3 = persistent ring; 4 = ring + shared-memory gather windows;
-                            5 = two-colour systems: both colours in one launch per sweep (L2 wavefront) */
+                            5 = two-colour systems: both colours in one launch per sweep (L2 wavefront);
+                            6 = small systems: the whole solve in one persistent launch (grid barriers)  */
     int compute_residual;/* 1 = also return ||b - A x||_2 per right-hand side in stats                */
     int fused_lead;      /* kernel 5: tiles colour 0 runs ahead of colour 1 beyond the dependency
                             distance; 0 = library default (one tile per resident CTA)                 */
@@ -140,7 +141,7 @@ typedef struct gsb_gs_stats {
     int sweeps;          /* cnt at exit (v2 :377)                                                     */
     int n_colors;
     int ordering_used;
-    int kernel_used;     /* 1..5 as above; strip solver: +10 halo exchange fused into the phase kernels,
+    int kernel_used;     /* 1..6 as above; strip solver: +10 halo exchange fused into the phase kernels,
                             +20 more when the stop-rule all-reduce is fused into the end-of-sweep kernel */
     int64_t kernel_launches; /* launches of this library's kernels enqueued by the call              */
     double last_eps[4];  /* L1 norm of the last evaluated sweep update, per right-hand side (v2 :376) */

@@ -383,8 +383,8 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
     r, c, v, b2, _ = wl.diag_dominant_system(7001, 6, seed=13)
     sg = gsb.SparseMatrix(np.float64)
     sg.initializeFromVector(r, c, v)
-    outs = [sg.gaussSeidel(b2, epsilon=0.0, max_iteration=6, options=gsb.SparseMatrix.options(kernel=k)) for k in (1, 2, 3, 0)]
-    assert sg.last_stats.kernel_used == 3  # random columns do not form windows: auto keeps global gathers
+    outs = [sg.gaussSeidel(b2, epsilon=0.0, max_iteration=6, options=gsb.SparseMatrix.options(kernel=k)) for k in (1, 2, 3, 6, 0)]
+    assert sg.last_stats.kernel_used == 6  # auto: a small system runs in one persistent launch
     assert all(np.array_equal(outs[0], o) for o in outs[1:])
     for k in (4, 5):  # no gather windows, more than two colours
         with pytest.raises(gsb.GsbError):
@@ -395,9 +395,53 @@ def test_all_kernels_agree_bitwise(gsb, nrhs):
 
 
 def AUTO_GRID_KERNEL(nrhs):
-    """300 x 217 is far below the size where the fused sweep (5) pays: the per-phase ring kernels, with gather
-    windows for one right-hand side (measured policy, gsb_plan_effective_kernel)."""
-    return 4 if nrhs == 1 else 3
+    """300 x 217 x 2 colours is a small system: the whole solve in one persistent launch (kernel 6)."""
+    return 6
+
+
+def test_small_system_persistent_kernel(gsb, oracle_mod):
+    """Kernel 6 (one launch per solve, grid barriers between the colours, stop rule inside the loop) against kernel 1:
+    x bit for bit, the same stop sweep, on the lab3 4 x 4 system, BASELINE configs[0] (n = 1e4, multicolour), a small
+    Poisson grid with three right-hand sides and a one-row system; and it is what small systems get by default."""
+    from coursecomputationalphotography_b200 import workloads as wl
+    K = lambda k, **kw: gsb.SparseMatrix.options(kernel=k, **kw)
+    sp = gsb.SparseMatrix(np.int32)
+    sp.initialize(4, 4, [10, -1, 2, 0, -1, 11, -1, 3, 2, -1, 10, -1, 0, 3, -1, 8])
+    b = np.array([6.0, 25.0, -11.0, 15.0])
+    x6 = sp.gaussSeidel(b, options=K(6))
+    s6 = sp.last_stats.sweeps
+    assert sp.last_stats.kernel_used == 6 and np.allclose(x6, [1, 2, -1, 1], atol=1e-6)
+    x1 = sp.gaussSeidel(b, options=K(1, use_graph=0))
+    assert sp.last_stats.sweeps == s6 and np.array_equal(x1, x6)
+    assert sp.gaussSeidel(b) is not None and sp.last_stats.kernel_used == 6  # the default for small systems
+    # configs[0]
+    r, c, v, bb, xstar = wl.diag_dominant_system(10_000, 4, seed=42)
+    sd = gsb.SparseMatrix(np.float64)
+    sd.initializeFromVector(r, c, v)
+    for eps, cap in ((1e-6, 1000), (0.0, 7), (1e-3, 1000)):
+        y6 = sd.gaussSeidel(bb, epsilon=eps, max_iteration=cap, options=K(6))
+        n6, e6 = sd.last_stats.sweeps, sd.last_stats.last_eps[0]
+        assert sd.last_stats.kernel_used == 6 and sd.last_stats.kernel_launches <= 5
+        y1 = sd.gaussSeidel(bb, epsilon=eps, max_iteration=cap, options=K(1, use_graph=0))
+        assert sd.last_stats.sweeps == n6 and np.array_equal(y1, y6), (eps, cap)
+        assert abs(sd.last_stats.last_eps[0] - e6) <= 1e-12 * max(abs(e6), 1e-300)
+    assert np.abs(y6 - xstar).max() < 1e-2
+    # small Poisson grid, three channels, odd sizes
+    W, H = 97, 61
+    img, bp = _poisson_rhs_for(gsb, wl, W, H, C=3)
+    pg = gsb.SparseMatrix(np.float64)
+    pg.poisson(W, H)
+    z6 = pg.gaussSeidel(bp, epsilon=0.0, max_iteration=33, options=K(6))
+    assert pg.last_stats.kernel_used == 6 and pg.last_stats.sweeps == 33
+    assert np.array_equal(z6, pg.gaussSeidel(bp, epsilon=0.0, max_iteration=33, options=K(3, use_graph=0)))
+    # repeated solves reuse the barrier words; a one-row system
+    assert np.array_equal(z6, pg.gaussSeidel(bp, epsilon=0.0, max_iteration=33, options=K(6)))
+    one = gsb.SparseMatrix(np.float64)
+    one.initializeFromVector([0], [0], [4.0])
+    assert one.gaussSeidel(np.array([2.0]), options=K(6))[0] == 0.5
+    # check_every > 1 is not what this kernel implements
+    with pytest.raises(gsb.GsbError):
+        pg.gaussSeidel(bp, epsilon=0.0, max_iteration=4, options=K(6, check_every=2))
 
 
 @pytest.mark.parametrize("W,H,nrhs", [(300, 217, 3), (1024, 512, 1), (1024, 512, 3), (2048, 1600, 3)])
@@ -469,7 +513,7 @@ def test_fused_sweep_needs_banded_two_colour_system(gsb):
     sp.analyze(gsb._lib.ORDER_USER, (np.arange(n) >= half).astype(np.int32))
     b = rng.standard_normal(n)
     x = sp.gaussSeidel(b, epsilon=0.0, max_iteration=4)
-    assert sp.last_stats.kernel_used in (3, 4) and sp.last_stats.n_colors == 2
+    assert sp.last_stats.kernel_used in (3, 4, 6) and sp.last_stats.n_colors == 2
     with pytest.raises(gsb.GsbError):
         sp.gaussSeidel(b, epsilon=0.0, max_iteration=1, options=gsb.SparseMatrix.options(kernel=5))
     assert np.array_equal(x, sp.gaussSeidel(b, epsilon=0.0, max_iteration=4, options=gsb.SparseMatrix.options(kernel=1)))
