@@ -23,6 +23,7 @@
 #include <math.h>
 
 #define CG_THREADS 256
+#define CG_UNROLL 6      // rows up to this many entries take the gather-prefetch path
 #define CG_SPAN_CAP 2048 // CSR entries of a 256-row tile staged in shared memory (24 KB): rows up to 8 entries on average
 
 struct CgState {
@@ -133,12 +134,36 @@ __global__ void __launch_bounds__(CG_THREADS) cg_spmv_dot(const double *__restri
             double s[NRHS];
 #pragma unroll
             for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
-            for (int j = 0; j < len; ++j) {
-                const double v = staged ? v_s[kb - k0 + j] : vals[kb + j];
-                const int c = staged ? c_s[kb - k0 + j] : cols[kb + j];
+            if (len <= CG_UNROLL) {
+                // short rows (a 5-point row has 5 entries): fetch the row, issue ALL gathers, then accumulate in storage
+                // order -- the gathers' latencies overlap instead of adding up; padded slots load column 0 and are
+                // not accumulated
+                int cc[CG_UNROLL];
+                double vv[CG_UNROLL], xg[CG_UNROLL][NRHS];
 #pragma unroll
-                for (int r = 0; r < NRHS; ++r)
-                    if (live[r]) s[r] = __dadd_rn(s[r], __dmul_rn(v, in[r * ld + c]));
+                for (int j = 0; j < CG_UNROLL; ++j) {
+                    const bool in_row = j < len;
+                    cc[j] = in_row ? (staged ? c_s[kb - k0 + j] : cols[kb + j]) : 0;
+                    vv[j] = in_row ? (staged ? v_s[kb - k0 + j] : vals[kb + j]) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < CG_UNROLL; ++j)
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) xg[j][r] = live[r] ? in[r * ld + cc[j]] : 0.0;
+#pragma unroll
+                for (int j = 0; j < CG_UNROLL; ++j)
+                    if (j < len) {
+#pragma unroll
+                        for (int r = 0; r < NRHS; ++r) s[r] = __dadd_rn(s[r], __dmul_rn(vv[j], xg[j][r]));
+                    }
+            } else {
+                for (int j = 0; j < len; ++j) {
+                    const double v = staged ? v_s[kb - k0 + j] : vals[kb + j];
+                    const int c = staged ? c_s[kb - k0 + j] : cols[kb + j];
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r)
+                        if (live[r]) s[r] = __dadd_rn(s[r], __dmul_rn(v, in[r * ld + c]));
+                }
             }
 #pragma unroll
             for (int r = 0; r < NRHS; ++r)

@@ -434,6 +434,15 @@ def test_small_system_persistent_kernel(gsb, oracle_mod):
     z6 = pg.gaussSeidel(bp, epsilon=0.0, max_iteration=33, options=K(6))
     assert pg.last_stats.kernel_used == 6 and pg.last_stats.sweeps == 33
     assert np.array_equal(z6, pg.gaussSeidel(bp, epsilon=0.0, max_iteration=33, options=K(3, use_graph=0)))
+    # a system that takes several CTAs (grid barrier in global memory), two right-hand sides
+    W2, H2 = 300, 217
+    img2, bp2 = _poisson_rhs_for(gsb, wl, W2, H2, C=3)
+    pm = gsb.SparseMatrix(np.float64)
+    pm.poisson(W2, H2)
+    for cap in (1, 2, 25):
+        w6 = pm.gaussSeidel(bp2[:2], epsilon=0.0, max_iteration=cap, options=K(6))
+        assert pm.last_stats.kernel_used == 6 and pm.last_stats.sweeps == cap
+        assert np.array_equal(w6, pm.gaussSeidel(bp2[:2], epsilon=0.0, max_iteration=cap, options=K(3, use_graph=0))), cap
     # repeated solves reuse the barrier words; a one-row system
     assert np.array_equal(z6, pg.gaussSeidel(bp, epsilon=0.0, max_iteration=33, options=K(6)))
     one = gsb.SparseMatrix(np.float64)
