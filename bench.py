@@ -126,17 +126,27 @@ def pinned_like(pkg, a):
 
 
 def lib_sha16():
+    """Hash of the library's SOURCES (csrc/*.cu, *.cuh, *.h and the public header): what an ncu capture recorded in
+    profiles/traffic.json is valid for.  (The .so itself is no use as a key: nvcc / the linker do not produce the same
+    bytes twice from the same sources.)"""
+    import glob
     import hashlib
-    try:
-        return hashlib.sha256(open(os.path.join(ROOT, "coursecomputationalphotography_b200", "libgsb200.so"), "rb").read()).hexdigest()[:16]
-    except OSError:
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "coursecomputationalphotography_b200", "csrc")
+    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) +
+                   glob.glob(os.path.join(csrc, "*.h")) + [os.path.join(ROOT, "include", "gsb200.h")])
+    if not files:
         return None
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def recorded_traffic(kernel_used, W, H, ch, check_every):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
     recorded in profiles/traffic.json (one entry per kernel / shape).  It is a recorded number, not a measurement of
-    this run: `traffic_source` names the capture and `traffic_stale` says when the library has been rebuilt since."""
+    this run: `traffic_source` names the capture and `traffic_stale` says when the library's sources have changed since."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         db = json.load(open(path))
@@ -148,8 +158,8 @@ def recorded_traffic(kernel_used, W, H, ch, check_every):
         return {"traffic_source": "no ncu capture recorded for %s" % key}
     out = {"traffic": ent["dram_bytes_per_launch"], "traffic_source": ent.get("source")}
     sha = lib_sha16()
-    if ent.get("lib_sha16") and sha and ent["lib_sha16"] != sha:
-        out["traffic_stale"] = "captured on libgsb200.so %s, this run uses %s" % (ent["lib_sha16"], sha)
+    if ent.get("src_sha16") and sha and ent["src_sha16"] != sha:
+        out["traffic_stale"] = "captured on library sources %s, this run is built from %s" % (ent["src_sha16"], sha)
     return out
 
 

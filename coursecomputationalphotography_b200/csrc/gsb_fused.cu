@@ -12,16 +12,16 @@
 // stages of kernel 3.  A colour-1 tile B_j may run once the colour-0 tiles in dep[j] = [lo, hi] have finished:
 // those are the tiles whose new values it gathers (read after write) and the tiles that gather ITS rows' old values
 // (write after read); the plan computes the range from the column indices, and L >= max_j(hi_j - j) + 1 puts every
-// dependency earlier in the sequence, so the in-order walk cannot deadlock (all CTAs are resident: grid = SMs x
-// occupancy).  Colour-0 tiles never wait: what they read is the previous sweep's output (kernel boundary).
-// A finished colour-0 tile publishes flags[t] = sweep number with a release store; a colour-1 tile's first warp
-// polls its range with acquire loads before the tile's gathers.  With L a few hundred tiles the dependencies are
-// long finished when a tile comes up, and the reuse distance (~2L tiles, some tens of MB) sits inside L2:
-// colour 1's gathers and x_old hit L2, every x is read from HBM once and written once per sweep -- the
-// algorithmic count -- and the stop rule costs no traffic at all.
+// dependency earlier in the sequence; together with "a CTA that has to wait first retires and publishes its own
+// current tile" (control warp, below) no cycle of waits can form (all CTAs are resident: grid = SMs x occupancy).
+// Colour-0 tiles never wait: what they read is the previous sweep's output (kernel boundary).  A finished colour-0
+// tile publishes flags[t] = sweep number (release); the control warp polls a colour-1 tile's range (relaxed loads,
+// one acquire fence) before it releases the tile to the compute warps.  The reuse distance (~2L tiles, a few MB to
+// tens of MB) sits inside L2: colour 1's gathers and x_old hit L2, every x is read from HBM once and written once
+// per sweep -- the algorithmic count -- and the stop rule costs no traffic at all.
 //
 // Arithmetic is the row body of the phase kernels (gs_row_sigma, unfused, storage order): x after every sweep is
-// bit-identical to kernels 1-4 (tests/test_gs_gpu.py::test_all_kernels_agree_bitwise).
+// bit-identical to kernels 1-4 and 6 (tests/test_gs_gpu.py::test_all_kernels_agree_bitwise).
 #include "gsb_ring.cuh"
 
 #include <limits.h>
