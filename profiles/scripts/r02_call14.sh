@@ -3,6 +3,7 @@
 # no tile is a halo tile, no flag is touched) -- timing against the plain strip path, and one ncu capture of it
 cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out/r02c14; mkdir -p $O
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log; tail -2 $O/smoke.log
 S="python bench.py --strips --steps 5 --warmup 3 --no-e2e --no-c4 --no-time-to-tol"
 timeout 300 $S > $O/bench_strips_n1.json 2>&1
 GSB_DIST_FORCE_HALO=1 timeout 300 $S > $O/bench_strips_n1_halo.json 2>&1
