@@ -125,28 +125,26 @@ def pinned_like(pkg, a):
     return out
 
 
-def lib_sha16():
-    """Hash of the library's SOURCES (csrc/*.cu, *.cuh, *.h and the public header): what an ncu capture recorded in
-    profiles/traffic.json is valid for.  (The .so itself is no use as a key: nvcc / the linker do not produce the same
-    bytes twice from the same sources.)"""
-    import glob
+def src_sha16(files):
+    """Hash of the source files that define a kernel (names relative to coursecomputationalphotography_b200/csrc):
+    what an ncu capture recorded in profiles/traffic.json is valid for.  (The .so itself is no use as a key: nvcc /
+    the linker do not produce the same bytes twice from the same sources.)"""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "coursecomputationalphotography_b200", "csrc")
-    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) +
-                   glob.glob(os.path.join(csrc, "*.h")) + [os.path.join(ROOT, "include", "gsb200.h")])
-    if not files:
+    try:
+        for f in sorted(files):
+            h.update(f.encode())
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    except OSError:
         return None
-    for f in files:
-        h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
 
 
 def recorded_traffic(kernel_used, W, H, ch, check_every):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
     recorded in profiles/traffic.json (one entry per kernel / shape).  It is a recorded number, not a measurement of
-    this run: `traffic_source` names the capture and `traffic_stale` says when the library's sources have changed since."""
+    this run: `traffic_source` names the capture and `traffic_stale` says when the kernel's source files have changed since."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         db = json.load(open(path))
@@ -157,9 +155,10 @@ def recorded_traffic(kernel_used, W, H, ch, check_every):
     if not ent:
         return {"traffic_source": "no ncu capture recorded for %s" % key}
     out = {"traffic": ent["dram_bytes_per_launch"], "traffic_source": ent.get("source")}
-    sha = lib_sha16()
-    if ent.get("src_sha16") and sha and ent["src_sha16"] != sha:
-        out["traffic_stale"] = "captured on library sources %s, this run is built from %s" % (ent["src_sha16"], sha)
+    if ent.get("src_files"):
+        sha = src_sha16(ent["src_files"])
+        if ent.get("src_sha16") and sha and ent["src_sha16"] != sha:
+            out["traffic_stale"] = "captured when %s hashed to %s, now %s" % (ent["src_files"], ent["src_sha16"], sha)
     return out
 
 
@@ -440,7 +439,7 @@ def run_time_to_tol(args):
     sm = pkg.SparseMatrix(np.float64)
     sm.initializeFromEigenRowMajor(va, len(va), ro[:-1], n, ci, n)
     sm.analyze(pkg._lib.ORDER_USER, colors)
-    opts = pkg.SparseMatrix.options(check_every=args.check_every)
+    opts = pkg.SparseMatrix.options(check_every=args.check_every, kernel=args.kernel)
     sm.gaussSeidel(b, epsilon=0.0, max_iteration=20, options=opts)  # warm-up: plan, workspaces
     tol = 1e-4 * 255.0
 
@@ -659,7 +658,7 @@ def other_config_child(args, which, timeout):
 def time_to_tol_child(args):
     """Run the leg in a child process; returns its dict or {"error": ...}."""
     cmd = [sys.executable, os.path.abspath(__file__), "--time-to-tol-only", "--size", str(args.size), "--channels",
-           str(args.channels), "--check-every", str(args.check_every)]
+           str(args.channels), "--check-every", str(args.check_every), "--kernel", str(args.kernel)]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]

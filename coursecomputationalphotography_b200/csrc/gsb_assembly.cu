@@ -20,6 +20,8 @@ gsb_matrix::~gsb_matrix() {
     ctl_host = nullptr;
     if (cg_state_host) cudaFreeHost(cg_state_host);
     cg_state_host = nullptr;
+    if (b_ready_event) cudaEventDestroy((cudaEvent_t)b_ready_event);
+    b_ready_event = nullptr;
 }
 
 extern "C" int gsb_matrix_create(gsb_matrix **out, int vtype) {

@@ -13,6 +13,7 @@
 void gsb_set_error(const char *fmt, ...);
 int gsb_current_device();
 cudaStream_t gsb_cur_stream();
+cudaStream_t gsb_copy_stream(); // per device, for uploads that overlap work on the main stream
 int gsb_sm_count();
 int gsb_ensure_device(); // GSB_OK or GSB_ERR_NO_DEVICE
 
@@ -151,6 +152,8 @@ struct gsb_matrix {
     DevBuf<double> xw, bw; // permuted x and b, nrhs * n_rows
     int ws_nrhs = 0;
     DevBuf<double> stage_b, stage_x; // natural-order device copies of host b / x for the host-pointer entry points
+    void *b_ready_event = nullptr;   // cudaEvent_t: stage_b's upload on the copy stream (host entry point, first solve)
+    bool b_upload_pending = false;   // the solver core has to wait for b_ready_event before it reads stage_b
     DevBuf<double> partials;   // per-block partial sums of the stop rule
     DevBuf<unsigned char> ctl; // GsCtl
     DevBuf<unsigned> small_bar; // kernel 6: grid-barrier counter + generation

@@ -138,6 +138,18 @@ cudaStream_t gsb_cur_stream() {
     return g_streams[g_device];
 }
 
+// second stream per device for host -> device copies that can overlap work on the main stream (the upload of b
+// while the ordering analysis of a freshly imported matrix runs)
+static cudaStream_t g_copy_streams[64] = {nullptr};
+cudaStream_t gsb_copy_stream() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_copy_streams[g_device]) {
+        cudaSetDevice(g_device);
+        cudaStreamCreateWithFlags(&g_copy_streams[g_device], cudaStreamNonBlocking);
+    }
+    return g_copy_streams[g_device];
+}
+
 extern "C" void *gsb_stream(void) {
     if (gsb_ensure_device() != GSB_OK) return nullptr;
     return (void *)gsb_cur_stream();

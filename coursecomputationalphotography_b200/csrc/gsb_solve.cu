@@ -165,6 +165,10 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     }
     const int nbv = (int)((n + 255) / 256);
     const int64_t ld = gsb_padded_ld(n);
+    if (m->b_upload_pending) { // the host entry point uploaded b on the copy stream while the analysis ran here
+        GSB_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)m->b_ready_event, 0));
+        m->b_upload_pending = false;
+    }
     gather_perm<<<nbv, 256, 0, st>>>(b_dev, m->perm.p, n, ld, nrhs, m->bw.p);
     GSB_KERNEL_CHECK();
     if (x0_dev)
@@ -427,7 +431,22 @@ static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, d
     GSB_TRY(db.alloc(n * nrhs));
     GSB_TRY(dx.alloc(n * nrhs));
     size_t bytes = sizeof(double) * (size_t)(n * nrhs);
-    GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    if (!m->analyzed) {
+        // a freshly imported matrix: the ordering analysis and the launch plan (several device round trips) come
+        // first in the solver core -- b travels on the copy stream meanwhile and the core waits for it only where it
+        // first reads it (the previous solve's use of stage_b is over: every entry point ends with a stream sync)
+        if (!m->b_ready_event) {
+            cudaEvent_t ev = nullptr;
+            GSB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            m->b_ready_event = ev;
+        }
+        cudaStream_t cs = gsb_copy_stream();
+        GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, cs));
+        GSB_CUDA(cudaEventRecord((cudaEvent_t)m->b_ready_event, cs));
+        m->b_upload_pending = true;
+    } else {
+        GSB_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    }
     const double *x0_dev = nullptr;
     if (x0) {
         GSB_CUDA(cudaMemcpyAsync(dx.p, x0, bytes, cudaMemcpyHostToDevice, st));
@@ -435,7 +454,12 @@ static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, d
     }
     // x0 lives in dx and the result is scattered into dx: gs_solve_device permutes x0 into its
     // workspace before it writes dx, so the aliasing is safe.
-    GSB_TRY(gs_solve_device(m, db.p, x0_dev, nrhs, epsilon, max_iteration, opts, dx.p, stats));
+    const int solved = gs_solve_device(m, db.p, x0_dev, nrhs, epsilon, max_iteration, opts, dx.p, stats);
+    if (m->b_upload_pending) { // the core failed before it consumed the upload: do not leave a copy in flight
+        cudaStreamSynchronize(gsb_copy_stream());
+        m->b_upload_pending = false;
+    }
+    GSB_TRY(solved);
     GSB_CUDA(cudaMemcpyAsync(x_out, dx.p, bytes, cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
     return GSB_OK;

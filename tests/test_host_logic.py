@@ -122,6 +122,6 @@ def test_bench_gpu_arm_fails_loudly_without_a_gpu(gsb):
     import bench
 
     class A:
-        size, channels, check_every = 64, 3, 1
+        size, channels, check_every, kernel = 64, 3, 1, 0
     out = bench.time_to_tol_child(A)
     assert "error" in out and "NO_DEVICE" in out["error"]
