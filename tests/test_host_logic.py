@@ -105,6 +105,13 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the workload-defining keys are the SAME dict the GPU arm and the strip arm emit (what each arm did with the
+    # workload is in "run"), and the warm-up clamp is the GPU arm's
+    sys.path.insert(0, root)
+    import bench
+    from coursecomputationalphotography_b200 import workloads as wl
+    assert d["config"] == bench.workload_config(256, 256, 3, 256 * 256, wl.poisson_nnz(256, 256))
+    assert d["warmup"] == 3 and "sweeps_per_step" in d["run"] and "sweeps_per_step" not in d["config"]
 
 
 def test_bench_gpu_arm_fails_loudly_without_a_gpu(gsb):
