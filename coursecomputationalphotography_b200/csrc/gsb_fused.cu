@@ -31,6 +31,7 @@ struct GsbFusedArgs { // (scalar members, selected with ?: -- indexing a by-valu
     int row0_0, row0_1, row1_0, row1_1, nt0, nt1;
     const int *tile_k0, *tile_k1; // CSR offset at every tile boundary of the colour
     const int2 *dep;      // per colour-1 tile: first / last colour-0 tile it waits for
+    const int2 *span;     // per tile (colour 0 first): smallest / largest column it gathers ({INT_MAX, -1}: none)
     int *flags;           // per colour-0 tile
     int lead, nalt;       // colour 0 runs `lead` tiles ahead; `nalt` = alternating (B, R) pairs after the lead
 };
@@ -63,7 +64,11 @@ __device__ __forceinline__ void fused_item(const GsbFusedArgs &fa, int p, int &c
 struct __align__(16) FusedItem {
     int k0, k1, r_begin, rows; // CSR span of the tile, its first row and row count
     int c, t, dep_lo, dep_hi;  // colour, tile, colour-0 tiles to wait for (dep_lo > dep_hi: none)
+    // A colour-0 item waits for nothing; its dep fields carry an L2 prefetch hint instead: the x columns
+    // [dep_lo, dep_lo + (-dep_hi - 1)) -- the top of its gather span, i.e. the values of the other colour that no
+    // earlier tile of the sweep has touched (on a grid: the neighbours in the next image row).
 };
+#define GS_FUSED_GATHER_HINT_COLS 320 // a tile's rows + the raggedness of a 5-point row boundary
 
 __global__ void __launch_bounds__(256) plan_fused_items(const GsbFusedArgs fa, FusedItem *__restrict__ items) {
     const int p = blockIdx.x * 256 + threadIdx.x;
@@ -81,6 +86,14 @@ __global__ void __launch_bounds__(256) plan_fused_items(const GsbFusedArgs fa, F
         const int2 d = fa.dep[it.t];
         it.dep_lo = d.x;
         it.dep_hi = d.y;
+    } else if (fa.span) {
+        const int2 sp = fa.span[it.t];
+        if (sp.y >= sp.x) { // 16-byte aligned start, even count; the planes are padded to an even length
+            const int lo = max(sp.x, sp.y + 1 - GS_FUSED_GATHER_HINT_COLS) & ~1;
+            const int cnt = ((sp.y + 2) & ~1) - lo;
+            it.dep_lo = lo;
+            it.dep_hi = -cnt - 1;
+        }
     }
     items[p] = it;
 }
@@ -98,7 +111,16 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t byte
 // compute warps' gathers are ordered after the colour-0 tiles' stores (release / acquire at GPU scope, cumulative
 // through the warp and mbarrier synchronisation).  Bounded: a flag that never comes (it cannot, short of a device
 // fault) raises ctl->error instead of hanging the GPU, and once one tile has given up nobody waits any more.
-__device__ __forceinline__ void fused_wait_tiles(const int *flags, int lo, int hi, int epoch, GsCtl *ctl) {
+__device__ __forceinline__ void fused_acquire_fence(bool split) {
+    // split: acquire only (SASS: CCTL.IVALL, the L1 invalidation) -- fence.acq_rel adds a MEMBAR.ALL.GPU in front of it,
+    // i.e. the warp also waits for its outstanding accesses, which an observer of flags does not need
+    if (split)
+        asm volatile("fence.acquire.gpu;" ::: "memory");
+    else
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+__device__ __forceinline__ void fused_wait_tiles(const int *flags, int lo, int hi, int epoch, GsCtl *ctl, bool split) {
     const int lane = threadIdx.x & 31;
     for (int base = lo; base <= hi; base += 32) {
         const int i = base + lane;
@@ -114,7 +136,7 @@ __device__ __forceinline__ void fused_wait_tiles(const int *flags, int lo, int h
             __nanosleep(spins < 16 ? 20 : 200);
         }
     }
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    fused_acquire_fence(split);
     __syncwarp();
 }
 
@@ -218,6 +240,36 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
                 }
             }
         };
+        // hints & 16 -- lane 0: pull the inputs of the item AFTER the next refill into L2 (no completion tracking).  The
+        // ring has two stages, so a refill has one tile time to land; issued a tile time before the refill, the
+        // prefetch turns the refill's HBM round trip (~3 us under load) into an L2 hit.
+        auto prefetch_l2 = [&](const FusedItem &d) {
+            const int r_begin = d.r_begin, rows = d.rows, k0 = d.k0, k1 = d.k1;
+            const int kv0 = k0 & ~1, kc0 = k0 & ~3;
+            const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
+            const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
+            const int ea = r_begin & ~1;
+            const uint32_t bytes_p = (uint32_t)(((r_begin + rows + 1) & ~1) - ea) * 8u;
+            if (hints & 16) {
+                if (bytes_v) bulk_prefetch_l2(va + kv0, bytes_v);
+                if (bytes_c) bulk_prefetch_l2(ci + kc0, bytes_c);
+            }
+            if ((hints & 64) && d.c == 0 && d.dep_hi < -1) { // the gathers' compulsory misses (see FusedItem)
+                const uint32_t bytes_g = (uint32_t)(-d.dep_hi - 1) * 8u;
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) bulk_prefetch_l2(x + r * n + d.dep_lo, bytes_g);
+            }
+            if (hints & 32) {
+                const int ra = r_begin & ~3;
+                bulk_prefetch_l2(rp + ra, (uint32_t)(((r_begin + rows + 1 + 3) & ~3) - ra) * 4u);
+                bulk_prefetch_l2(dg + ea, bytes_p);
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    bulk_prefetch_l2(b + r * n + ea, bytes_p);
+                    if (CHECK) bulk_prefetch_l2(x + r * n + ea, bytes_p);
+                }
+            }
+        };
         // ---- dependency polls, issued one iteration before they are needed ------------------------------------
         // start: every lane loads one flag of the item's range (relaxed; the load completes in the background -- its
         // value is first looked at an iteration later).  finish: all lanes saw `epoch` -> one acquire fence; else the
@@ -236,8 +288,13 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
         int pend_n = 0, pend_t0 = 0, pend_t1 = 0, pend_t2 = 0, pend_t3 = 0;
         auto flush = [&]() {
             if (pend_n && lane == 0 && !(debug & 2)) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory"); // release: cumulative over the compute warps' stores
-                                                                  // observed through the `empty` mbarriers
+                // release: cumulative over the compute warps' stores observed through the `empty` mbarriers.
+                // hints & 8: fence.release (MEMBAR.ALL.GPU only) instead of fence.acq_rel (MEMBAR + CCTL.IVALL): the
+                // publisher has nothing to acquire, and the L1 invalidation costs the SM's other CTAs their gather hits
+                if (hints & 8)
+                    asm volatile("fence.release.gpu;" ::: "memory");
+                else
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t0), "r"(epoch) : "memory");
                 if (pend_n > 1) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t1), "r"(epoch) : "memory");
                 if (pend_n > 2) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + pend_t2), "r"(epoch) : "memory");
@@ -248,7 +305,7 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
         // blocking completion of a poll (the slow path); fences and re-converges the warp itself
         auto wait_blocking = [&](const FusedItem &d) {
             flush();
-            fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl);
+            fused_wait_tiles(flags, d.dep_lo, d.dep_hi, epoch, ctl, (hints & 8) != 0);
         };
         // did the poll started an iteration ago see every flag?  (uniform over the warp)
         auto poll_ready = [&](const FusedItem &d, int v) -> bool {
@@ -258,7 +315,7 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
         };
         auto acquire = [&](const FusedItem &d) {
             if (d.dep_hi >= d.dep_lo && !(debug & 1)) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                fused_acquire_fence((hints & 8) != 0);
                 __syncwarp();
             }
         };
@@ -315,7 +372,11 @@ __global__ void __launch_bounds__(GS_FUSED_THREADS, (NRHS >= 4 ? 3 : 4))
                 }
                 if (lane == 0) mbar_arrive(&full[(j + 1) % STAGES]);
             }
-            if (!retired) retire();
+            if (!retired) {
+                // (r2 = item j+2 was fetched an iteration ago; it is refilled into stage s right after the wait below)
+                if ((hints & (16 | 32 | 64)) && lane == 0 && j + 2 < my_items) prefetch_l2(r2);
+                retire();
+            }
             if (j + 2 < my_items) pv2 = start_poll(r2);
             if (j + 3 < my_items) r3 = load_item(j + 3);
             r0 = r1;
@@ -472,7 +533,7 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     if (!p->fused_allowed || p->n_colors != 2 || p->tile_rows != GS_THREADS) return GSB_OK;
     const int nt0 = p->blocks[0], nt1 = p->blocks[1];
     if (nt0 <= 0 || nt1 <= 0) return GSB_OK;
-    DevBuf<int2> span;
+    DevBuf<int2> &span = p->fused_span; // kept: the item table takes the colour-0 tiles' gather hints from it
     DevBuf<int> stats;
     GSB_TRY(span.alloc((int64_t)nt0 + nt1));
     GSB_TRY(stats.alloc(4));
@@ -494,6 +555,7 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     if (h[0] != 0 || h[2] > GS_FUSED_DEP_WIDTH_MAX) {
         p->fused_dep.release();
         p->fused_flags.release();
+        p->fused_span.release();
         return GSB_OK;
     }
     p->fused_lead_min = h[1] + 1 > 1 ? h[1] + 1 : 1;
@@ -518,7 +580,10 @@ static const FusedEnv &fused_env() {
         e.lead = v ? atoi(v) : 0;
         v = getenv("GSB_FUSED_PUBK"); // colour-0 tiles published per release fence (1..4)
         e.pubk = v ? atoi(v) : 0;
-        v = getenv("GSB_FUSED_L2HINT"); // 1: matrix / b copies evict-first; 2: x_old copies evict-last; 3: both
+        // 1: matrix / b copies evict-first; 2: x_old copies evict-last; 4: x stores evict-last; 8: release / acquire
+        // fences instead of acq_rel; 16: L2 prefetch of the next refill's matrix spans; 32: ... and of its vectors;
+        // 64: L2 prefetch of the x columns a colour-0 tile is the first to gather
+        v = getenv("GSB_FUSED_L2HINT");
         e.hints = v ? atoi(v) : GS_FUSED_L2HINT_DEFAULT;
         v = getenv("GSB_RING_CTAS");
         e.ctas = v ? atoi(v) : 0;
@@ -547,6 +612,7 @@ int gsb_plan_fused_reset(const GsbPlan *p, cudaStream_t st) {
     fa.tile_k0 = p->tile_k.p + p->tile_off[0];
     fa.tile_k1 = p->tile_k.p + p->tile_off[1];
     fa.dep = reinterpret_cast<const int2 *>(p->fused_dep.p);
+    fa.span = p->fused_span.p;
     fa.flags = p->fused_flags.p;
     fa.lead = lead;
     fa.nalt = nt1 < nt0 - lead ? nt1 : nt0 - lead;

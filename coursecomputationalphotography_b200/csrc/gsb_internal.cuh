@@ -228,6 +228,7 @@ struct GsbPlan {
     int fused_lead_extra = 0;   // caller's gsb_gs_options.fused_lead (0 = default)
     DevBuf<int> fused_dep;      // 2 ints per colour-1 tile: first, last colour-0 tile
     DevBuf<int> fused_flags;    // per colour-0 tile: number of the last sweep that updated it (reset per solve)
+    DevBuf<int2> fused_span;    // per tile (colour 0 first): smallest / largest column among its off-diagonal entries
     DevBuf<int4> fused_items;   // per work item of the sweep, sequence order: two int4 (FusedItem, gsb_fused.cu)
     int fused_items_lead = -1;  // the lead the table was built for
     int total_blocks() const;

@@ -11,7 +11,9 @@
 // All CTAs must be resident (the barrier spins): grid = min(ceil(largest colour / 256), SMs x occupancy).
 #include "gsb_ring.cuh"
 
+#include <cooperative_groups.h>
 #include <stdlib.h>
+namespace cg = cooperative_groups;
 
 #define GS_SMALL_MAX_COLORS 64
 
@@ -134,6 +136,229 @@ __global__ void __launch_bounds__(THREADS) gs_small_persistent(const int *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One CTA (<= GS_SMALL_SINGLE_ROWS rows, BASELINE configs[0]): the solve is a chain of (colour, pass) steps separated
+// by __syncthreads, and the time of a step is the chain of dependent loads inside it -- row offsets -> entries ->
+// x gathers -> divide (measured: 3.7 us per colour of 1250 rows, 2 passes).  The matrix does not change and the
+// schedule is static (a thread meets the same rows in the same order every sweep), so everything that does not depend
+// on x is loaded ahead: the row offsets two steps ahead, the entries, the diagonal, b (and the row's own old x) one
+// step ahead, while the current step's gathers are in flight.  What stays on the critical path of a step is one
+// gather round trip, the multiply-add chain, the divide and the barrier -- and with XS the gathers come out of shared
+// memory: x (all right-hand sides) lives there for the whole solve when it fits and is written back once.
+// CSIZE > 1: the same loop on a thread-block CLUSTER of CSIZE CTAs (one SM each).  One SM is what limits the one-CTA
+// version (measured: 1.4 us per step of 1024 rows -- ~200 instructions per row, 45 of them the IEEE divide, through
+// one SM's issue slots).  Every CTA keeps a complete copy of x in its shared memory; a thread that has computed x_i
+// stores it into all CSIZE copies (distributed shared memory), so that every gather stays a local shared-memory read,
+// and the colours are separated by the hardware cluster barrier (release / acquire at cluster scope orders the
+// remote stores) instead of __syncthreads.  The stop rule's partials meet in CTA 0's shared memory, which folds
+// them in rank order and writes its decision into every CTA.
+// Arithmetic and its order are those of gs_row_sigma / gs_small_persistent: the same bits.
+struct SmallRowA {
+    int i, k0, len; // i < 0: this thread has no row in the step
+};
+template <int NRHS>
+struct SmallRowB {
+    int cc[GS_UNROLL];
+    double vv[GS_UNROLL];
+    double d, bb[NRHS], xo[NRHS];
+};
+
+template <int NRHS, int THREADS, bool XS, int CSIZE>
+__global__ void __launch_bounds__(THREADS) gs_small_one_cta(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                            const double *__restrict__ va, const double *__restrict__ dg,
+                                                            const double *__restrict__ b, double *x, int64_t n, GsCtl *ctl,
+                                                            double *partials, const GsbSmallArgs a) {
+    extern __shared__ __align__(16) double xs[]; // XS: NRHS planes of `nrows` doubles
+    __shared__ double ws[NRHS][THREADS / 32];
+    __shared__ int cs[GS_SMALL_MAX_COLORS + 1];
+    __shared__ int done_s;
+    __shared__ double part_s[CSIZE][NRHS]; // CTA 0: every CTA's share of the sweep's update norm
+    static_assert(CSIZE == 1 || XS, "the cluster version keeps x in (distributed) shared memory");
+    constexpr int STRIDE = CSIZE * THREADS; // rows per step
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int rank = 0;
+    double *xs_of[CSIZE]; // every CTA's copy of x ([0] = this CTA's for CSIZE == 1)
+    xs_of[0] = xs;
+    if constexpr (CSIZE > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        rank = (int)cluster.block_rank();
+#pragma unroll
+        for (int q = 0; q < CSIZE; ++q) xs_of[q] = cluster.map_shared_rank(xs, q);
+    }
+    auto barrier = [&]() {
+        if constexpr (CSIZE > 1)
+            cg::this_cluster().sync();
+        else
+            __syncthreads();
+    };
+    if (*(volatile int *)&ctl->done) return; // (the same value in every CTA: nobody is left waiting)
+    const int nc = a.n_colors;
+    for (int c = tid; c <= nc; c += THREADS) cs[c] = a.color_start[c];
+    const int nrows = a.color_start[nc];
+    if (XS) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r)
+            for (int i = tid; i < nrows; i += THREADS) xs[r * nrows + i] = x[r * n + i];
+    }
+    barrier(); // (cluster: no CTA stores into a copy that is still being filled)
+    auto xread = [&](int col, int r) -> double { return XS ? xs[r * nrows + col] : x[r * n + col]; };
+    // the step after (c, p) in sweep order; true when it belongs to the next sweep
+    auto advance = [&](int &c, int &p) -> bool {
+        if (cs[c] + (p + 1) * STRIDE < cs[c + 1]) {
+            ++p;
+            return false;
+        }
+        p = 0;
+        if (++c == nc) {
+            c = 0;
+            return true;
+        }
+        return false;
+    };
+    auto load_a = [&](int c, int p) -> SmallRowA {
+        SmallRowA A;
+        const int i = cs[c] + p * STRIDE + rank * THREADS + tid;
+        if (i < cs[c + 1]) {
+            A.i = i;
+            A.k0 = rp[i];
+            A.len = rp[i + 1] - A.k0;
+        } else {
+            A.i = -1;
+            A.k0 = 0;
+            A.len = 0;
+        }
+        return A;
+    };
+    auto load_b = [&](const SmallRowA &A) -> SmallRowB<NRHS> {
+        SmallRowB<NRHS> B;
+        const bool row = A.i >= 0, shortrow = row && A.len <= GS_UNROLL;
+#pragma unroll
+        for (int j = 0; j < GS_UNROLL; ++j) {
+            B.cc[j] = (shortrow && j < A.len) ? ci[A.k0 + j] : 0;
+            B.vv[j] = (shortrow && j < A.len) ? va[A.k0 + j] : 0.0;
+        }
+        B.d = row ? dg[A.i] : 0.0;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            B.bb[r] = row ? b[r * n + A.i] : 0.0;
+            B.xo[r] = (row && !XS) ? x[r * n + A.i] : 0.0; // the row's own old value: nobody else writes it
+        }
+        return B;
+    };
+    double acc[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
+    auto compute = [&](const SmallRowA &A, const SmallRowB<NRHS> &B) {
+        if (A.i < 0) return;
+        double sig[NRHS];
+        if (A.len <= GS_UNROLL) {
+            double xg[GS_UNROLL][NRHS];
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j)
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) xg[j][r] = xread(B.cc[j], r); // padded positions read index 0 (valid)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j)
+                if (j < A.len) {
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(B.vv[j], xg[j][r]));
+                }
+        } else {
+            gs_row_sigma<NRHS>(ci + A.k0, va + A.k0, A.len, xread, sig);
+        }
+        if (B.d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                const double xn = __ddiv_rn(__dsub_rn(B.bb[r], sig[r]), B.d);
+                if (XS) {
+                    acc[r] += fabs(xn - xs[r * nrows + A.i]);
+#pragma unroll
+                    for (int q = 0; q < CSIZE; ++q) xs_of[q][r * nrows + A.i] = xn;
+                } else {
+                    acc[r] += fabs(xn - B.xo[r]);
+                    x[r * n + A.i] = xn;
+                }
+            }
+        }
+    };
+
+    int c0 = 0, p0 = 0, c1 = 0, p1 = 0, sweep = 0;
+    SmallRowA A0 = load_a(0, 0);
+    SmallRowB<NRHS> B0 = load_b(A0);
+    bool wrap1 = advance(c1, p1);
+    SmallRowA A1 = load_a(c1, p1);
+    for (;;) {
+        int c2 = c1, p2 = p1;
+        const bool wrap2 = advance(c2, p2);
+        const SmallRowA A2 = load_a(c2, p2);      // two steps ahead: row offsets
+        const SmallRowB<NRHS> B1 = load_b(A1);    // one step ahead: entries, diagonal, b
+        compute(A0, B0);
+        if (wrap1) { // the sweep is complete: fold the update norm in a fixed order, decide (v2 :356, :376-377)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                double t = acc[r];
+#pragma unroll
+                for (int d2 = 16; d2 > 0; d2 >>= 1) t += __shfl_down_sync(0xffffffffu, t, d2);
+                if (lane == 0) ws[r][wid] = t;
+                acc[r] = 0.0;
+            }
+            __syncthreads();
+            if (tid < NRHS) { // this CTA's share, warps in order -> slot `rank` of CTA 0
+                double t = 0.0;
+                for (int w = 0; w < THREADS / 32; ++w) t += ws[tid][w];
+                if constexpr (CSIZE > 1)
+                    cg::this_cluster().map_shared_rank(&part_s[0][0], 0)[rank * NRHS + tid] = t;
+                else
+                    part_s[0][tid] = t;
+            }
+            barrier();
+            if (rank == 0 && tid == 0) {
+                bool all_ok = true;
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < CSIZE; ++q) {
+                        partials[q * NRHS + r] = part_s[q][r];
+                        tot += part_s[q][r];
+                    }
+                    ctl->eps_last[r] = tot;
+                    if (tot > ctl->epsilon) all_ok = false;
+                }
+                const int cnt = ctl->sweeps + 1;
+                ctl->sweeps = cnt;
+                const int d = (all_ok || cnt >= ctl->max_iter) ? 1 : 0;
+                if (d) ctl->done = 1;
+                if constexpr (CSIZE > 1) {
+#pragma unroll
+                    for (int q = 0; q < CSIZE; ++q) *cg::this_cluster().map_shared_rank(&done_s, q) = d;
+                } else {
+                    done_s = d;
+                }
+            }
+            barrier();
+            if (done_s || ++sweep >= a.max_sweeps) break;
+        } else if (c1 != c0) {
+            barrier();
+        }
+        A0 = A1;
+        B0 = B1;
+        A1 = A2;
+        c0 = c1;
+        p0 = p1;
+        c1 = c2;
+        p1 = p2;
+        wrap1 = wrap2;
+    }
+    if (XS) { // all copies are equal after the last barrier: every CTA writes a share back
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r)
+            for (int i = rank * THREADS + tid; i < nrows; i += STRIDE) x[r * n + i] = xs[r * nrows + i];
+    }
+}
+
 // Is the system small enough for kernel 6 to be the better path?  (auto policy; GSB_SMALL_PERSISTENT=0|1 forces)
 bool gsb_small_auto(int64_t n_rows, int n_colors, int check_every) {
     static int env = -1;
@@ -146,7 +371,10 @@ bool gsb_small_auto(int64_t n_rows, int n_colors, int check_every) {
     return n_rows * (int64_t)n_colors < ((int64_t)1 << 20); // where the CUDA-graph path used to be chosen
 }
 
-#define GS_SMALL_SINGLE_ROWS 16384 // up to this many rows: ONE CTA of 1024 threads, barriers are __syncthreads
+#define GS_SMALL_SINGLE_ROWS 16384 // up to this many rows: ONE CTA, barriers are __syncthreads
+#define GS_SMALL_XS_BYTES_MAX (200 * 1024) // x of all right-hand sides in shared memory up to this size
+#define GS_SMALL_CLUSTER 8                 // CTAs of the cluster version (the portable maximum)
+#define GS_SMALL_CLUSTER_MIN_ROWS 1024     // largest colour: below this one CTA has the rows in a single pass anyway
 
 template <int NRHS>
 static int launch_small_t(const int *rp, const int *ci, const double *va, const double *dg, const double *b, double *x,
@@ -161,7 +389,72 @@ static int launch_small_t(const int *rp, const int *ci, const double *va, const 
     int largest = 1;
     for (int c = 0; c < n_colors; ++c) largest = largest > color_start[c + 1] - color_start[c] ? largest : color_start[c + 1] - color_start[c];
     if (color_start[n_colors] - color_start[0] <= GS_SMALL_SINGLE_ROWS) {
-        gs_small_persistent<NRHS, 1024><<<1, 1024, 0, st>>>(rp, ci, va, dg, b, x, ld, ctl, partials, a);
+        // GSB_SMALL_PIPE: 0 = the plain one-CTA loop, 1 = loads issued ahead (x in global memory), 2 = and x in shared
+        // memory when all right-hand sides fit, 3 (default) = and on a cluster of GS_SMALL_CLUSTER CTAs when a colour
+        // has enough rows to occupy it
+        static const int pipe = [] {
+            const char *e = getenv("GSB_SMALL_PIPE");
+            return e ? atoi(e) : 3;
+        }();
+        const size_t xs_bytes = sizeof(double) * (size_t)NRHS * (size_t)color_start[n_colors];
+        const int dev = gsb_current_device();
+        const bool dev_ok = dev >= 0 && dev < 64;
+        if (pipe >= 1 && color_start[0] == 0) {
+            constexpr int T = NRHS == 1 ? 1024 : 512; // registers: the rows in flight of k right-hand sides
+            constexpr int TC = 512, CS = GS_SMALL_CLUSTER; // cluster version: CS CTAs of TC threads
+            static int cluster_ok[64] = {0};                // per device: 0 unknown, 1 usable, -1 not
+            bool launched = false;
+            if (pipe >= 3 && xs_bytes <= GS_SMALL_XS_BYTES_MAX && largest >= GS_SMALL_CLUSTER_MIN_ROWS &&
+                !(dev_ok && cluster_ok[dev] < 0)) {
+                auto kern = gs_small_one_cta<NRHS, TC, true, CS>;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(CS);
+                cfg.blockDim = dim3(TC);
+                cfg.dynamicSmemBytes = xs_bytes;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = CS;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (!dev_ok || cluster_ok[dev] == 0) { // once per device: shared-memory limit, can a cluster be resident?
+                    int nclu = 0;
+                    cudaError_t e = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         GS_SMALL_XS_BYTES_MAX);
+                    cudaLaunchConfig_t probe = cfg;
+                    probe.dynamicSmemBytes = GS_SMALL_XS_BYTES_MAX;
+                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nclu, (const void *)kern, &probe);
+                    if (e != cudaSuccess) cudaGetLastError();
+                    if (dev_ok) cluster_ok[dev] = (e == cudaSuccess && nclu >= 1) ? 1 : -1;
+                    if (e != cudaSuccess || nclu < 1) cfg.numAttrs = 0; // -> the one-CTA version below
+                }
+                if (cfg.numAttrs == 1) {
+                    GSB_CUDA(cudaLaunchKernelEx(&cfg, kern, rp, ci, va, dg, b, x, ld, ctl, partials, a));
+                    launched = true;
+                    if (slots) *slots = CS;
+                }
+            }
+            if (launched) {
+                GSB_KERNEL_CHECK();
+                return GSB_OK;
+            }
+            if (pipe >= 2 && xs_bytes <= GS_SMALL_XS_BYTES_MAX) {
+                auto kern = gs_small_one_cta<NRHS, T, true, 1>;
+                static bool attr_set[64] = {false}; // per device
+                if (!dev_ok || !attr_set[dev]) {
+                    GSB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  GS_SMALL_XS_BYTES_MAX));
+                    if (dev_ok) attr_set[dev] = true;
+                }
+                kern<<<1, T, xs_bytes, st>>>(rp, ci, va, dg, b, x, ld, ctl, partials, a);
+            } else {
+                gs_small_one_cta<NRHS, T, false, 1><<<1, T, 0, st>>>(rp, ci, va, dg, b, x, ld, ctl, partials, a);
+            }
+        } else {
+            gs_small_persistent<NRHS, 1024><<<1, 1024, 0, st>>>(rp, ci, va, dg, b, x, ld, ctl, partials, a);
+        }
         GSB_KERNEL_CHECK();
         if (slots) *slots = 1;
         return GSB_OK;

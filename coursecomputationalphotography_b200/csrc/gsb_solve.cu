@@ -431,7 +431,11 @@ static int gs_host(gsb_matrix *m, const double *b, const double *x0, int nrhs, d
     GSB_TRY(db.alloc(n * nrhs));
     GSB_TRY(dx.alloc(n * nrhs));
     size_t bytes = sizeof(double) * (size_t)(n * nrhs);
-    if (!m->analyzed) {
+    static const int b_overlap = [] { // GSB_B_OVERLAP=0: upload b on the main stream (measurement aid)
+        const char *e = getenv("GSB_B_OVERLAP");
+        return e ? atoi(e) : 1;
+    }();
+    if (!m->analyzed && b_overlap) {
         // a freshly imported matrix: the ordering analysis and the launch plan (several device round trips) come
         // first in the solver core -- b travels on the copy stream meanwhile and the core waits for it only where it
         // first reads it (the previous solve's use of stage_b is over: every entry point ends with a stream sync)
