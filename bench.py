@@ -41,7 +41,7 @@ def parse():
     p.add_argument("--sweeps", type=int, default=100, help="GS sweeps per step")
     p.add_argument("--check-every", type=int, default=1)
     p.add_argument("--kernel", type=int, default=0)
-    p.add_argument("--e2e-steps", type=int, default=5)
+    p.add_argument("--e2e-steps", type=int, default=10)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--strips", action="store_true", help="N = 1 through the strip solver (measurement aid)")
@@ -351,8 +351,15 @@ def run_ours(args):
         t_e2e, t_imp, t_setup, steps_e2e = 0.0, 0.0, 0.0, max(1, args.e2e_steps)
         per_step, per_step_parts = [], []
         st_e = pkg.GsStats()
-        warm_e2e = max(args.warmup, 3)  # untimed: the first imports into a fresh handle allocate GB-sized buffers
-        for it in range(steps_e2e + warm_e2e):
+        # untimed warm-up: at least 3 steps (the first imports into a fresh handle allocate GB-sized buffers), then --
+        # on a shared box the first steps after the pinned allocations are erratic -- until two consecutive steps
+        # agree to 10 %, at most 12
+        warm_min, warm_max, warm_ms = max(args.warmup, 3), 12, []
+        while True:
+            timed = len(warm_ms) >= warm_min and (len(warm_ms) >= warm_max or
+                                                  abs(warm_ms[-1] - warm_ms[-2]) <= 0.1 * min(warm_ms[-2:]))
+            if timed and len(per_step) >= steps_e2e:
+                break
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             spe.initializeFromEigenRowMajor(va, len(va), ro_in, n, ci, n)
@@ -361,7 +368,9 @@ def run_ours(args):
                                               pkg._lib.ptr(x_pin), C.byref(st_e)), "gsb_gauss_seidel")
             torch.cuda.synchronize()
             t2 = time.perf_counter()
-            if it >= warm_e2e:
+            if not timed and not per_step:
+                warm_ms.append((t2 - t0) * 1e3)
+            else:
                 t_e2e += t2 - t0
                 t_imp += t1 - t0
                 t_setup += st_e.setup_ms
@@ -371,7 +380,7 @@ def run_ours(args):
         d2h = x_pin.nbytes
         e2e = {"value": nnz * ch * args.sweeps * steps_e2e / t_e2e / 1e9, "unit": "Gnnz/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / steps_e2e * 1e3,
-               "steps": steps_e2e, "warmup": warm_e2e, "ms_per_step_min": min(per_step), "ms_per_step_median": float(np.median(per_step)),
+               "steps": steps_e2e, "warmup": len(warm_ms), "warmup_ms": [round(v, 2) for v in warm_ms], "ms_per_step_min": min(per_step), "ms_per_step_median": float(np.median(per_step)),
                "per_step_ms": [round(v, 2) for v in per_step], "per_step_import_analysis_sweeps_ms": per_step_parts,
                "includes": "CSR import (H2D) + ordering analysis + b H2D + sweeps + x D2H",
                "import_ms": t_imp / steps_e2e * 1e3, "analysis_ms": t_setup / steps_e2e,

@@ -327,8 +327,9 @@ extern "C" int gsb_matrix_import_csr(gsb_matrix *m, const void *values, int n_va
     const int nr = n_row_off;
     GSB_TRY(alloc_layout(m, n_values, nr));
     m->n_cols = n_col_off;
-    DevBuf<int> off_in, first, cnt_in;
-    GSB_TRY(off_in.alloc(nr));
+    DevBuf<int> &off_in = m->scratch_rows;
+    DevBuf<int> first;
+    GSB_TRY(off_in.alloc((int64_t)nr + 1));
     GSB_TRY(first.alloc(1));
     size_t es = elem_size(m->vtype);
     if (n_values > 0) {

@@ -563,7 +563,9 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     return GSB_OK;
 }
 
-#define GS_FUSED_L2HINT_DEFAULT 3 // measured (r02_call9): 0 -> 0.836, 1 -> 0.848, 3 -> 0.855, 7 -> 0.856 of peak
+#define GS_FUSED_L2HINT_DEFAULT 59 // measured (r02_call9): 0 -> 0.836, 1 -> 0.848, 3 -> 0.855, 7 -> 0.856 of peak; calls 17 / 18,
+                                   // same box, alternating: 3 -> 0.834 / 0.833 / 0.842, 59 -> 0.857 / 0.838 / 0.848 (bits 8 + 16 + 32:
+                                   // +0.5 .. 2.7 %); bit 64 (gather windows) loses 2 % (67: 0.824 / 0.837, 123: 0.822 / 0.821)
 #define GS_FUSED_LEAD_DEFAULT 128 // beyond the dependency distance: long enough for the dependencies of a tile to be
                                   // finished when it comes up, short enough for the reuse to stay in L2 (measured)
 #define GS_FUSED_PUBK_DEFAULT 1 // measured: batching delays availability by a whole item of the owning CTA (-13 %)

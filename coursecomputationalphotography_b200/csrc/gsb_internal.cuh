@@ -152,6 +152,8 @@ struct gsb_matrix {
     DevBuf<double> xw, bw; // permuted x and b, nrhs * n_rows
     int ws_nrhs = 0;
     DevBuf<double> stage_b, stage_x; // natural-order device copies of host b / x for the host-pointer entry points
+    DevBuf<int> scratch_rows;        // n_rows + 1 ints of scratch for import / analysis (kept: a re-import of the same
+                                     // shape then makes no GB-scale cudaMalloc / cudaFree, each a device-wide sync)
     void *b_ready_event = nullptr;   // cudaEvent_t: stage_b's upload on the copy stream (host entry point, first solve)
     bool b_upload_pending = false;   // the solver core has to wait for b_ready_event before it reads stage_b
     DevBuf<double> partials;   // per-block partial sums of the stop rule

@@ -276,8 +276,9 @@ static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
     const int nb = (n + 255) / 256;
     GSB_TRY(m->perm.alloc(n));
     GSB_TRY(m->iperm.alloc(n));
-    DevBuf<int> flag, tot;
-    GSB_TRY(flag.alloc(n + 1));
+    DevBuf<int> &flag = m->scratch_rows;
+    DevBuf<int> tot;
+    GSB_TRY(flag.alloc((int64_t)n + 1));
     GSB_TRY(tot.alloc(1));
     int base = 0;
     for (int c = 0; c < m->n_colors; ++c) {

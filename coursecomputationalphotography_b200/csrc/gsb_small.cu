@@ -359,6 +359,255 @@ __global__ void __launch_bounds__(THREADS) gs_small_one_cta(const int *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster version, second generation: no fence and no cluster barrier inside the loop.
+//
+// ncu of gs_small_one_cta<.., CSIZE = 8> on configs[0] (profiles/r02_small_cluster_v1.txt): 3600 cycles per colour,
+// of which the row arithmetic is ~400 -- cluster.sync() is MEMBAR.ALL.GPU + ERRBAR + UCGABAR_ARV / _WAIT + CCTL.IVALL
+// (48 % of the stall samples), and the per-step bookkeeping is executed by 16 warps per SM of which 5 have rows.
+// Here the colour barrier is the data itself: a thread sends x_i to every CTA's copy with st.async (SASS STAS: an
+// asynchronous store into a peer's shared memory that completes transaction bytes on a peer mbarrier), every CTA
+// arms one mbarrier per colour phase with the bytes that phase delivers -- (rows of the colour) x NRHS x 8, the same
+// in every CTA -- and its threads wait on that mbarrier before they gather.  The hardware counts the bytes; nothing
+// is flushed, nobody waits for anybody's outstanding loads.  Two mbarriers alternate (a CTA can be at most one phase
+// ahead of another: it passes phase k only with every CTA's phase-k values, which a CTA sends only after it has
+// passed phase k-1), and one __syncthreads per phase keeps the threads of a CTA within a phase of each other, so that
+// the one-bit phase parity cannot be misread.  Write after read needs no extra step: the bytes of a thread's row
+// arrive only after that thread's gathers (its value depends on them), so when a CTA has seen phase k complete no
+// thread anywhere still reads the old values that phase k+1 overwrites.  Rows with a zero diagonal send their
+// unchanged value (the byte count stays exact).  The stop rule travels the same way: every CTA's partial to CTA 0's
+// `red` mbarrier, CTA 0's decision to every CTA's `done` mbarrier.
+// Arithmetic and its order are those of gs_row_sigma / gs_small_persistent: the same bits.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_b64(uint32_t addr, unsigned long long v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr), "l"(v), "r"(mbar)
+                 : "memory");
+}
+// bounded: a byte that never arrives (it cannot, short of a fault) raises ctl->error instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity, GsCtl *ctl) {
+    uint32_t done = 0;
+    for (int spins = 0; spins < (1 << 24); ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    ctl->error = 3;
+    return false;
+}
+
+template <int NRHS, int THREADS, int CSIZE>
+__global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                            const double *__restrict__ va, const double *__restrict__ dg,
+                                                            const double *__restrict__ b, double *x, int64_t n, GsCtl *ctl,
+                                                            double *partials, const GsbSmallArgs a) {
+    extern __shared__ __align__(16) double xs[]; // this CTA's copy of x: NRHS planes of `nrows` doubles
+    __shared__ double ws[NRHS][THREADS / 32];
+    __shared__ int cs[GS_SMALL_MAX_COLORS + 1];
+    __shared__ __align__(8) double part_s[CSIZE][NRHS]; // CTA 0: every CTA's share of the sweep's update norm
+    __shared__ __align__(8) unsigned long long done_s;
+    __shared__ __align__(8) uint64_t bar_x[2], bar_red, bar_done;
+    constexpr int STRIDE = CSIZE * THREADS; // rows per step
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    if (*(volatile int *)&ctl->done) return; // (the same value in every CTA: nobody is left waiting)
+    const int nc = a.n_colors;
+    for (int c = tid; c <= nc; c += THREADS) cs[c] = a.color_start[c];
+    const int nrows = a.color_start[nc];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r)
+        for (int i = tid; i < nrows; i += THREADS) xs[r * nrows + i] = x[r * n + i];
+    if (tid == 0) {
+        mbar_init(&bar_x[0], 1);
+        mbar_init(&bar_x[1], 1);
+        mbar_init(&bar_red, 1);
+        mbar_init(&bar_done, 1);
+    }
+    cluster.sync(); // copies filled and mbarriers initialised everywhere before the first remote store
+    uint32_t xs_of[CSIZE], bx_of[CSIZE][2]; // shared::cluster addresses of every CTA's copy and phase mbarriers
+#pragma unroll
+    for (int q = 0; q < CSIZE; ++q) {
+        xs_of[q] = mapa_u32(smem_u32(xs), q);
+        bx_of[q][0] = mapa_u32(smem_u32(&bar_x[0]), q);
+        bx_of[q][1] = mapa_u32(smem_u32(&bar_x[1]), q);
+    }
+    auto xread = [&](int col, int r) -> double { return xs[r * nrows + col]; };
+    auto advance = [&](int &c, int &p) -> bool { // the step after (c, p) in sweep order; true: it opens the next sweep
+        if (cs[c] + (p + 1) * STRIDE < cs[c + 1]) {
+            ++p;
+            return false;
+        }
+        p = 0;
+        if (++c == nc) {
+            c = 0;
+            return true;
+        }
+        return false;
+    };
+    auto load_a = [&](int c, int p) -> SmallRowA {
+        SmallRowA A;
+        const int i = cs[c] + p * STRIDE + rank * THREADS + tid;
+        if (i < cs[c + 1]) {
+            A.i = i;
+            A.k0 = rp[i];
+            A.len = rp[i + 1] - A.k0;
+        } else {
+            A.i = -1;
+            A.k0 = 0;
+            A.len = 0;
+        }
+        return A;
+    };
+    auto load_b = [&](const SmallRowA &A) -> SmallRowB<NRHS> {
+        SmallRowB<NRHS> B;
+        const bool row = A.i >= 0, shortrow = row && A.len <= GS_UNROLL;
+#pragma unroll
+        for (int j = 0; j < GS_UNROLL; ++j) {
+            B.cc[j] = (shortrow && j < A.len) ? ci[A.k0 + j] : 0;
+            B.vv[j] = (shortrow && j < A.len) ? va[A.k0 + j] : 0.0;
+        }
+        B.d = row ? dg[A.i] : 0.0;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            B.bb[r] = row ? b[r * n + A.i] : 0.0;
+            B.xo[r] = 0.0;
+        }
+        return B;
+    };
+    double acc[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
+    int phase = 0; // colour phases since the start of the launch: mbarrier bar_x[phase & 1], parity (phase >> 1) & 1
+    auto compute = [&](const SmallRowA &A, const SmallRowB<NRHS> &B) {
+        if (A.i < 0) return;
+        double sig[NRHS];
+        if (A.len <= GS_UNROLL) {
+            double xg[GS_UNROLL][NRHS];
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j)
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) xg[j][r] = xread(B.cc[j], r); // padded positions read index 0 (valid)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
+#pragma unroll
+            for (int j = 0; j < GS_UNROLL; ++j)
+                if (j < A.len) {
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(B.vv[j], xg[j][r]));
+                }
+        } else {
+            gs_row_sigma<NRHS>(ci + A.k0, va + A.k0, A.len, xread, sig);
+        }
+        const uint32_t pb = (uint32_t)phase & 1u;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            const double xo = xs[r * nrows + A.i];
+            double xn = xo; // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363) -- and sent as it is
+            if (B.d != 0.0) {
+                xn = __ddiv_rn(__dsub_rn(B.bb[r], sig[r]), B.d);
+                acc[r] += fabs(xn - xo);
+            }
+            const uint32_t off = (uint32_t)(r * nrows + A.i) * 8u;
+#pragma unroll
+            for (int q = 0; q < CSIZE; ++q)
+                st_async_b64(xs_of[q] + off, (unsigned long long)__double_as_longlong(xn), pb ? bx_of[q][1] : bx_of[q][0]);
+        }
+    };
+
+    int c0 = 0, p0 = 0, c1 = 0, p1 = 0, sweep = 0;
+    SmallRowA A0 = load_a(0, 0);
+    SmallRowB<NRHS> B0 = load_b(A0);
+    bool wrap1 = advance(c1, p1);
+    SmallRowA A1 = load_a(c1, p1);
+    for (;;) {
+        if (p0 == 0) { // a colour phase opens: every thread of the CTA has passed the previous phase's wait
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&bar_x[phase & 1], (uint32_t)(cs[c0 + 1] - cs[c0]) * (uint32_t)(NRHS * 8));
+                if (c0 == 0) { // ... and a sweep: the stop rule's two mbarriers
+                    if (rank == 0) mbar_expect_tx(&bar_red, (uint32_t)(CSIZE * NRHS * 8));
+                    mbar_expect_tx(&bar_done, 8u);
+                }
+            }
+        }
+        int c2 = c1, p2 = p1;
+        const bool wrap2 = advance(c2, p2);
+        const SmallRowA A2 = load_a(c2, p2);   // two steps ahead: row offsets
+        const SmallRowB<NRHS> B1 = load_b(A1); // one step ahead: entries, diagonal, b
+        compute(A0, B0);
+        if (wrap1 || c1 != c0) { // the colour is complete once its bytes are: every CTA's values of it are in this copy
+            if (!mbar_wait_bounded(&bar_x[phase & 1], (uint32_t)(phase >> 1) & 1u, ctl)) return;
+            ++phase;
+        }
+        if (wrap1) { // the sweep is complete: fold the update norm in a fixed order, decide (v2 :356, :376-377)
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) {
+                double t = acc[r];
+#pragma unroll
+                for (int d2 = 16; d2 > 0; d2 >>= 1) t += __shfl_down_sync(0xffffffffu, t, d2);
+                if (lane == 0) ws[r][wid] = t;
+                acc[r] = 0.0;
+            }
+            __syncthreads();
+            if (tid < NRHS) { // this CTA's share, warps in order -> slot `rank` of CTA 0
+                double t = 0.0;
+                for (int w = 0; w < THREADS / 32; ++w) t += ws[tid][w];
+                st_async_b64(mapa_u32(smem_u32(&part_s[rank][tid]), 0), (unsigned long long)__double_as_longlong(t),
+                             mapa_u32(smem_u32(&bar_red), 0));
+            }
+            const uint32_t sp = (uint32_t)sweep & 1u;
+            if (rank == 0 && tid == 0) {
+                if (!mbar_wait_bounded(&bar_red, sp, ctl)) return;
+                bool all_ok = true;
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < CSIZE; ++q) {
+                        partials[q * NRHS + r] = part_s[q][r];
+                        tot += part_s[q][r];
+                    }
+                    ctl->eps_last[r] = tot;
+                    if (tot > ctl->epsilon) all_ok = false;
+                }
+                const int cnt = ctl->sweeps + 1;
+                ctl->sweeps = cnt;
+                const int d = (all_ok || cnt >= ctl->max_iter) ? 1 : 0;
+                if (d) ctl->done = 1;
+#pragma unroll
+                for (int q = 0; q < CSIZE; ++q)
+                    st_async_b64(mapa_u32(smem_u32(&done_s), q), (unsigned long long)d, mapa_u32(smem_u32(&bar_done), q));
+            }
+            if (!mbar_wait_bounded(&bar_done, sp, ctl)) return;
+            if (done_s != 0ull || ++sweep >= a.max_sweeps) break;
+        }
+        A0 = A1;
+        B0 = B1;
+        A1 = A2;
+        c0 = c1;
+        p0 = p1;
+        c1 = c2;
+        p1 = p2;
+        wrap1 = wrap2;
+    }
+    // all copies are equal (every phase has been waited for): every CTA writes a share back
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r)
+        for (int i = rank * THREADS + tid; i < nrows; i += STRIDE) x[r * n + i] = xs[r * nrows + i];
+    cluster.sync(); // no CTA leaves while a peer could still be sending to it
+}
+
 // Is the system small enough for kernel 6 to be the better path?  (auto policy; GSB_SMALL_PERSISTENT=0|1 forces)
 bool gsb_small_auto(int64_t n_rows, int n_colors, int check_every) {
     static int env = -1;
@@ -391,7 +640,7 @@ static int launch_small_t(const int *rp, const int *ci, const double *va, const 
     if (color_start[n_colors] - color_start[0] <= GS_SMALL_SINGLE_ROWS) {
         // GSB_SMALL_PIPE: 0 = the plain one-CTA loop, 1 = loads issued ahead (x in global memory), 2 = and x in shared
         // memory when all right-hand sides fit, 3 (default) = and on a cluster of GS_SMALL_CLUSTER CTAs when a colour
-        // has enough rows to occupy it
+        // has enough rows to occupy it (gs_small_cluster: st.async + mbarriers); 4 = the cluster.sync() version of that
         static const int pipe = [] {
             const char *e = getenv("GSB_SMALL_PIPE");
             return e ? atoi(e) : 3;
@@ -401,12 +650,12 @@ static int launch_small_t(const int *rp, const int *ci, const double *va, const 
         const bool dev_ok = dev >= 0 && dev < 64;
         if (pipe >= 1 && color_start[0] == 0) {
             constexpr int T = NRHS == 1 ? 1024 : 512; // registers: the rows in flight of k right-hand sides
-            constexpr int TC = 512, CS = GS_SMALL_CLUSTER; // cluster version: CS CTAs of TC threads
+            constexpr int TC = 256, CS = GS_SMALL_CLUSTER; // cluster version: CS CTAs of TC threads
             static int cluster_ok[64] = {0};                // per device: 0 unknown, 1 usable, -1 not
             bool launched = false;
             if (pipe >= 3 && xs_bytes <= GS_SMALL_XS_BYTES_MAX && largest >= GS_SMALL_CLUSTER_MIN_ROWS &&
                 !(dev_ok && cluster_ok[dev] < 0)) {
-                auto kern = gs_small_one_cta<NRHS, TC, true, CS>;
+                auto kern = pipe == 4 ? gs_small_one_cta<NRHS, TC, true, CS> : gs_small_cluster<NRHS, TC, CS>;
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(CS);
                 cfg.blockDim = dim3(TC);
