@@ -22,6 +22,9 @@ gsb_matrix::~gsb_matrix() {
     cg_state_host = nullptr;
     if (b_ready_event) cudaEventDestroy((cudaEvent_t)b_ready_event);
     b_ready_event = nullptr;
+    if (ev_t0) cudaEventDestroy((cudaEvent_t)ev_t0);
+    if (ev_t1) cudaEventDestroy((cudaEvent_t)ev_t1);
+    ev_t0 = ev_t1 = nullptr;
 }
 
 extern "C" int gsb_matrix_create(gsb_matrix **out, int vtype) {

@@ -18,9 +18,10 @@
 // Dot products are fixed-order tree reductions (the reference's transform_reduce leaves the order unspecified), so
 // iterates agree with the reference to rounding, not bit for bit; run to run they are identical.
 // Workspaces stay with the matrix handle: repeated solves (three channels, every frame) allocate nothing.
-#include "gsb_internal.cuh"
+#include "gsb_ring.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #define CG_THREADS 256
 #define CG_UNROLL 6      // rows up to this many entries take the gather-prefetch path
@@ -186,6 +187,162 @@ __global__ void __launch_bounds__(CG_THREADS) cg_spmv_dot(const double *__restri
     }
 }
 
+// The same product as a PERSISTENT kernel with a two-stage ring of bulk copies (the structure of the colour-phase
+// kernels, gsb_phase.cu): cg_spmv_dot loads a tile's span, waits, computes, waits -- every tile pays two exposed
+// round trips to HBM and the kernel reaches half of the copy bandwidth at 4096^2 (ncu launch list, round 2 call 20:
+// 605 us for 1.95 GB).  Here thread 0 issues tile j+2's four spans (values, columns, row_begin, row_nnz: each one
+// contiguous piece of the slack CSR, 16-byte aligned by rounding its ends outwards) as cp.async.bulk copies on the
+// stage's mbarrier while the CTA computes tile j; the tile boundaries of the tile after that are fetched into registers an
+// iteration ahead, so that the issue never waits for a load.  Tiles that do not fit the stage (long rows) and the
+// last tile (its aligned ends could leave the arrays) are read row per thread as before.  Same arithmetic, same
+// storage order: bit-exact with applyToVector and with cg_spmv_dot.
+struct CgStage {
+    int v_off, c_off, rb_off, rn_off, hdr_off, bytes;
+};
+__host__ __device__ inline CgStage cg_stage_layout() {
+    CgStage L;
+    L.v_off = 0;
+    L.c_off = L.v_off + (CG_SPAN_CAP + 2) * 8;
+    L.rb_off = L.c_off + (CG_SPAN_CAP + 8) * 4;
+    L.rn_off = L.rb_off + CG_THREADS * 4;
+    L.hdr_off = L.rn_off + CG_THREADS * 4;
+    L.bytes = L.hdr_off + 16;
+    return L;
+}
+
+template <int NRHS, bool DOT>
+__global__ void __launch_bounds__(CG_THREADS, 4) cg_spmv_ring(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                              const int *__restrict__ row_begin,
+                                                              const int *__restrict__ row_nnz, int n_rows, int64_t store,
+                                                              const double *__restrict__ in, double *__restrict__ out,
+                                                              int64_t ld, CgState *st, double *__restrict__ partials) {
+    extern __shared__ __align__(128) unsigned char cg_smem[];
+    __shared__ double ws[NRHS][CG_THREADS / 32];
+    const CgStage L = cg_stage_layout();
+    uint64_t *full = reinterpret_cast<uint64_t *>(cg_smem);
+    unsigned char *stage0 = cg_smem + 64;
+    const int tid = threadIdx.x, bid = blockIdx.x, gsz = gridDim.x;
+    if (DOT && *(volatile int *)&st->all_done) return;
+    bool live[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) live[r] = !DOT || !st->done[r];
+    double dot[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) dot[r] = 0.0;
+    const int ntiles = (n_rows + CG_THREADS - 1) / CG_THREADS;
+    const int my_tiles = bid < ntiles ? (ntiles - bid + gsz - 1) / gsz : 0;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+    }
+    __syncthreads();
+    // thread 0: CSR offsets at the two ends of the tile it will issue next (fetched an iteration ahead)
+    int64_t nk0 = 0, nk1 = 0;
+    auto fetch_bounds = [&](int j) {
+        if (j >= my_tiles) return;
+        const int r0 = (bid + j * gsz) * CG_THREADS, r1 = r0 + CG_THREADS;
+        nk0 = row_begin[r0];
+        nk1 = r1 < n_rows ? (int64_t)row_begin[r1] : store;
+    };
+    auto issue = [&](int j, int s) { // thread 0
+        const int t = bid + j * gsz, r0 = t * CG_THREADS;
+        unsigned char *sp = stage0 + (size_t)s * L.bytes;
+        int *hdr = reinterpret_cast<int *>(sp + L.hdr_off);
+        const int64_t k0 = nk0, k1 = nk1;
+        const int64_t kv0 = k0 & ~(int64_t)1, kv1 = (k1 + 1) & ~(int64_t)1;
+        const int64_t kc0 = k0 & ~(int64_t)3, kc1 = (k1 + 3) & ~(int64_t)3;
+        const bool staged = t != ntiles - 1 && k1 - k0 <= CG_SPAN_CAP && kc1 <= store && k1 >= k0;
+        hdr[0] = staged ? 1 : 0;
+        if (staged) {
+            const uint32_t bytes_v = (uint32_t)(kv1 - kv0) * 8u, bytes_c = (uint32_t)(kc1 - kc0) * 4u;
+            const uint32_t bytes_r = CG_THREADS * 4u;
+            mbar_expect_tx(&full[s], bytes_v + bytes_c + 2u * bytes_r);
+            if (bytes_v) bulk_g2s(sp + L.v_off, vals + kv0, bytes_v, &full[s]);
+            if (bytes_c) bulk_g2s(sp + L.c_off, cols + kc0, bytes_c, &full[s]);
+            bulk_g2s(sp + L.rb_off, row_begin + r0, bytes_r, &full[s]);
+            bulk_g2s(sp + L.rn_off, row_nnz + r0, bytes_r, &full[s]);
+        } else {
+            mbar_expect_tx(&full[s], 0u); // nothing to wait for: the rows read global memory
+        }
+    };
+    if (tid == 0) {
+        fetch_bounds(0);
+        if (my_tiles > 0) issue(0, 0);
+        fetch_bounds(1);
+        if (my_tiles > 1) issue(1, 1);
+        fetch_bounds(2);
+    }
+    for (int j = 0; j < my_tiles; ++j) {
+        const int s = j & 1;
+        const unsigned char *sp = stage0 + (size_t)s * L.bytes;
+        mbar_wait(&full[s], (uint32_t)(j >> 1) & 1u);
+        const bool staged = reinterpret_cast<const int *>(sp + L.hdr_off)[0] != 0;
+        const int t = bid + j * gsz, r0 = t * CG_THREADS, r1 = min(r0 + CG_THREADS, n_rows);
+        const int i = r0 + tid;
+        if (i < r1) {
+            const int64_t kb = staged ? (int64_t)reinterpret_cast<const int *>(sp + L.rb_off)[tid] : (int64_t)row_begin[i];
+            const int len = staged ? reinterpret_cast<const int *>(sp + L.rn_off)[tid] : row_nnz[i];
+            // the stage holds vals[kv0 ..) and cols[kc0 ..): index them by the global offset k
+            const int64_t k0 = staged ? (int64_t)reinterpret_cast<const int *>(sp + L.rb_off)[0] : 0;
+            const double *v_s = reinterpret_cast<const double *>(sp + L.v_off) - (k0 & ~(int64_t)1);
+            const int *c_s = reinterpret_cast<const int *>(sp + L.c_off) - (k0 & ~(int64_t)3);
+            double sum[NRHS];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) sum[r] = 0.0;
+            if (len <= CG_UNROLL) {
+                int cc[CG_UNROLL];
+                double vv[CG_UNROLL], xg[CG_UNROLL][NRHS];
+#pragma unroll
+                for (int q = 0; q < CG_UNROLL; ++q) {
+                    const bool in_row = q < len;
+                    cc[q] = in_row ? (staged ? c_s[kb + q] : cols[kb + q]) : 0;
+                    vv[q] = in_row ? (staged ? v_s[kb + q] : vals[kb + q]) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < CG_UNROLL; ++q)
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) xg[q][r] = live[r] ? in[r * ld + cc[q]] : 0.0;
+#pragma unroll
+                for (int q = 0; q < CG_UNROLL; ++q)
+                    if (q < len) {
+#pragma unroll
+                        for (int r = 0; r < NRHS; ++r) sum[r] = __dadd_rn(sum[r], __dmul_rn(vv[q], xg[q][r]));
+                    }
+            } else {
+                for (int q = 0; q < len; ++q) {
+                    const double v = staged ? v_s[kb + q] : vals[kb + q];
+                    const int c = staged ? c_s[kb + q] : cols[kb + q];
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r)
+                        if (live[r]) sum[r] = __dadd_rn(sum[r], __dmul_rn(v, in[r * ld + c]));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+                if (live[r]) {
+                    out[r * ld + i] = sum[r];
+                    if (DOT) dot[r] += in[r * ld + i] * sum[r];
+                }
+        }
+        __syncthreads(); // every row of the tile has read its stage
+        if (tid == 0) {
+            if (j + 2 < my_tiles) issue(j + 2, s);
+            fetch_bounds(j + 3);
+        }
+    }
+    if (DOT) {
+        if (cg_block_partial<NRHS>(dot, partials, &st->ticket[0], ws)) {
+            double sum[NRHS];
+            cg_fold<NRHS>(partials, gridDim.x, sum, ws);
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r)
+                    if (!st->done[r]) st->alpha[r] = st->rho[r] / sum[r]; // v2 :420-421 / :517-518
+            }
+        }
+    }
+}
+
 // start-up: r = b - A x0 (Ax0 in `ax`, or absent: r = b), z = M^-1 r (inv != null), p = z, rho = z.r
 template <int NRHS>
 __global__ void __launch_bounds__(CG_THREADS) cg_start(const double *__restrict__ b, const double *__restrict__ ax,
@@ -267,8 +424,10 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_xr(double *__restrict__ 
                         st->beta[q] = rho_new / st->rho[q]; // v2 :426 / :528
                         st->rho[q] = rho_new;
                         st->cnt[q] += 1;
-                        // (the p update below still runs for this right-hand side: the reference updates p, bumps
-                        // cnt and only then tests cnt < max_iteration)
+                        // the reference updates p, bumps cnt and only then tests cnt < max_iteration: a right-hand side
+                        // that has used up its iterations stops here -- its last p update is skipped, which nothing
+                        // observes (x and cnt are final)
+                        if (st->cnt[q] >= st->max_iter) st->done[q] = 1;
                     }
                 }
                 all = all && st->done[q];
@@ -296,17 +455,6 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_p(double *__restrict__ p
             if (live[q]) p[q * ld + i] = __dadd_rn(z[q * ld + i], __dmul_rn(beta[q], p[q * ld + i])); // v2 :427 / :530
     }
 }
-// after cg_update_p of every iteration (one thread): a right-hand side whose counter reached max_iteration stops
-__global__ void cg_check_max(CgState *st) {
-    if (st->all_done) return;
-    int all = 1;
-    for (int q = 0; q < GSB_MAX_RHS; ++q) {
-        if (!st->done[q] && st->cnt[q] >= st->max_iter) st->done[q] = 1;
-        all = all && st->done[q];
-    }
-    st->all_done = all;
-}
-
 // extractDiagnolColInv (v2 :472-491): 1/a_ii where the diagonal is stored and nonzero, else 1
 __global__ void __launch_bounds__(256) cg_inv_diag(const double *__restrict__ vals, const int *__restrict__ cols,
                                                    const int *__restrict__ row_begin,
@@ -340,6 +488,33 @@ static int cg_common_check(gsb_matrix *m, const double *b, double *x, int nrhs) 
     return gsb_set_device(m->device);
 }
 
+// A p (+ p.Ap): the ring kernel when the rows are short enough for its stage to be of use (GSB_CG_RING=0: never)
+template <int NRHS, bool DOT>
+static int cg_launch_spmv(gsb_matrix *m, const double *in, double *out, int64_t ld, CgState *ds, int grid_s, int *grid_ring,
+                          cudaStream_t st) {
+    static const int ring_env = [] {
+        const char *e = getenv("GSB_CG_RING");
+        return e ? atoi(e) : 1;
+    }();
+    const int64_t n = m->n_rows;
+    if (ring_env && n >= 4 * CG_THREADS && m->store <= (int64_t)n * (CG_SPAN_CAP / CG_THREADS)) {
+        auto kern = cg_spmv_ring<NRHS, DOT>;
+        const int smem = 64 + 2 * cg_stage_layout().bytes;
+        int per_sm = 1;
+        GSB_TRY(gsb_kernel_occupancy((const void *)kern, smem, &per_sm, CG_THREADS));
+        const int ntiles = (int)((n + CG_THREADS - 1) / CG_THREADS);
+        int grid = gsb_sm_count() * per_sm;
+        if (grid > ntiles) grid = ntiles;
+        if (grid > *grid_ring) grid = *grid_ring; // (the partials buffer was sized for this many CTAs)
+        kern<<<grid, CG_THREADS, smem, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, m->n_rows, m->store, in, out, ld,
+                                            ds, m->cg_partials.p);
+        return GSB_OK;
+    }
+    cg_spmv_dot<NRHS, DOT><<<grid_s, CG_THREADS, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, m->n_rows, m->store,
+                                                         in, out, ld, ds, m->cg_partials.p);
+    return GSB_OK;
+}
+
 template <int NRHS>
 static int cg_run(gsb_matrix *m, const double *b_dev, const double *x0_dev, bool jacobi, double epsilon,
                   int max_iteration, double *x_dev, int *iters) {
@@ -349,6 +524,7 @@ static int cg_run(gsb_matrix *m, const double *b_dev, const double *x0_dev, bool
     const int grid_v = gsb_blocks_for(n, CG_THREADS * 4, gsb_sm_count() * 8);
     const int ntiles = (int)((n + CG_THREADS - 1) / CG_THREADS);
     const int grid_s = ntiles < gsb_sm_count() * 8 ? ntiles : gsb_sm_count() * 8;
+    int grid_ring = grid_v > grid_s ? grid_v : grid_s; // upper bound of the ring kernel's grid (slots in cg_partials)
     // workspace with the handle: r, p, Ap (, z, inv) + partials + state
     const int nvec = jacobi ? 4 : 3;
     GSB_TRY(m->cg_ws.alloc((int64_t)nvec * NRHS * n + (jacobi ? n : 0)));
@@ -370,8 +546,7 @@ static int cg_run(gsb_matrix *m, const double *b_dev, const double *x0_dev, bool
     const size_t bytes = sizeof(double) * (size_t)(NRHS * n);
     if (x0_dev) {
         if (x0_dev != x_dev) GSB_CUDA(cudaMemcpyAsync(x_dev, x0_dev, bytes, cudaMemcpyDeviceToDevice, st));
-        cg_spmv_dot<NRHS, false><<<grid_s, CG_THREADS, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p, m->n_rows,
-                                                               m->store, x_dev, ap, ld, ds, m->cg_partials.p);
+        GSB_TRY((cg_launch_spmv<NRHS, false>(m, x_dev, ap, ld, ds, grid_s, &grid_ring, st)));
         GSB_KERNEL_CHECK();
     } else {
         GSB_CUDA(cudaMemsetAsync(x_dev, 0, bytes, st)); // v2 :398-403: zero start
@@ -387,21 +562,19 @@ static int cg_run(gsb_matrix *m, const double *b_dev, const double *x0_dev, bool
     const int batch = 16;
     while (!hs->all_done) {
         for (int k = 0; k < batch; ++k) {
-            cg_spmv_dot<NRHS, true><<<grid_s, CG_THREADS, 0, st>>>(m->vals(), m->cols.p, m->row_begin.p, m->row_nnz.p,
-                                                                  m->n_rows, m->store, p, ap, ld, ds, m->cg_partials.p);
+            GSB_TRY((cg_launch_spmv<NRHS, true>(m, p, ap, ld, ds, grid_s, &grid_ring, st)));
             if (jacobi)
                 cg_update_xr<NRHS, true><<<grid_v, CG_THREADS, 0, st>>>(x_dev, r, p, ap, inv, z, n, ld, ds, m->cg_partials.p);
             else
                 cg_update_xr<NRHS, false><<<grid_v, CG_THREADS, 0, st>>>(x_dev, r, p, ap, nullptr, nullptr, n, ld, ds,
                                                                         m->cg_partials.p);
             cg_update_p<NRHS><<<grid_v, CG_THREADS, 0, st>>>(p, z, n, ld, ds);
-            cg_check_max<<<1, 1, 0, st>>>(ds);
         }
         GSB_KERNEL_CHECK();
         issued += batch;
         GSB_CUDA(cudaMemcpyAsync(hs, ds, sizeof(CgState), cudaMemcpyDeviceToHost, st));
         GSB_CUDA(cudaStreamSynchronize(st));
-        if (issued > max_iteration + batch) break; // cannot happen (cg_check_max stops at max_iteration)
+        if (issued > max_iteration + batch) break; // cannot happen (cg_update_xr stops a right-hand side at max_iteration)
     }
     GSB_CUDA(cudaStreamSynchronize(st));
     if (iters)

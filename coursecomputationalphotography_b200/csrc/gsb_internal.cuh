@@ -154,6 +154,7 @@ struct gsb_matrix {
     DevBuf<double> stage_b, stage_x; // natural-order device copies of host b / x for the host-pointer entry points
     DevBuf<int> scratch_rows;        // n_rows + 1 ints of scratch for import / analysis (kept: a re-import of the same
                                      // shape then makes no GB-scale cudaMalloc / cudaFree, each a device-wide sync)
+    void *ev_t0 = nullptr, *ev_t1 = nullptr; // cudaEvent_t pair timing the sweep loop (kept: a small solve is a few hundred us)
     void *b_ready_event = nullptr;   // cudaEvent_t: stage_b's upload on the copy stream (host entry point, first solve)
     bool b_upload_pending = false;   // the solver core has to wait for b_ready_event before it reads stage_b
     DevBuf<double> partials;   // per-block partial sums of the stop rule

@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(THREADS) gs_small_persistent(const int *__rest
 // them in rank order and writes its decision into every CTA.
 // Arithmetic and its order are those of gs_row_sigma / gs_small_persistent: the same bits.
 struct SmallRowA {
-    int i, k0, len; // i < 0: this thread has no row in the step
+    int i, k0, k1; // i < 0: this thread has no row in the step.  (The row length is k1 - k0, formed where it is used:
+                   // an in-order warp stalls at the first instruction that consumes a load.)
+    __device__ __forceinline__ int len() const { return k1 - k0; }
 };
 template <int NRHS>
 struct SmallRowB {
@@ -221,21 +223,21 @@ __global__ void __launch_bounds__(THREADS) gs_small_one_cta(const int *__restric
         if (i < cs[c + 1]) {
             A.i = i;
             A.k0 = rp[i];
-            A.len = rp[i + 1] - A.k0;
+            A.k1 = rp[i + 1];
         } else {
             A.i = -1;
             A.k0 = 0;
-            A.len = 0;
+            A.k1 = 0;
         }
         return A;
     };
     auto load_b = [&](const SmallRowA &A) -> SmallRowB<NRHS> {
         SmallRowB<NRHS> B;
-        const bool row = A.i >= 0, shortrow = row && A.len <= GS_UNROLL;
+        const bool row = A.i >= 0, shortrow = row && A.len() <= GS_UNROLL;
 #pragma unroll
         for (int j = 0; j < GS_UNROLL; ++j) {
-            B.cc[j] = (shortrow && j < A.len) ? ci[A.k0 + j] : 0;
-            B.vv[j] = (shortrow && j < A.len) ? va[A.k0 + j] : 0.0;
+            B.cc[j] = (shortrow && j < A.len()) ? ci[A.k0 + j] : 0;
+            B.vv[j] = (shortrow && j < A.len()) ? va[A.k0 + j] : 0.0;
         }
         B.d = row ? dg[A.i] : 0.0;
 #pragma unroll
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(THREADS) gs_small_one_cta(const int *__restric
     auto compute = [&](const SmallRowA &A, const SmallRowB<NRHS> &B) {
         if (A.i < 0) return;
         double sig[NRHS];
-        if (A.len <= GS_UNROLL) {
+        if (A.len() <= GS_UNROLL) {
             double xg[GS_UNROLL][NRHS];
 #pragma unroll
             for (int j = 0; j < GS_UNROLL; ++j)
@@ -261,12 +263,12 @@ __global__ void __launch_bounds__(THREADS) gs_small_one_cta(const int *__restric
             for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
 #pragma unroll
             for (int j = 0; j < GS_UNROLL; ++j)
-                if (j < A.len) {
+                if (j < A.len()) {
 #pragma unroll
                     for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(B.vv[j], xg[j][r]));
                 }
         } else {
-            gs_row_sigma<NRHS>(ci + A.k0, va + A.k0, A.len, xread, sig);
+            gs_row_sigma<NRHS>(ci + A.k0, va + A.k0, A.len(), xread, sig);
         }
         if (B.d != 0.0) { // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363)
 #pragma unroll
@@ -461,21 +463,21 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
         if (i < cs[c + 1]) {
             A.i = i;
             A.k0 = rp[i];
-            A.len = rp[i + 1] - A.k0;
+            A.k1 = rp[i + 1];
         } else {
             A.i = -1;
             A.k0 = 0;
-            A.len = 0;
+            A.k1 = 0;
         }
         return A;
     };
     auto load_b = [&](const SmallRowA &A) -> SmallRowB<NRHS> {
         SmallRowB<NRHS> B;
-        const bool row = A.i >= 0, shortrow = row && A.len <= GS_UNROLL;
+        const bool row = A.i >= 0, shortrow = row && A.len() <= GS_UNROLL;
 #pragma unroll
         for (int j = 0; j < GS_UNROLL; ++j) {
-            B.cc[j] = (shortrow && j < A.len) ? ci[A.k0 + j] : 0;
-            B.vv[j] = (shortrow && j < A.len) ? va[A.k0 + j] : 0.0;
+            B.cc[j] = (shortrow && j < A.len()) ? ci[A.k0 + j] : 0;
+            B.vv[j] = (shortrow && j < A.len()) ? va[A.k0 + j] : 0.0;
         }
         B.d = row ? dg[A.i] : 0.0;
 #pragma unroll
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
     auto compute = [&](const SmallRowA &A, const SmallRowB<NRHS> &B) {
         if (A.i < 0) return;
         double sig[NRHS];
-        if (A.len <= GS_UNROLL) {
+        if (A.len() <= GS_UNROLL) {
             double xg[GS_UNROLL][NRHS];
 #pragma unroll
             for (int j = 0; j < GS_UNROLL; ++j)
@@ -502,12 +504,12 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
             for (int r = 0; r < NRHS; ++r) sig[r] = 0.0;
 #pragma unroll
             for (int j = 0; j < GS_UNROLL; ++j)
-                if (j < A.len) {
+                if (j < A.len()) {
 #pragma unroll
                     for (int r = 0; r < NRHS; ++r) sig[r] = __dadd_rn(sig[r], __dmul_rn(B.vv[j], xg[j][r]));
                 }
         } else {
-            gs_row_sigma<NRHS>(ci + A.k0, va + A.k0, A.len, xread, sig);
+            gs_row_sigma<NRHS>(ci + A.k0, va + A.k0, A.len(), xread, sig);
         }
         const uint32_t pb = (uint32_t)phase & 1u;
 #pragma unroll

@@ -215,9 +215,14 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         GSB_CUDA(cudaMemsetAsync(m->small_bar.p, 0, 2 * sizeof(unsigned), st)); // (a solve that gave up may have left it mid-count)
     }
 
-    cudaEvent_t ev0, ev1;
-    GSB_CUDA(cudaEventCreate(&ev0));
-    GSB_CUDA(cudaEventCreate(&ev1));
+    if (!m->ev_t0) {
+        cudaEvent_t a = nullptr, b2 = nullptr;
+        GSB_CUDA(cudaEventCreate(&a));
+        m->ev_t0 = a;
+        GSB_CUDA(cudaEventCreate(&b2));
+        m->ev_t1 = b2;
+    }
+    cudaEvent_t ev0 = (cudaEvent_t)m->ev_t0, ev1 = (cudaEvent_t)m->ev_t1;
     GSB_CUDA(cudaEventRecord(ev0, st));
     int status = GSB_OK;
     int issued = 0;
@@ -297,8 +302,6 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     cudaEventSynchronize(ev1);
     float solve_ms = 0.f;
     cudaEventElapsedTime(&solve_ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     if (status != GSB_OK) return status;
 
     scatter_perm<<<nbv, 256, 0, st>>>(m->xw.p, m->perm.p, n, ld, nrhs, x_dev);

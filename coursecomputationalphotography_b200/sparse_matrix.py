@@ -364,13 +364,16 @@ class SparseMatrix:
         self.last_iters = it.value
         return x
 
-    def conjugateGradientMulti(self, b, epsilon=1e-16, max_iteration=1000, initialize=None):
+    def conjugateGradientMulti(self, b, epsilon=1e-16, max_iteration=1000, initialize=None, out=None):
         """EXTENSION: b (nrhs, n), nrhs <= 4: the right-hand sides share every pass over the matrix; each stops on its
-        own.  self.last_iters = list of the nrhs loop counts."""
+        own.  self.last_iters = list of the nrhs loop counts.  `out`: a C-contiguous float64 array of b's shape to
+        receive x (e.g. page-locked memory, so that the download runs at PCIe speed)."""
         self._push()
         b = np.ascontiguousarray(b, np.float64)
         nrhs = 1 if b.ndim == 1 else b.shape[0]
-        x = np.empty_like(b)
+        if out is not None and (out.dtype != np.float64 or out.shape != b.shape or not out.flags.c_contiguous):
+            raise ValueError("out must be a C-contiguous float64 array of the shape of b")
+        x = np.empty_like(b) if out is None else out
         it = (C.c_int * 4)()
         x0 = None
         if initialize is not None and len(initialize):
