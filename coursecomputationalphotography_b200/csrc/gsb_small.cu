@@ -408,35 +408,61 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity
     return false;
 }
 
-template <int NRHS, int THREADS, int CSIZE>
-__global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restrict__ rp, const int *__restrict__ ci,
+#define GS_SMALL_CLUSTER_THREADS_MAX 512
+#define GS_SMALL_MAX_STEPS 192 // (colour, pass) steps per sweep the step table holds
+
+// One (colour, pass) step of the sweep as the cluster sees it: rows [base, end) are dealt out `threads` per CTA;
+// flags: 1 = the step opens its colour's phase, 2 = it closes it (wait for the phase's bytes), 4 = it closes the sweep
+struct __align__(16) SmallStep {
+    int base, end, flags, phase_bytes;
+};
+
+template <int NRHS, int CSIZE>
+__global__ void __launch_bounds__(GS_SMALL_CLUSTER_THREADS_MAX) gs_small_cluster(const int *__restrict__ rp, const int *__restrict__ ci,
                                                             const double *__restrict__ va, const double *__restrict__ dg,
                                                             const double *__restrict__ b, double *x, int64_t n, GsCtl *ctl,
                                                             double *partials, const GsbSmallArgs a) {
     extern __shared__ __align__(16) double xs[]; // this CTA's copy of x: NRHS planes of `nrows` doubles
-    __shared__ double ws[NRHS][THREADS / 32];
-    __shared__ int cs[GS_SMALL_MAX_COLORS + 1];
+    __shared__ double ws[NRHS][GS_SMALL_CLUSTER_THREADS_MAX / 32];
+    __shared__ SmallStep steps[GS_SMALL_MAX_STEPS];
+    __shared__ int nsteps_s;
     __shared__ __align__(8) double part_s[CSIZE][NRHS]; // CTA 0: every CTA's share of the sweep's update norm
     __shared__ __align__(8) unsigned long long done_s;
     __shared__ __align__(8) uint64_t bar_x[2], bar_red, bar_done;
-    constexpr int STRIDE = CSIZE * THREADS; // rows per step
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int threads = (int)blockDim.x, stride = CSIZE * threads; // rows per step
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = threads >> 5;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     if (*(volatile int *)&ctl->done) return; // (the same value in every CTA: nobody is left waiting)
     const int nc = a.n_colors;
-    for (int c = tid; c <= nc; c += THREADS) cs[c] = a.color_start[c];
     const int nrows = a.color_start[nc];
-#pragma unroll
-    for (int r = 0; r < NRHS; ++r)
-        for (int i = tid; i < nrows; i += THREADS) xs[r * nrows + i] = x[r * n + i];
-    if (tid == 0) {
+    const int ldx = (nrows + 1) & ~1; // plane stride of the copies: even, so that a row's parity decides 16-byte alignment
+    if (tid == 0) { // the sweep's schedule, once (the host has checked that it fits)
+        int ns = 0;
+        for (int c = 0; c < nc; ++c) {
+            const int c0 = a.color_start[c], c1 = a.color_start[c + 1];
+            int base = c0;
+            do {
+                SmallStep sp;
+                sp.base = base;
+                sp.end = c1;
+                sp.phase_bytes = (c1 - c0) * NRHS * 8; // every row of the colour arrives here, this CTA's own included
+                sp.flags = (base == c0 ? 1 : 0) | (base + stride >= c1 ? 2 : 0) | ((base + stride >= c1 && c == nc - 1) ? 4 : 0);
+                steps[ns++] = sp;
+                base += stride;
+            } while (base < c1);
+        }
+        nsteps_s = ns;
         mbar_init(&bar_x[0], 1);
         mbar_init(&bar_x[1], 1);
         mbar_init(&bar_red, 1);
         mbar_init(&bar_done, 1);
     }
-    cluster.sync(); // copies filled and mbarriers initialised everywhere before the first remote store
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r)
+        for (int i = tid; i < nrows; i += threads) xs[r * ldx + i] = x[r * n + i];
+    cluster.sync(); // copies filled, schedule and mbarriers in place everywhere before the first remote store
+    const int nsteps = nsteps_s;
     uint32_t xs_of[CSIZE], bx_of[CSIZE][2]; // shared::cluster addresses of every CTA's copy and phase mbarriers
 #pragma unroll
     for (int q = 0; q < CSIZE; ++q) {
@@ -444,23 +470,12 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
         bx_of[q][0] = mapa_u32(smem_u32(&bar_x[0]), q);
         bx_of[q][1] = mapa_u32(smem_u32(&bar_x[1]), q);
     }
-    auto xread = [&](int col, int r) -> double { return xs[r * nrows + col]; };
-    auto advance = [&](int &c, int &p) -> bool { // the step after (c, p) in sweep order; true: it opens the next sweep
-        if (cs[c] + (p + 1) * STRIDE < cs[c + 1]) {
-            ++p;
-            return false;
-        }
-        p = 0;
-        if (++c == nc) {
-            c = 0;
-            return true;
-        }
-        return false;
-    };
-    auto load_a = [&](int c, int p) -> SmallRowA {
+    auto xread = [&](int col, int r) -> double { return xs[r * ldx + col]; };
+    const int my_off = rank * threads + tid;
+    auto load_a = [&](int sidx) -> SmallRowA {
         SmallRowA A;
-        const int i = cs[c] + p * STRIDE + rank * THREADS + tid;
-        if (i < cs[c + 1]) {
+        const int i = steps[sidx].base + my_off;
+        if (i < steps[sidx].end) {
             A.i = i;
             A.k0 = rp[i];
             A.k1 = rp[i + 1];
@@ -491,6 +506,9 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) acc[r] = 0.0;
     int phase = 0; // colour phases since the start of the launch: mbarrier bar_x[phase & 1], parity (phase >> 1) & 1
+    // (One bulk copy per warp and peer -- shared memory to shared::cluster, 256 bytes instead of 32 st.async packets --
+    // was measured too: 220 us against 193 us on configs[0], profiles/r02_call24_summary.txt.  A bulk copy's fixed
+    // latency is on the critical path of every step; the single stores leave as soon as the row is computed.)
     auto compute = [&](const SmallRowA &A, const SmallRowB<NRHS> &B) {
         if (A.i < 0) return;
         double sig[NRHS];
@@ -514,45 +532,45 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
         const uint32_t pb = (uint32_t)phase & 1u;
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
-            const double xo = xs[r * nrows + A.i];
+            const double xo = xs[r * ldx + A.i];
             double xn = xo; // zero or absent diagonal: row skipped, x_i unchanged (v2 :360-363) -- and sent as it is
             if (B.d != 0.0) {
                 xn = __ddiv_rn(__dsub_rn(B.bb[r], sig[r]), B.d);
                 acc[r] += fabs(xn - xo);
             }
-            const uint32_t off = (uint32_t)(r * nrows + A.i) * 8u;
+            const uint32_t off = (uint32_t)(r * ldx + A.i) * 8u;
 #pragma unroll
             for (int q = 0; q < CSIZE; ++q)
                 st_async_b64(xs_of[q] + off, (unsigned long long)__double_as_longlong(xn), pb ? bx_of[q][1] : bx_of[q][0]);
         }
     };
+    auto next = [&](int sidx) -> int { return sidx + 1 == nsteps ? 0 : sidx + 1; };
 
-    int c0 = 0, p0 = 0, c1 = 0, p1 = 0, sweep = 0;
-    SmallRowA A0 = load_a(0, 0);
+    int s0 = 0, s1 = next(0), sweep = 0;
+    SmallRowA A0 = load_a(0);
     SmallRowB<NRHS> B0 = load_b(A0);
-    bool wrap1 = advance(c1, p1);
-    SmallRowA A1 = load_a(c1, p1);
+    SmallRowA A1 = load_a(s1);
     for (;;) {
-        if (p0 == 0) { // a colour phase opens: every thread of the CTA has passed the previous phase's wait
+        const int flags = steps[s0].flags;
+        if (flags & 1) { // a colour phase opens: every thread of the CTA has passed the previous phase's wait
             __syncthreads();
             if (tid == 0) {
-                mbar_expect_tx(&bar_x[phase & 1], (uint32_t)(cs[c0 + 1] - cs[c0]) * (uint32_t)(NRHS * 8));
-                if (c0 == 0) { // ... and a sweep: the stop rule's two mbarriers
+                mbar_expect_tx(&bar_x[phase & 1], (uint32_t)steps[s0].phase_bytes);
+                if (s0 == 0) { // ... and a sweep: the stop rule's two mbarriers
                     if (rank == 0) mbar_expect_tx(&bar_red, (uint32_t)(CSIZE * NRHS * 8));
                     mbar_expect_tx(&bar_done, 8u);
                 }
             }
         }
-        int c2 = c1, p2 = p1;
-        const bool wrap2 = advance(c2, p2);
-        const SmallRowA A2 = load_a(c2, p2);   // two steps ahead: row offsets
+        const int s2 = next(s1);
+        const SmallRowA A2 = load_a(s2);       // two steps ahead: row offsets
         const SmallRowB<NRHS> B1 = load_b(A1); // one step ahead: entries, diagonal, b
         compute(A0, B0);
-        if (wrap1 || c1 != c0) { // the colour is complete once its bytes are: every CTA's values of it are in this copy
+        if (flags & 2) { // the colour is complete once its bytes are: every CTA's values of it are in this copy
             if (!mbar_wait_bounded(&bar_x[phase & 1], (uint32_t)(phase >> 1) & 1u, ctl)) return;
             ++phase;
         }
-        if (wrap1) { // the sweep is complete: fold the update norm in a fixed order, decide (v2 :356, :376-377)
+        if (flags & 4) { // the sweep is complete: fold the update norm in a fixed order, decide (v2 :356, :376-377)
 #pragma unroll
             for (int r = 0; r < NRHS; ++r) {
                 double t = acc[r];
@@ -564,7 +582,7 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
             __syncthreads();
             if (tid < NRHS) { // this CTA's share, warps in order -> slot `rank` of CTA 0
                 double t = 0.0;
-                for (int w = 0; w < THREADS / 32; ++w) t += ws[tid][w];
+                for (int w = 0; w < nwarps; ++w) t += ws[tid][w];
                 st_async_b64(mapa_u32(smem_u32(&part_s[rank][tid]), 0), (unsigned long long)__double_as_longlong(t),
                              mapa_u32(smem_u32(&bar_red), 0));
             }
@@ -597,16 +615,13 @@ __global__ void __launch_bounds__(THREADS) gs_small_cluster(const int *__restric
         A0 = A1;
         B0 = B1;
         A1 = A2;
-        c0 = c1;
-        p0 = p1;
-        c1 = c2;
-        p1 = p2;
-        wrap1 = wrap2;
+        s0 = s1;
+        s1 = s2;
     }
     // all copies are equal (every phase has been waited for): every CTA writes a share back
 #pragma unroll
     for (int r = 0; r < NRHS; ++r)
-        for (int i = rank * THREADS + tid; i < nrows; i += STRIDE) x[r * n + i] = xs[r * nrows + i];
+        for (int i = my_off; i < nrows; i += stride) x[r * n + i] = xs[r * ldx + i];
     cluster.sync(); // no CTA leaves while a peer could still be sending to it
 }
 
@@ -647,17 +662,29 @@ static int launch_small_t(const int *rp, const int *ci, const double *va, const 
             const char *e = getenv("GSB_SMALL_PIPE");
             return e ? atoi(e) : 3;
         }();
-        const size_t xs_bytes = sizeof(double) * (size_t)NRHS * (size_t)color_start[n_colors];
+        // (planes padded to an even length: the cluster version aligns its bulk copies on that)
+        const size_t xs_bytes = sizeof(double) * (size_t)NRHS * (size_t)((color_start[n_colors] + 1) & ~1);
         const int dev = gsb_current_device();
         const bool dev_ok = dev >= 0 && dev < 64;
         if (pipe >= 1 && color_start[0] == 0) {
             constexpr int T = NRHS == 1 ? 1024 : 512; // registers: the rows in flight of k right-hand sides
-            constexpr int TC = 256, CS = GS_SMALL_CLUSTER; // cluster version: CS CTAs of TC threads
+            constexpr int CS = GS_SMALL_CLUSTER; // cluster version: CS CTAs
+            // threads per CTA: enough for the largest colour in ONE pass when that is possible (a pass costs a fixed
+            // latency, not throughput), a multiple of 32 in [128, 512]
+            int TC = ((largest + CS - 1) / CS + 31) / 32 * 32;
+            if (TC < 128) TC = 128;
+            if (TC > GS_SMALL_CLUSTER_THREADS_MAX) TC = GS_SMALL_CLUSTER_THREADS_MAX;
+            int cluster_steps = 0;
+            for (int c = 0; c < n_colors; ++c) {
+                const int rows_c = color_start[c + 1] - color_start[c];
+                cluster_steps += rows_c > 0 ? (rows_c + CS * TC - 1) / (CS * TC) : 1;
+            }
             static int cluster_ok[64] = {0};                // per device: 0 unknown, 1 usable, -1 not
             bool launched = false;
             if (pipe >= 3 && xs_bytes <= GS_SMALL_XS_BYTES_MAX && largest >= GS_SMALL_CLUSTER_MIN_ROWS &&
-                !(dev_ok && cluster_ok[dev] < 0)) {
-                auto kern = pipe == 4 ? gs_small_one_cta<NRHS, TC, true, CS> : gs_small_cluster<NRHS, TC, CS>;
+                cluster_steps <= GS_SMALL_MAX_STEPS && !(dev_ok && cluster_ok[dev] < 0)) {
+                if (pipe == 4) TC = 256;
+                auto kern = pipe == 4 ? gs_small_one_cta<NRHS, 256, true, CS> : gs_small_cluster<NRHS, CS>;
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(CS);
                 cfg.blockDim = dim3(TC);
@@ -676,6 +703,7 @@ static int launch_small_t(const int *rp, const int *ci, const double *va, const 
                                                          GS_SMALL_XS_BYTES_MAX);
                     cudaLaunchConfig_t probe = cfg;
                     probe.dynamicSmemBytes = GS_SMALL_XS_BYTES_MAX;
+                    if (pipe != 4) probe.blockDim = dim3(GS_SMALL_CLUSTER_THREADS_MAX);
                     if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nclu, (const void *)kern, &probe);
                     if (e != cudaSuccess) cudaGetLastError();
                     if (dev_ok) cluster_ok[dev] = (e == cudaSuccess && nclu >= 1) ? 1 : -1;
