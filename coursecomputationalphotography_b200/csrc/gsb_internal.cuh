@@ -225,6 +225,7 @@ struct GsbPlan {
     int wcap = 0;         // doubles per right-hand side reserved per stage for the windows
     // kernel 5 (two colours, one launch per sweep): per tile of colour 1 the range of colour-0 tiles it has to see
     // finished (the ones it reads, and the ones that read its rows' old values); per tile of colour 0 a flag
+    int64_t nnz_hint = 0;       // stored entries of the matrix (set by the single-GPU solver: kernel 2's L2-hint policy)
     bool fused_allowed = false; // set by the single-GPU solver before gsb_plan_build (strip plans never fuse)
     bool fused_ok = false;
     int fused_lead_min = 0;     // colour 0 has to run at least this many tiles ahead of colour 1

@@ -59,7 +59,21 @@ __global__ void __launch_bounds__(GS_THREADS)
 // ---------------------------------------------------------------------------------------------
 // kernel 2: bulk-copy staged CSR tiles
 // ---------------------------------------------------------------------------------------------
-template <int NRHS, bool CHECK>
+// HINT: L2 residency control for matrices whose x (all right-hand sides) fits in L2 while the matrix does not
+// (BASELINE configs[4]: n = 1e7 -> x is 80 MB, the CSR 3.2 GB per sweep).  With random columns every gather touches its
+// own 32-byte sector, and when the matrix stream has pushed x out of L2 each of them goes to DRAM -- several times the
+// algorithmic traffic.  The streamed arrays (values, columns, row offsets, diagonal, b) are fetched evict-first and
+// the x lines (gathers, the row's own old value, the store) evict-last, so that x stays resident across the sweep.
+__device__ __forceinline__ double ld_f64_l2hint(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_f64_l2hint(double *p, double v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+}
+
+template <int NRHS, bool CHECK, bool HINT>
 __global__ void __launch_bounds__(GS_THREADS, 4)
     gs_phase_staged(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
                     const double *__restrict__ dg, const double *__restrict__ b, double *x, int64_t n, int row0,
@@ -82,37 +96,51 @@ __global__ void __launch_bounds__(GS_THREADS, 4)
         const uint32_t bytes_v = (uint32_t)(((k1 + 1) & ~1) - kv0) * 8u;
         const uint32_t bytes_c = (uint32_t)(((k1 + 3) & ~3) - kc0) * 4u;
         mbar_expect_tx(mbar, bytes_v + bytes_c);
-        if (bytes_v) bulk_g2s(va_s, va + kv0, bytes_v, mbar);
-        if (bytes_c) bulk_g2s(ci_s, ci + kc0, bytes_c, mbar);
+        if (HINT) {
+            const uint64_t pol_stream = l2_policy_evict_first();
+            if (bytes_v) bulk_g2s_hint(va_s, va + kv0, bytes_v, mbar, pol_stream);
+            if (bytes_c) bulk_g2s_hint(ci_s, ci + kc0, bytes_c, mbar, pol_stream);
+        } else {
+            if (bytes_v) bulk_g2s(va_s, va + kv0, bytes_v, mbar);
+            if (bytes_c) bulk_g2s(ci_s, ci + kc0, bytes_c, mbar);
+        }
     }
     // coalesced per-row loads overlap the bulk copies
     const int i = r_begin + threadIdx.x;
     const bool valid = threadIdx.x < tile_rows && i < r_end;
+    const uint64_t pol_keep = HINT ? l2_policy_evict_last() : 0;
     int rs = 0, re = 0;
     double d = 0.0, bb[NRHS], xo[NRHS], diff[NRHS];
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) bb[r] = xo[r] = diff[r] = 0.0;
     if (valid) {
-        rs = rp[i];
-        re = rp[i + 1];
-        d = dg[i];
+        rs = HINT ? __ldcs(rp + i) : rp[i];
+        re = HINT ? __ldcs(rp + i + 1) : rp[i + 1];
+        d = HINT ? __ldcs(dg + i) : dg[i];
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) {
-            bb[r] = b[r * n + i];
-            if (CHECK) xo[r] = x[r * n + i];
+            bb[r] = HINT ? __ldcs(b + r * n + i) : b[r * n + i];
+            if (CHECK) xo[r] = HINT ? ld_f64_l2hint(x + r * n + i, pol_keep) : x[r * n + i];
         }
     }
     mbar_wait(mbar, 0);
 
     if (valid) {
         double sig[NRHS];
-        gs_row_sigma<NRHS>(ci_s + (rs - kc0), va_s + (rs - kv0), re - rs, [&](int c, int r) { return x[r * n + c]; }, sig);
+        if (HINT)
+            gs_row_sigma<NRHS>(ci_s + (rs - kc0), va_s + (rs - kv0), re - rs,
+                               [&](int c, int r) { return ld_f64_l2hint(x + r * n + c, pol_keep); }, sig);
+        else
+            gs_row_sigma<NRHS>(ci_s + (rs - kc0), va_s + (rs - kv0), re - rs, [&](int c, int r) { return x[r * n + c]; }, sig);
         if (d != 0.0) {
 #pragma unroll
             for (int r = 0; r < NRHS; ++r) {
                 const double xn = __ddiv_rn(__dsub_rn(bb[r], sig[r]), d);
                 if (CHECK) diff[r] = fabs(xn - xo[r]);
-                x[r * n + i] = xn;
+                if (HINT)
+                    st_f64_l2hint(x + r * n + i, xn, pol_keep);
+                else
+                    x[r * n + i] = xn;
             }
         }
     }
@@ -768,6 +796,8 @@ __global__ void __launch_bounds__(256) gs_fold_partials(const double *__restrict
 // 1024^2 (0.5 M rows, 12 us) it gains 8 %; a strip of an 8-GPU solve is on the small side.  Policy: unset = auto
 // (on for phases of at most GS_PDL_AUTO_ROWS rows), GSB_PDL=0 off, 1 on, 2 on without the early prologue.
 #define GS_PDL_AUTO_ROWS (3 << 20)
+#define GS_STAGED_HINT_AUTO 1                 // measured (r02_call26): configs[4] n = 1e7 58.5 -> 51.7 ms, n = 5e6 21.0 -> 16.7 ms per 20 sweeps
+#define GS_STAGED_HINT_X_BYTES (96.0 * 1048576.0) // x of all right-hand sides that L2 (126 MB) can keep
 static thread_local int g_pdl_suppress = 0;
 static thread_local int g_pdl_last = 0; // decision of the most recent ring launch: gs_end_sweep follows it
 void gsb_pdl_suppress(int on) { g_pdl_suppress = on; }
@@ -845,7 +875,10 @@ __global__ void __launch_bounds__(256) plan_tile_k(const int *__restrict__ rp, i
 // sweep's working set must exceed L2 -- and when a tile carries enough bytes to amortise its flag traffic.  Measured on
 // B200 (profiles/README.md, 4096^2): k = 3: 0.85 of the copy bandwidth against 0.80 for kernel 3; k = 1: 0.82 against
 // 0.93 for the window kernel (4); 1024^2 (L2-resident): 0.45 against 0.70.  GSB_FUSED_SWEEP=0 never, =2 whenever possible.
-#define GS_FUSED_AUTO_MIN_ROWS (3 << 20)
+// (the 5.03 M-row masked blend of the time-to-tolerance leg, k = 3: kernel 3 1206 / 1216 ms against kernel 5 1239 / 1243 /
+// 1283 ms over calls 15 and 25 -- at a third of the 4096^2 grid a sweep is short enough for the ring kernels' dependent
+// launches to hide what kernel 5 saves in traffic; hence 8 M rows, not the 3 M at which the working set leaves L2)
+#define GS_FUSED_AUTO_MIN_ROWS (8 << 20)
 static bool fused_sweep_auto(const GsbPlan *p, int nrhs) {
     static int env = -1;
     if (env < 0) {
@@ -1161,11 +1194,21 @@ static int plan_launch_t(const GsbPlan *p, int c, const int *rp, const int *ci, 
                                     nb, tk, tw, p->cap, wcap, ctl, partials, (const GsbHaloArgs)halo,
                                     (const GsbEndArgs)end));
     } else if (eff == 2) {
-        auto kt = gs_phase_staged<NRHS, true>;
-        auto kf = gs_phase_staged<NRHS, false>;
+        // L2 residency hints (see gs_phase_staged): GSB_STAGED_L2HINT=0 never, 1 always, default: when x of all right-
+        // hand sides is at most GS_STAGED_HINT_X_BYTES and the CSR is several times that
+        static const int hint_env = [] {
+            const char *e = getenv("GSB_STAGED_L2HINT");
+            return e ? atoi(e) : -1;
+        }();
+        const double x_bytes = 8.0 * (double)NRHS * (double)(p->color_start[p->n_colors] - p->color_start[0]);
+        const double csr_bytes = 12.0 * (double)p->nnz_hint;
+        const bool hint = hint_env >= 0 ? hint_env != 0
+                                        : (GS_STAGED_HINT_AUTO && x_bytes <= GS_STAGED_HINT_X_BYTES && csr_bytes >= 4.0 * x_bytes);
+        auto kt = hint ? gs_phase_staged<NRHS, true, true> : gs_phase_staged<NRHS, true, false>;
+        auto kf = hint ? gs_phase_staged<NRHS, false, true> : gs_phase_staged<NRHS, false, false>;
         if (p->smem_bytes > 48 * 1024) {
-            static bool set_t[8] = {false}, set_f[8] = {false};
-            bool &flag = check ? set_t[NRHS] : set_f[NRHS];
+            static bool set_t[8][2] = {{false}}, set_f[8][2] = {{false}};
+            bool &flag = check ? set_t[NRHS][hint ? 1 : 0] : set_f[NRHS][hint ? 1 : 0];
             if (!flag) {
                 GSB_CUDA(cudaFuncSetAttribute(check ? (const void *)kt : (const void *)kf,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 16 + GS_TILE_CAP_MAX * 12 + 256));

@@ -113,6 +113,7 @@ static int ensure_workspace(gsb_matrix *m, int nrhs, int kernel_request, cudaStr
     if (!m->plan) return GSB_ERR_ALLOC;
     if (!m->plan->valid || m->plan->requested != kernel_request) {
         m->plan->fused_allowed = true;
+        m->plan->nnz_hint = m->nnz;
         GSB_TRY(gsb_plan_build(m->plan, m->rp.p, m->ci.p, m->color_start, m->n_colors, kernel_request, st));
         GSB_TRY(m->partials.alloc((int64_t)(m->plan->total_blocks() + 1 + 64) * MAX_RHS)); // +64: second-level fold
         drop_graph(m);
