@@ -355,12 +355,18 @@ def run_ours(args):
         # on a shared box the first steps after the pinned allocations are erratic -- until two consecutive steps
         # agree to 10 %, at most 12
         warm_min, warm_max, warm_ms = max(args.warmup, 3), 12, []
+        def dev_allocs():
+            a, f = C.c_int64(0), C.c_int64(0)
+            L.gsb_alloc_counters(C.byref(a), C.byref(f))
+            return a.value + f.value
+        allocs_timed = 0
         while True:
             timed = len(warm_ms) >= warm_min and (len(warm_ms) >= warm_max or
                                                   abs(warm_ms[-1] - warm_ms[-2]) <= 0.1 * min(warm_ms[-2:]))
             if timed and len(per_step) >= steps_e2e:
                 break
             torch.cuda.synchronize()
+            a0 = dev_allocs()
             t0 = time.perf_counter()
             spe.initializeFromEigenRowMajor(va, len(va), ro_in, n, ci, n)
             t1 = time.perf_counter()
@@ -371,6 +377,7 @@ def run_ours(args):
             if not timed and not per_step:
                 warm_ms.append((t2 - t0) * 1e3)
             else:
+                allocs_timed += dev_allocs() - a0
                 t_e2e += t2 - t0
                 t_imp += t1 - t0
                 t_setup += st_e.setup_ms
@@ -384,7 +391,8 @@ def run_ours(args):
                "per_step_ms": [round(v, 2) for v in per_step], "per_step_import_analysis_sweeps_ms": per_step_parts,
                "includes": "CSR import (H2D) + ordering analysis + b H2D + sweeps + x D2H",
                "import_ms": t_imp / steps_e2e * 1e3, "analysis_ms": t_setup / steps_e2e,
-               "host_memory": "pinned (gsb_host_alloc)"}
+               "host_memory": "pinned (gsb_host_alloc)",
+               "device_allocs_and_frees_per_step": allocs_timed / steps_e2e}
         assert np.array_equal(x_pin, x_host), "e2e result differs from the resident-input result"
 
     cpu = None

@@ -129,6 +129,7 @@ SIGNATURES = {
     "gsb_dist_group_gauss_seidel": [_vp, _vp, _i, _d, _i, C.POINTER(GsOptions), _vp, C.POINTER(GsStats)],
     "gsb_dist_group_residual_l2": [_vp, _vp, _vp, _dp],
     "gsb_host_alloc": [C.POINTER(_vp), _i64],
+    "gsb_alloc_counters": [C.POINTER(_i64), C.POINTER(_i64)],
     "gsb_host_free": [_vp],
 }
 _RESTYPE = {"gsb_last_error": C.c_char_p, "gsb_stream": C.c_void_p, "gsb_gs_default_options": None,

@@ -69,16 +69,16 @@ __global__ void sum_i32_to_i64(const int *__restrict__ in, int64_t n, unsigned l
 int gsb_matrix_finish_layout(gsb_matrix *m) {
     cudaStream_t st = gsb_cur_stream();
     m->drop_analysis();
-    DevBuf<unsigned long long> tot;
-    GSB_TRY(tot.alloc(1));
-    GSB_CUDA(cudaMemsetAsync(tot.p, 0, sizeof(unsigned long long), st));
+    GSB_TRY(gsb_tiny_alloc(m));
+    unsigned long long *tot = reinterpret_cast<unsigned long long *>(m->tiny.p + GSB_TINY_TOT64);
+    GSB_CUDA(cudaMemsetAsync(tot, 0, sizeof(unsigned long long), st));
     if (m->n_rows > 0) {
         sum_i32_to_i64<<<gsb_blocks_for(m->n_rows, 256 * 4, gsb_sm_count() * 8), 256, 0, st>>>(m->row_nnz.p,
-                                                                                              m->n_rows, tot.p);
+                                                                                              m->n_rows, tot);
         GSB_KERNEL_CHECK();
     }
     unsigned long long h = 0;
-    GSB_CUDA(cudaMemcpyAsync(&h, tot.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaMemcpyAsync(&h, tot, sizeof(h), cudaMemcpyDeviceToHost, st));
     if (m->vtype == GSB_I32) {
         GSB_TRY(m->values_f64.alloc(m->store));
         if (m->store > 0) {
@@ -331,9 +331,9 @@ extern "C" int gsb_matrix_import_csr(gsb_matrix *m, const void *values, int n_va
     GSB_TRY(alloc_layout(m, n_values, nr));
     m->n_cols = n_col_off;
     DevBuf<int> &off_in = m->scratch_rows;
-    DevBuf<int> first;
     GSB_TRY(off_in.alloc((int64_t)nr + 1));
-    GSB_TRY(first.alloc(1));
+    GSB_TRY(gsb_tiny_alloc(m));
+    struct { int *p; } first = {m->tiny.p + GSB_TINY_FIRST};
     size_t es = elem_size(m->vtype);
     if (n_values > 0) {
         GSB_CUDA(cudaMemcpyAsync(m->values_raw.p, values, es * (size_t)n_values, cudaMemcpyHostToDevice, st));

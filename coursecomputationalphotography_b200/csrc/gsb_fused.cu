@@ -534,9 +534,9 @@ int gsb_plan_build_fused(GsbPlan *p, const int *rp, const int *ci, cudaStream_t 
     const int nt0 = p->blocks[0], nt1 = p->blocks[1];
     if (nt0 <= 0 || nt1 <= 0) return GSB_OK;
     DevBuf<int2> &span = p->fused_span; // kept: the item table takes the colour-0 tiles' gather hints from it
-    DevBuf<int> stats;
     GSB_TRY(span.alloc((int64_t)nt0 + nt1));
-    GSB_TRY(stats.alloc(4));
+    GSB_TRY(p->tiny.alloc(32));
+    struct { int *p; } stats = {p->tiny.p + 8};
     GSB_TRY(p->fused_dep.alloc((int64_t)2 * nt1));
     GSB_TRY(p->fused_flags.alloc(nt0));
     GSB_CUDA(cudaMemsetAsync(stats.p, 0, 4 * sizeof(int), st));

@@ -42,6 +42,7 @@ int gsb_ensure_device(); // GSB_OK or GSB_ERR_NO_DEVICE
     } while (0)
 
 // Device buffer with RAII; freed on the owning device.
+void gsb_count_alloc(int frees); // gsb_prims.cu: process-wide counters behind gsb_alloc_counters()
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -52,7 +53,10 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            cudaFree(p);
+            gsb_count_alloc(1);
+        }
         p = nullptr;
         n = 0;
         cap = 0;
@@ -75,6 +79,7 @@ struct DevBuf {
             cudaGetLastError();
             return GSB_ERR_ALLOC;
         }
+        gsb_count_alloc(0);
         n = count;
         cap = count;
         return GSB_OK;
@@ -88,7 +93,9 @@ struct DevBuf {
 
 // ---- device-wide primitives (gsb_prims.cu) ---------------------------------------------
 // exclusive prefix sum of int32 -> int32 (out may alias in); *total_dev (optional, device) gets the sum
-int gsb_exclusive_scan_i32(const int *in, int *out, int64_t n, int *total_dev, cudaStream_t st);
+int gsb_exclusive_scan_i32(const int *in, int *out, int64_t n, int *total_dev, cudaStream_t st, int *scratch = nullptr,
+                           int64_t scratch_ints = 0); // with enough scratch (gsb_scan_scratch_ints): no allocation, no sync
+int64_t gsb_scan_scratch_ints(int64_t n);
 // deterministic sum reduction helpers: result written to out_dev[0]
 int gsb_reduce_max_i32(const int *in, int64_t n, int *out_dev, cudaStream_t st);
 int gsb_l1_dist_dev(const double *a, const double *b, int64_t n, double *out_dev, cudaStream_t st);
@@ -152,6 +159,11 @@ struct gsb_matrix {
     DevBuf<double> xw, bw; // permuted x and b, nrhs * n_rows
     int ws_nrhs = 0;
     DevBuf<double> stage_b, stage_x; // natural-order device copies of host b / x for the host-pointer entry points
+    DevBuf<int> tiny;                // 64 ints of device scratch in fixed slots (GSB_TINY_*) for the few-word results of
+                                     // import / analysis kernels: a steady-state import + analysis + solve then makes no
+                                     // cudaMalloc / cudaFree at all (each is a trip into the driver that, on a box shared
+                                     // with other processes, was seen to take 100-900 ms every few calls)
+    DevBuf<int> scan_scratch;        // block sums of the analysis' prefix scans (gsb_scan_scratch_ints(n_rows + 1))
     DevBuf<int> scratch_rows;        // n_rows + 1 ints of scratch for import / analysis (kept: a re-import of the same
                                      // shape then makes no GB-scale cudaMalloc / cudaFree, each a device-wide sync)
     void *ev_t0 = nullptr, *ev_t1 = nullptr; // cudaEvent_t pair timing the sweep loop (kept: a small solve is a few hundred us)
@@ -179,6 +191,13 @@ struct gsb_matrix {
 };
 
 int gsb_matrix_finish_layout(gsb_matrix *m); // compute nnz, f64 view after the five arrays are set
+// slots of gsb_matrix::tiny (ints; 8-byte values on even slots)
+#define GSB_TINY_FIRST 0
+#define GSB_TINY_TOT64 2
+#define GSB_TINY_COLOR_TOT 4
+#define GSB_TINY_INFO 8
+#define GSB_TINY_INTS 64
+static inline int gsb_tiny_alloc(gsb_matrix *m) { return m->tiny.alloc(GSB_TINY_INTS); }
 
 // gsb_assembly.cu: sorted COO (device pointers) -> slack CSR in m
 template <typename T>
@@ -226,6 +245,7 @@ struct GsbPlan {
     // kernel 5 (two colours, one launch per sweep): per tile of colour 1 the range of colour-0 tiles it has to see
     // finished (the ones it reads, and the ones that read its rows' old values); per tile of colour 0 a flag
     int64_t nnz_hint = 0;       // stored entries of the matrix (set by the single-GPU solver: kernel 2's L2-hint policy)
+    DevBuf<int> tiny;           // 32 ints of scratch for the plan kernels' few-word results (slots 0, 4, 8), kept
     bool fused_allowed = false; // set by the single-GPU solver before gsb_plan_build (strip plans never fuse)
     bool fused_ok = false;
     int fused_lead_min = 0;     // colour 0 has to run at least this many tiles ahead of colour 1

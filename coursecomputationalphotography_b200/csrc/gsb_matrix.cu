@@ -277,14 +277,15 @@ static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
     GSB_TRY(m->perm.alloc(n));
     GSB_TRY(m->iperm.alloc(n));
     DevBuf<int> &flag = m->scratch_rows;
-    DevBuf<int> tot;
     GSB_TRY(flag.alloc((int64_t)n + 1));
-    GSB_TRY(tot.alloc(1));
+    GSB_TRY(gsb_tiny_alloc(m));
+    GSB_TRY(m->scan_scratch.alloc(gsb_scan_scratch_ints((int64_t)n + 1)));
+    struct { int *p; } tot = {m->tiny.p + GSB_TINY_COLOR_TOT};
     int base = 0;
     for (int c = 0; c < m->n_colors; ++c) {
         color_flag<<<nb, 256, 0, st>>>(m->colors.p, n, c, flag.p);
         GSB_KERNEL_CHECK();
-        GSB_TRY(gsb_exclusive_scan_i32(flag.p, flag.p, n, tot.p, st));
+        GSB_TRY(gsb_exclusive_scan_i32(flag.p, flag.p, n, tot.p, st, m->scan_scratch.p, m->scan_scratch.n));
         int h = 0;
         GSB_CUDA(cudaMemcpyAsync(&h, tot.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         GSB_CUDA(cudaStreamSynchronize(st));
@@ -301,7 +302,7 @@ static int build_solver_format(gsb_matrix *m, cudaStream_t st) {
     GSB_TRY(m->rp.alloc((int64_t)n + 1 + 8)); // +8: aligned bulk copies may over-read
     perm_row_len<<<(n + 1 + 255) / 256, 256, 0, st>>>(m->perm.p, m->row_begin.p, m->row_nnz.p, m->cols.p, n, m->rp.p);
     GSB_KERNEL_CHECK();
-    GSB_TRY(gsb_exclusive_scan_i32(m->rp.p, m->rp.p, (int64_t)n + 1, nullptr, st));
+    GSB_TRY(gsb_exclusive_scan_i32(m->rp.p, m->rp.p, (int64_t)n + 1, nullptr, st, m->scan_scratch.p, m->scan_scratch.n));
     int nnz_off = 0;
     GSB_CUDA(cudaMemcpyAsync(&nnz_off, m->rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
@@ -415,8 +416,8 @@ extern "C" int gsb_matrix_analyze(gsb_matrix *m, int ordering, const int *user_c
     cudaStream_t st = gsb_cur_stream();
     m->drop_analysis();
     const int n = m->n_rows;
-    DevBuf<int> info;
-    GSB_TRY(info.alloc(8));
+    GSB_TRY(gsb_tiny_alloc(m));
+    struct { int *p; } info = {m->tiny.p + GSB_TINY_INFO};
     int init[4] = {0, -1, INT32_MAX, 0};
     GSB_CUDA(cudaMemcpyAsync(info.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     probe_offsets<<<(n + 255) / 256, 256, 0, st>>>(m->cols.p, m->row_begin.p, m->row_nnz.p, n, info.p);

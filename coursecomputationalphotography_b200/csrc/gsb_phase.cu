@@ -945,8 +945,8 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
     p->smem_bytes = 0;
     p->fused_ok = false;
     if (kernel_request != 1) {
-        DevBuf<int> mx;
-        GSB_TRY(mx.alloc(1));
+        GSB_TRY(p->tiny.alloc(32));
+        struct { int *p; } mx = {p->tiny.p};
         for (int tile_rows = GS_THREADS; tile_rows >= 32; tile_rows >>= 1) {
             int total = 0;
             for (int c = 0; c < n_colors; ++c) {
@@ -987,8 +987,8 @@ int gsb_plan_build(GsbPlan *p, const int *rp, const int *ci, const int *color_st
                 p->win_off[c] = total;
                 total += p->blocks[c];
             }
-            DevBuf<int> stats;
-            GSB_TRY(stats.alloc(2));
+            GSB_TRY(p->tiny.alloc(32));
+            struct { int *p; } stats = {p->tiny.p + 4};
             GSB_CUDA(cudaMemsetAsync(stats.p, 0, 2 * sizeof(int), st));
             GSB_TRY(p->tile_win.alloc((int64_t)total * GS_WIN_DESC));
             for (int c = 0; c < n_colors; ++c) {

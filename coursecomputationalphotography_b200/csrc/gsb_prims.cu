@@ -3,6 +3,8 @@
 // deterministic two-pass reductions, and the reference's free vector helpers (A8).
 #include "gsb_internal.cuh"
 
+#include <atomic>
+
 #include <stdlib.h>
 
 #include <mutex>
@@ -189,6 +191,14 @@ extern "C" int gsb_host_alloc(void **ptr, int64_t bytes) {
     return GSB_OK;
 }
 
+static std::atomic<long long> g_dev_allocs{0}, g_dev_frees{0};
+void gsb_count_alloc(int frees) { (frees ? g_dev_frees : g_dev_allocs).fetch_add(1, std::memory_order_relaxed); }
+extern "C" int gsb_alloc_counters(int64_t *device_allocs, int64_t *device_frees) {
+    if (device_allocs) *device_allocs = (int64_t)g_dev_allocs.load();
+    if (device_frees) *device_frees = (int64_t)g_dev_frees.load();
+    return GSB_OK;
+}
+
 extern "C" int gsb_host_free(void *ptr) {
     if (!ptr) return GSB_OK;
     GSB_CUDA(cudaFreeHost(ptr));
@@ -289,7 +299,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const int *in, int *o
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = off + tot;
 }
 
-int gsb_exclusive_scan_i32(const int *in, int *out, int64_t n, int *total_dev, cudaStream_t st) {
+// ints of caller-provided scratch that make gsb_exclusive_scan_i32 allocation-free for n elements
+int64_t gsb_scan_scratch_ints(int64_t n) {
+    int64_t tot = 0;
+    while (n > SCAN_TILE) {
+        n = (n + SCAN_TILE - 1) / SCAN_TILE;
+        tot += n;
+    }
+    return tot + 1;
+}
+
+int gsb_exclusive_scan_i32(const int *in, int *out, int64_t n, int *total_dev, cudaStream_t st, int *scratch,
+                           int64_t scratch_ints) {
     if (n <= 0) {
         if (total_dev) GSB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(int), st));
         return GSB_OK;
@@ -299,6 +320,14 @@ int gsb_exclusive_scan_i32(const int *in, int *out, int64_t n, int *total_dev, c
         scan_apply<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr, total_dev);
         GSB_KERNEL_CHECK();
         return GSB_OK;
+    }
+    if (scratch && scratch_ints >= gsb_scan_scratch_ints(n)) { // the block sums of every level live in the caller's buffer
+        scan_block_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, scratch);
+        GSB_KERNEL_CHECK();
+        GSB_TRY(gsb_exclusive_scan_i32(scratch, scratch, nb, nullptr, st, scratch + nb, scratch_ints - nb));
+        scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, scratch, total_dev);
+        GSB_KERNEL_CHECK();
+        return GSB_OK; // (stream-ordered: nothing to free, no host synchronisation)
     }
     DevBuf<int> sums;
     GSB_TRY(sums.alloc(nb));

@@ -139,24 +139,22 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
     if (opts.check_every < 1) opts.check_every = 1;
     cudaStream_t st = gsb_cur_stream();
     double setup_ms = 0.0;
+    if (!m->ev_t0) { // one pair of timing events per handle (analysis, then the sweep loop)
+        cudaEvent_t a = nullptr, b2 = nullptr;
+        GSB_CUDA(cudaEventCreate(&a));
+        m->ev_t0 = a;
+        GSB_CUDA(cudaEventCreate(&b2));
+        m->ev_t1 = b2;
+    }
     if (!m->analyzed) {
-        cudaEvent_t e0, e1;
-        GSB_CUDA(cudaEventCreate(&e0));
-        GSB_CUDA(cudaEventCreate(&e1));
+        cudaEvent_t e0 = (cudaEvent_t)m->ev_t0, e1 = (cudaEvent_t)m->ev_t1;
         GSB_CUDA(cudaEventRecord(e0, st));
-        int s = gsb_matrix_analyze(m, opts.ordering, nullptr);
-        if (s != GSB_OK) {
-            cudaEventDestroy(e0);
-            cudaEventDestroy(e1);
-            return s;
-        }
+        GSB_TRY(gsb_matrix_analyze(m, opts.ordering, nullptr));
         GSB_CUDA(cudaEventRecord(e1, st));
         GSB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         setup_ms = ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     }
     const int64_t n = m->n_rows;
     GSB_TRY(ensure_workspace(m, nrhs, opts.kernel, st));
@@ -216,13 +214,6 @@ static int gs_solve_device(gsb_matrix *m, const double *b_dev, const double *x0_
         GSB_CUDA(cudaMemsetAsync(m->small_bar.p, 0, 2 * sizeof(unsigned), st)); // (a solve that gave up may have left it mid-count)
     }
 
-    if (!m->ev_t0) {
-        cudaEvent_t a = nullptr, b2 = nullptr;
-        GSB_CUDA(cudaEventCreate(&a));
-        m->ev_t0 = a;
-        GSB_CUDA(cudaEventCreate(&b2));
-        m->ev_t1 = b2;
-    }
     cudaEvent_t ev0 = (cudaEvent_t)m->ev_t0, ev1 = (cudaEvent_t)m->ev_t1;
     GSB_CUDA(cudaEventRecord(ev0, st));
     int status = GSB_OK;

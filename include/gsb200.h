@@ -355,6 +355,11 @@ int gsb_dist_set_colors(gsb_dist *d, const unsigned char *colors, int64_t n_glob
 int gsb_host_alloc(void **ptr, int64_t bytes);
 int gsb_host_free(void *ptr);
 
+/* Diagnostics: how many device allocations / frees (cudaMalloc / cudaFree) the library has made in this process so
+   far.  A steady-state import + analyse + solve of an unchanged shape makes none (bench.py reports the count per e2e
+   step). */
+int gsb_alloc_counters(int64_t *device_allocs, int64_t *device_frees);
+
 #ifdef __cplusplus
 }
 #endif
