@@ -115,6 +115,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def e2e_warm_done(warm_ms, warm_min=3, warm_max=12, tol=0.1):
+    """The e2e leg's untimed warm-up is over: at least `warm_min` steps, then as soon as two consecutive steps agree to
+    `tol` (or after `warm_max` steps).  On the pool's shared boxes the first steps after the GB-sized page-locked
+    allocations are erratic; the timed region starts once the step time has settled."""
+    if len(warm_ms) < warm_min:
+        return False
+    return len(warm_ms) >= warm_max or abs(warm_ms[-1] - warm_ms[-2]) <= tol * min(warm_ms[-2:])
+
+
 def pinned_like(pkg, a):
     """Copy of numpy array `a` in page-locked host memory (gsb_host_alloc): the e2e leg copies from / to it."""
     p = C.c_void_p()
@@ -354,15 +363,14 @@ def run_ours(args):
         # untimed warm-up: at least 3 steps (the first imports into a fresh handle allocate GB-sized buffers), then --
         # on a shared box the first steps after the pinned allocations are erratic -- until two consecutive steps
         # agree to 10 %, at most 12
-        warm_min, warm_max, warm_ms = max(args.warmup, 3), 12, []
+        warm_min, warm_ms = max(args.warmup, 3), []
         def dev_allocs():
             a, f = C.c_int64(0), C.c_int64(0)
             L.gsb_alloc_counters(C.byref(a), C.byref(f))
             return a.value + f.value
         allocs_timed = 0
         while True:
-            timed = len(warm_ms) >= warm_min and (len(warm_ms) >= warm_max or
-                                                  abs(warm_ms[-1] - warm_ms[-2]) <= 0.1 * min(warm_ms[-2:]))
+            timed = e2e_warm_done(warm_ms, warm_min)
             if timed and len(per_step) >= steps_e2e:
                 break
             torch.cuda.synchronize()

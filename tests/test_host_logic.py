@@ -132,3 +132,27 @@ def test_bench_gpu_arm_fails_loudly_without_a_gpu(gsb):
         size, channels, check_every, kernel = 64, 3, 1, 0
     out = bench.time_to_tol_child(A)
     assert "error" in out and "NO_DEVICE" in out["error"]
+
+
+def test_e2e_warmup_rule():
+    """bench.py's e2e leg: at least three untimed steps, then timed as soon as two consecutive steps agree to 10 %, at
+    most twelve warm-up steps."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    done = bench.e2e_warm_done
+    assert not done([]) and not done([80.0, 80.0])
+    assert done([1700.0, 80.0, 81.0])              # settled by the third step
+    assert not done([1700.0, 80.0, 120.0])         # the last two differ by more than 10 %
+    assert done([1700.0, 80.0, 120.0, 118.0])
+    assert done([100.0 + 50 * i for i in range(12)])   # never settles: stop warming up after twelve
+    assert not done([100.0 + 50 * i for i in range(11)])
+    assert done([5.0, 5.0, 5.0, 5.0], warm_min=4) and not done([5.0, 5.0, 5.0], warm_min=4)
