@@ -153,6 +153,6 @@ def test_e2e_warmup_rule():
     assert done([1700.0, 80.0, 81.0])              # settled by the third step
     assert not done([1700.0, 80.0, 120.0])         # the last two differ by more than 10 %
     assert done([1700.0, 80.0, 120.0, 118.0])
-    assert done([100.0 + 50 * i for i in range(12)])   # never settles: stop warming up after twelve
-    assert not done([100.0 + 50 * i for i in range(11)])
+    assert done([100.0 * 1.5 ** i for i in range(12)])   # never settles: stop warming up after twelve
+    assert not done([100.0 * 1.5 ** i for i in range(11)])
     assert done([5.0, 5.0, 5.0, 5.0], warm_min=4) and not done([5.0, 5.0, 5.0], warm_min=4)
