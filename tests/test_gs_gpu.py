@@ -453,6 +453,32 @@ def test_small_system_persistent_kernel(gsb, oracle_mod):
         pg.gaussSeidel(bp, epsilon=0.0, max_iteration=4, options=K(6, check_every=2))
 
 
+@pytest.mark.parametrize("W,H", [(128, 100), (127, 129)])
+def test_small_cluster_two_passes_per_colour(gsb, W, H):
+    """Kernel 6 on a thread-block cluster when a colour has more rows than the cluster has threads (8 x 512): the
+    colour's phase then spans two passes that share one mbarrier phase.  1 to 4 right-hand sides (every instantiation
+    of gs_small_cluster), x bit for bit against kernel 1, also over a long run with the stop rule armed.  (The rule's
+    semantics on the cluster kernel are held by test_small_system_persistent_kernel.)"""
+    from coursecomputationalphotography_b200 import workloads as wl
+    K = lambda k, **kw: gsb.SparseMatrix.options(kernel=k, **kw)
+    sp = gsb.SparseMatrix(np.float64)
+    sp.poisson(W, H)
+    _, b3 = _poisson_rhs_for(gsb, wl, W, H, C=3)
+    b = np.concatenate([b3, b3[:1][:, ::-1]], axis=0)  # a fourth right-hand side
+    assert W * H <= 16384 and (W * H + 1) // 2 > 8 * 512
+    for k in (1, 2, 3, 4):
+        bb = np.ascontiguousarray(b[:k]) if k > 1 else np.ascontiguousarray(b[0])
+        x6 = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=7, options=K(6))
+        assert sp.last_stats.kernel_used == 6 and sp.last_stats.sweeps == 7
+        x1 = sp.gaussSeidel(bb, epsilon=0.0, max_iteration=7, options=K(1, use_graph=0))
+        assert np.array_equal(x6, x1), k
+    # a longer run with the stop rule armed: the same sweep count (the rule, or the cap) and the same bits
+    y6 = sp.gaussSeidel(b[0], epsilon=1e-1, max_iteration=300, options=K(6))
+    s6 = sp.last_stats.sweeps
+    y1 = sp.gaussSeidel(b[0], epsilon=1e-1, max_iteration=300, options=K(1, use_graph=0))
+    assert sp.last_stats.sweeps == s6 and np.array_equal(y6, y1)
+
+
 @pytest.mark.parametrize("W,H,nrhs", [(300, 217, 3), (1024, 512, 1), (1024, 512, 3), (2048, 1600, 3)])
 def test_fused_sweep_wavefront_bitwise(gsb, W, H, nrhs):
     """Kernel 5 (both colours in one launch, colour 1 trailing colour 0 by `lead` tiles and waiting on per-tile
